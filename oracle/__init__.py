@@ -1,0 +1,230 @@
+"""ctypes binding of the CPU oracle (oracle/stocs_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Imported by tests/, __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of
+bench.py.  The product package (model_matching_b200) never imports this module.
+PARITY UNPINNED: see the header of stocs_oracle.cpp.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_DIR, "liboracle.so")
+    src = os.path.join(_DIR, "stocs_oracle.cpp")
+    hdr = os.path.join(_DIR, "..", "model_matching_b200", "csrc", "stocs_math.h")
+    stale = (not os.path.exists(so)) or any(
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(so) for p in (src, hdr))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _DIR, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    L.orc_backproject.argtypes = [u16p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, C.c_float, f32p, C.c_void_p]
+    L.orc_ppf_compute.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, i32p]
+    L.orc_math_eval.argtypes = [C.c_int, f32p, f32p, C.c_int, f32p]
+    L.orc_philox.argtypes = [C.c_uint32] * 6 + [u32p]
+    L.orc_ppfmap_build.restype = C.c_void_p
+    L.orc_ppfmap_build.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int]
+    L.orc_ppfmap_free.argtypes = [C.c_void_p]
+    L.orc_ppfmap_num_keys.restype = C.c_longlong
+    L.orc_ppfmap_num_keys.argtypes = [C.c_void_p]
+    L.orc_ppfmap_num_entries.restype = C.c_longlong
+    L.orc_ppfmap_num_entries.argtypes = [C.c_void_p]
+    L.orc_ppfmap_lookup.restype = C.c_longlong
+    L.orc_ppfmap_lookup.argtypes = [C.c_void_p, i32p, i32p, C.c_longlong]
+    L.orc_ppfmap_keys.argtypes = [C.c_void_p, i32p]
+    L.orc_est_create.restype = C.c_void_p
+    L.orc_est_create.argtypes = [f32p, f32p, f32p, C.c_void_p, C.c_int, f32p, f32p, C.c_int,
+                                 C.c_void_p, C.c_float, C.c_int, C.c_int]
+    L.orc_est_free.argtypes = [C.c_void_p]
+    L.orc_est_centroids.argtypes = [C.c_void_p, f32p, f32p]
+    L.orc_est_centred.argtypes = [C.c_void_p, f32p, f32p]
+    L.orc_est_kd_query.argtypes = [C.c_void_p, f32p, C.c_int, C.c_float, i32p]
+    L.orc_est_kd_num_nodes.argtypes = [C.c_void_p]
+    L.orc_est_score.argtypes = [C.c_void_p, f32p, C.c_longlong, f32p, i32p, C.c_int]
+    L.orc_best.argtypes = [f32p, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
+    L.orc_est_sample_class_base.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, i32p, f32p,
+                                            C.POINTER(C.c_int)]
+    L.orc_est_current_prob.argtypes = [C.c_void_p, f32p]
+    L.orc_est_find_congruent.restype = C.c_longlong
+    L.orc_est_find_congruent.argtypes = [C.c_void_p, i32p, C.c_float, C.c_float, i32p,
+                                         C.c_longlong, i32p]
+    L.orc_est_fit.argtypes = [C.c_void_p, i32p, i32p, f32p, f32p]
+    L.orc_try_sampled_base.argtypes = [C.c_void_p, i32p, f32p, C.POINTER(C.c_int)]
+    _LIB = L
+    return L
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def backproject(depth, bgr, fx, cx, fy, cy, depth_scale):
+    H, W = depth.shape
+    xyz = np.empty((H * W, 3), np.float32)
+    rgb = np.empty(H * W, np.uint32)
+    d = np.ascontiguousarray(depth, np.uint16)
+    b = np.ascontiguousarray(bgr, np.uint8) if bgr is not None else None
+    lib().orc_backproject(d, b.ctypes.data if b is not None else None, W, H, fx, cx, fy, cy,
+                          depth_scale, xyz, rgb.ctypes.data)
+    return xyz, rgb
+
+
+def ppf_compute(p1, n1, p2, n2, tr=5, rot=5):
+    p1, n1, p2, n2 = map(_f32, (p1, n1, p2, n2))
+    n = p1.reshape(-1, 3).shape[0]
+    out = np.empty((n, 4), np.int32)
+    lib().orc_ppf_compute(p1, n1, p2, n2, n, tr, rot, out)
+    return out
+
+
+MATH_FN = {"acos": 0, "atan2": 1, "atan": 2, "sin": 3, "cos": 4, "log2": 5}
+
+
+def math_eval(fn, x, y=None):
+    x = _f32(x)
+    y = _f32(y) if y is not None else np.zeros_like(x)
+    out = np.empty_like(x)
+    lib().orc_math_eval(MATH_FN[fn], x, y, x.size, out)
+    return out
+
+
+def philox(ctr, key):
+    out = np.empty(4, np.uint32)
+    lib().orc_philox(*[int(c) for c in ctr], *[int(k) for k in key], out)
+    return out
+
+
+class PPFMap:
+    """The reference's fully expanded std::map (include/rgbd.hpp:23)."""
+
+    def __init__(self, mpos, mnrm, tr=5, rot=5):
+        self.mpos, self.mnrm = _f32(mpos), _f32(mnrm)
+        self.h = lib().orc_ppfmap_build(self.mpos, self.mnrm, self.mpos.shape[0], tr, rot)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_ppfmap_free(self.h)
+            self.h = None
+
+    @property
+    def num_keys(self):
+        return lib().orc_ppfmap_num_keys(self.h)
+
+    @property
+    def num_entries(self):
+        return lib().orc_ppfmap_num_entries(self.h)
+
+    def keys(self):
+        k = np.empty((self.num_keys, 4), np.int32)
+        lib().orc_ppfmap_keys(self.h, k)
+        return k
+
+    def lookup(self, key):
+        key = np.ascontiguousarray(key, np.int32)
+        n = lib().orc_ppfmap_lookup(self.h, key, np.empty((1, 2), np.int32), 0)
+        if n < 0:
+            return None
+        out = np.empty((n, 2), np.int32)
+        lib().orc_ppfmap_lookup(self.h, key, out, n)
+        return out
+
+
+class Estimator:
+    """Restatement of stocs::stocs_estimator's online methods (src/stocs.cpp)."""
+
+    def __init__(self, spos, snrm, scls, mpos, mnrm, ppfmap=None, spix=None,
+                 distance_threshold=0.005, tr=5, rot=5):
+        self.S, self.M = len(spos), len(mpos)
+        self._keep = (_f32(spos), _f32(snrm), _f32(scls), _f32(mpos), _f32(mnrm), ppfmap)
+        pix = np.ascontiguousarray(spix, np.int32) if spix is not None else None
+        self._pix = pix
+        self.h = lib().orc_est_create(self._keep[0], self._keep[1], self._keep[2],
+                                      pix.ctypes.data if pix is not None else None, self.S,
+                                      self._keep[3], self._keep[4], self.M,
+                                      ppfmap.h if ppfmap is not None else None,
+                                      distance_threshold, tr, rot)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_est_free(self.h)
+            self.h = None
+
+    def centroids(self):
+        a, b = np.empty(3, np.float32), np.empty(3, np.float32)
+        lib().orc_est_centroids(self.h, a, b)
+        return a, b
+
+    def centred(self):
+        s, m = np.empty((self.S, 3), np.float32), np.empty((self.M, 3), np.float32)
+        lib().orc_est_centred(self.h, s, m)
+        return s, m
+
+    def kd_query(self, q, sqdist):
+        q = _f32(q).reshape(-1, 3)
+        out = np.empty(q.shape[0], np.int32)
+        lib().orc_est_kd_query(self.h, q, q.shape[0], sqdist, out)
+        return out
+
+    def score(self, T, threads=1):
+        T = _f32(T).reshape(-1, 16)
+        H = T.shape[0]
+        lcp, inl = np.empty(H, np.float32), np.empty(H, np.int32)
+        lib().orc_est_score(self.h, T, H, lcp, inl, threads)
+        return lcp, inl
+
+    def sample_class_base(self, seed, base_no):
+        ids, inv, st = np.empty(4, np.int32), np.empty(2, np.float32), C.c_int(0)
+        ok = lib().orc_est_sample_class_base(self.h, seed, base_no, ids, inv, C.byref(st))
+        return bool(ok), ids, inv, st.value
+
+    def current_prob(self):
+        out = np.empty(self.S, np.float32)
+        lib().orc_est_current_prob(self.h, out)
+        return out
+
+    def find_congruent(self, base, inv1, inv2, cap=1 << 22):
+        base = np.ascontiguousarray(base, np.int32)
+        q = np.empty((cap, 4), np.int32)
+        npq = np.zeros(2, np.int32)
+        n = lib().orc_est_find_congruent(self.h, base, float(inv1), float(inv2), q, cap, npq)
+        assert n <= cap
+        return q[:n].copy(), int(npq[0]), int(npq[1])
+
+    def fit(self, base, quad):
+        base = np.ascontiguousarray(base, np.int32)
+        quad = np.ascontiguousarray(quad, np.int32)
+        Tc, Tw = np.empty(16, np.float32), np.empty(16, np.float32)
+        ok = lib().orc_est_fit(self.h, base, quad, Tc, Tw)
+        return bool(ok), Tc, Tw
+
+    def try_sampled_base(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32).copy()
+        inv, ok = np.empty(2, np.float32), C.c_int(0)
+        lib().orc_try_sampled_base(self.h, ids, inv, C.byref(ok))
+        return bool(ok.value), ids, inv
+
+
+def best(lcp):
+    lcp = _f32(lcp)
+    bi, bl = C.c_longlong(0), C.c_float(0)
+    lib().orc_best(lcp, lcp.size, C.byref(bi), C.byref(bl))
+    return bi.value, bl.value

@@ -1,0 +1,816 @@
+// stocs_oracle.cpp -- TEST INFRASTRUCTURE ONLY.  CPU restatement of the StoCS hot path of
+// kuwt/model_matching, used as the parity checker by tests/, __graft_entry__.smoke() and the
+// cpu_baseline / --impl reference legs of bench.py.  Nothing in the product
+// (model_matching_b200/, include/) links, imports or executes this file.
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or expected outputs
+// (SURVEY.md section 4), and it cannot be compiled here (Eigen, PCL, OpenCV-contrib and
+// Boost are absent), so this restatement is pinned only by (i) statement-by-statement citations
+// of the reference below, (ii) known-answer tests written by hand in tests/, and (iii)
+// independent brute-force cross checks (numpy / mpmath) of its leaf results.
+//
+// The leaf fp32 arithmetic (Eigen's published evaluation orders; float overloads of libm
+// replaced by fixed series) comes from model_matching_b200/csrc/stocs_math.h so that g++ and
+// nvcc agree bit for bit; the ALGORITHMS here are the reference's own (kd-tree NN, std::map
+// expanded PPF table, IndexedNormalSet 6-D grid, sequential loops), deliberately not the
+// GPU's (voxel grid, compact own-bin table, sorted buckets).
+//
+// Documented deviations from the reference (SURVEY.md section 8 "Quirks"):
+//   D1 (quirk 3)  degenerate bases/quads in ComputeRigidTransformation are rejected instead of
+//                 pushing an uninitialised matrix (src/stocs.cpp:299-310 returns kLargeNumber
+//                 from a bool function).
+//   D2 (quirk 8)  cos(alpha) is clamped to [-1,1] before acos (normalset.hpp:178 would produce
+//                 NaN and an undefined unsigned conversion).
+//   D3 (quirk 11) the categorical draw uses a counter-based Philox4x32-10 stream and an exact
+//                 fixed-point CDF instead of wall-clock-seeded minstd_rand0 + a double CDF
+//                 (src/stocs.cpp:133-148); the distribution is the same to 2^-40.
+//   D4            computeRotationScaling's SVD (src/stocs.cpp:931) is replaced by the linear part
+//                 itself (rot*scale == linear up to 1 ulp).
+//   D5            Quaternion::setFromTwoVectors' SVD branch for antiparallel vectors uses
+//                 normalized(v0 x v1) (or +x) as the axis; Eigen's sign there is unspecified.
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <set>
+#include <utility>
+#include <vector>
+
+#include "../model_matching_b200/csrc/stocs_math.h"
+
+#include <atomic>
+#include <thread>
+
+using stocsm::V3;
+using stocsm::v3;
+
+namespace orc {
+
+// ------------------------------------------------------------------------------------------
+// Kd-tree: include/super4pcs/accelerators/kdtree.h:355-370 (finalize), :522-538 (split),
+// :560-641 (createTree), :394-459 (doQueryRestrictedClosestIndex), bbox.h:65-96.
+struct KdNode {
+  // The reference packs these into a union; keeping them apart is behaviour-neutral.
+  float splitValue = 0.f;
+  unsigned firstChildId = 0;
+  unsigned dim = 0;
+  unsigned leaf = 0;
+  unsigned start = 0;
+  unsigned size = 0;
+};
+
+struct KdTree {
+  std::vector<V3> pts;
+  std::vector<int> idx;
+  std::vector<KdNode> nodes;
+
+  static float comp(const V3& v, unsigned d) { return d == 0 ? v.x : (d == 1 ? v.y : v.z); }
+
+  void build(const std::vector<V3>& points) {
+    pts = points;
+    idx.resize(points.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+    nodes.clear();
+    nodes.emplace_back();
+    nodes.back().leaf = 0;
+    create(0, 0, (unsigned)pts.size(), 1, 64, 32);
+  }
+
+  unsigned split(int start, int end, unsigned dim, float sv) {
+    int l = start, r = end - 1;
+    for (; l < r; ++l, --r) {
+      while (l < end && comp(pts[l], dim) < sv) l++;
+      while (r >= start && comp(pts[r], dim) >= sv) r--;
+      if (l > r) break;
+      std::swap(pts[l], pts[r]);
+      std::swap(idx[l], idx[r]);
+    }
+    if (l >= end) return (unsigned)end;  // reference would read one past the range here
+    return (comp(pts[l], dim) < sv ? l + 1 : l);
+  }
+
+  void create(unsigned nodeId, unsigned start, unsigned end, unsigned level, unsigned cell,
+              unsigned maxDepth) {
+    const float big = std::numeric_limits<float>::max() / 2;
+    V3 mn = v3(big, big, big), mx = v3(-big, -big, -big);
+    for (unsigned i = start; i < end; ++i) {
+      const V3& q = pts[i];
+      if (q.x < mn.x) mn.x = q.x;
+      if (q.y < mn.y) mn.y = q.y;
+      if (q.z < mn.z) mn.z = q.z;
+      if (q.x > mx.x) mx.x = q.x;
+      if (q.y > mx.y) mx.y = q.y;
+      if (q.z > mx.z) mx.z = q.z;
+    }
+    float dg[3] = {0.5f * (mx.x - mn.x), 0.5f * (mx.y - mn.y), 0.5f * (mx.z - mn.z)};
+    unsigned dim = 0;  // Eigen maxCoeff(&dim): first maximum wins
+    if (dg[1] > dg[dim]) dim = 1;
+    if (dg[2] > dg[dim]) dim = 2;
+    float mnd = comp(mn, dim), mxd = comp(mx, dim);
+    float sv = mnd + ((mxd - mnd) / 2.0f);  // AABB::center()
+    nodes[nodeId].dim = dim;
+    nodes[nodeId].splitValue = sv;
+    unsigned mid = split((int)start, (int)end, dim, sv);
+    unsigned first = (unsigned)nodes.size();
+    nodes[nodeId].firstChildId = first;
+    nodes.emplace_back();
+    nodes.emplace_back();
+    {
+      unsigned c = first;
+      if (mid - start <= cell || level >= maxDepth) {
+        nodes[c].leaf = 1; nodes[c].start = start; nodes[c].size = mid - start;
+      } else {
+        nodes[c].leaf = 0;
+        create(c, start, mid, level + 1, cell, maxDepth);
+      }
+    }
+    {
+      unsigned c = first + 1;
+      if (end - mid <= cell || level >= maxDepth) {
+        nodes[c].leaf = 1; nodes[c].start = mid; nodes[c].size = end - mid;
+      } else {
+        nodes[c].leaf = 0;
+        create(c, mid, end, level + 1, cell, maxDepth);
+      }
+    }
+  }
+
+  // kdtree.h:394-459.  Thread-safe variant (the reference keeps the stack in a member).
+  int query(const V3& q, float sqdist) const {
+    struct QN { unsigned nodeId; float sq; };
+    QN stack[64];
+    int cl_id = -1;
+    float cl_dist = sqdist;
+    stack[0].nodeId = 0; stack[0].sq = 0.f;
+    unsigned count = 1;
+    while (count) {
+      QN& qn = stack[count - 1];
+      const KdNode& node = nodes[qn.nodeId];
+      if (qn.sq < cl_dist) {
+        if (node.leaf) {
+          --count;
+          const int end = (int)(node.start + node.size);
+          for (int i = (int)node.start; i < end; ++i) {
+            const float d = stocsm::sqnorm(stocsm::sub(q, pts[i]));
+            if (d <= cl_dist) { cl_dist = d; cl_id = idx[i]; }
+          }
+        } else {
+          const float new_off = comp(q, node.dim) - node.splitValue;
+          if (new_off < 0.) {
+            stack[count].nodeId = node.firstChildId;
+            qn.nodeId = node.firstChildId + 1;
+          } else {
+            stack[count].nodeId = node.firstChildId + 1;
+            qn.nodeId = node.firstChildId;
+          }
+          stack[count].sq = qn.sq;
+          qn.sq = new_off * new_off;
+          ++count;
+        }
+      } else {
+        --count;
+      }
+    }
+    return cl_id;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// PPF map: include/rgbd.hpp:23, src/rgbd.cpp:123-154, src/stocs.cpp:62-78.
+using Key = std::array<int, 4>;
+using PPFMap = std::map<Key, std::vector<std::pair<int, int>>>;
+
+static void ppf_map_insert(PPFMap& m, const stocsm::Ppf4& f, float tr, float rot,
+                           std::pair<int, int> pr) {
+  for (int p1 = f.f[0] - tr; p1 < f.f[0] + tr; p1 += tr)
+    for (int p2 = f.f[1] - 2 * rot; p2 < f.f[1] + 2 * rot; p2 += rot)
+      for (int p3 = f.f[2] - 2 * rot; p3 < f.f[2] + 2 * rot; p3 += rot)
+        for (int p4 = f.f[3] - 2 * rot; p4 < f.f[3] + 2 * rot; p4 += rot) {
+          if (p1 <= 5 || p2 < 0 || p3 < 0 || p4 < 0) continue;
+          Key k = {p1, p2, p3, p4};
+          m[k].push_back(pr);
+        }
+}
+
+struct Model {
+  std::vector<V3> pos, nrm;
+};
+
+static void build_ppf_map(const Model& mdl, int tr, int rot, PPFMap& out) {
+  const int M = (int)mdl.pos.size();
+  for (int id1 = 0; id1 < M; ++id1)
+    for (int id2 = 0; id2 < M; ++id2) {
+      if (id1 == id2) continue;
+      stocsm::Ppf4 f = stocsm::ppf_compute(mdl.pos[id1], mdl.nrm[id1], mdl.pos[id2], mdl.nrm[id2],
+                                           tr, rot);
+      ppf_map_insert(out, f, (float)tr, (float)rot, std::make_pair(id1, id2));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// IndexedNormalSet<Vector3f,3,7,float>: normalset.h:86-122, normalset.hpp:116-131,168-214,
+// utils.h:139-148.
+struct NormalSet {
+  static constexpr int NG = 7;
+  float nepsilon;
+  float epsilon;
+  int egSize;
+  std::map<int, std::array<std::vector<unsigned>, 343>> grid;  // sparse stand-in for _grid
+
+  explicit NormalSet(float eps) {
+    nepsilon = (float)((double)(1.0f / 7.0f) + 0.00001);
+    const int gridDepth = (int)(-stocsm::log2_f(eps));
+    egSize = 1 << gridDepth;  // std::pow(2, gridDepth)
+    epsilon = 1.f / (float)egSize;
+  }
+  int indexPos(const V3& p) const {
+    V3 c = stocsm::divs(p, epsilon);
+    return (int)c.z * egSize * egSize + ((int)c.y * egSize + (int)c.x);
+  }
+  int indexNormal(const V3& n) const {
+    V3 c = v3((n.x / 2.0f + 0.5f) / nepsilon, (n.y / 2.0f + 0.5f) / nepsilon,
+              (n.z / 2.0f + 0.5f) / nepsilon);
+    return (int)c.z * NG * NG + ((int)c.y * NG + (int)c.x);
+  }
+  void addElement(const V3& p, const V3& n, unsigned id) {
+    const int pId = indexPos(p);
+    const int nId = indexNormal(n);
+    if (nId < 0 || nId >= 343) return;  // std::array::at would throw
+    grid[pId][nId].push_back(id);
+  }
+};
+
+struct Quat { V3 vec; float w; };
+
+// Eigen QuaternionBase::setFromTwoVectors (Eigen/src/Geometry/Quaternion.h) + deviation D5.
+static Quat quat_from_two_vectors(V3 a, V3 b) {
+  V3 v0 = stocsm::normalized(a), v1 = stocsm::normalized(b);
+  float c = stocsm::dot(v1, v0);
+  Quat q;
+  if (c < -1.0f + 1e-5f) {
+    c = c > -1.0f ? c : -1.0f;
+    V3 ax = stocsm::cross(v0, v1);
+    if (stocsm::sqnorm(ax) > 0.0f) ax = stocsm::normalized(ax); else ax = v3(1.f, 0.f, 0.f);
+    float w2 = (1.0f + c) * 0.5f;
+    q.w = sqrtf(w2);
+    q.vec = stocsm::scale(ax, sqrtf(1.0f - w2));
+    return q;
+  }
+  V3 axis = stocsm::cross(v0, v1);
+  float s = sqrtf((1.0f + c) * 2.0f);
+  float invs = 1.0f / s;
+  q.vec = stocsm::scale(axis, invs);
+  q.w = s * 0.5f;
+  return q;
+}
+// QuaternionBase::_transformVector
+static V3 quat_rotate(const Quat& q, V3 v) {
+  V3 uv = stocsm::cross(q.vec, v);
+  uv = stocsm::add(uv, uv);
+  return stocsm::add(stocsm::add(v, stocsm::scale(uv, q.w)), stocsm::cross(q.vec, uv));
+}
+
+// normalset.hpp:168-214 (tryReverse=false): the set of non-empty normal bins hit by the cone.
+static void cone_bins(const NormalSet& ns, const std::array<std::vector<unsigned>, 343>& g,
+                      V3 n, float cosAlphaIn, std::set<unsigned>& colored) {
+  float cosAlpha = cosAlphaIn;
+  if (cosAlpha > 1.0f) cosAlpha = 1.0f;   // D2
+  if (cosAlpha < -1.0f) cosAlpha = -1.0f;
+  const float alpha = stocsm::acos_f(cosAlpha);
+  const float perimeter = (float)((double)2.0f * stocsm::kPi * (double)stocsm::atan_f(alpha));
+  const unsigned nbSample = (unsigned)(2.0f * ceilf(perimeter * 7.0f / 2.0f));
+  const float angleStep = (float)((double)2.0f * stocsm::kPi / (double)(float)nbSample);
+  const float sinAlpha = stocsm::sin_f(alpha);
+  Quat q = quat_from_two_vectors(v3(0.f, 0.f, 1.f), n);
+  for (unsigned a = 0; a != nbSample; a++) {
+    float theta = (float)a * angleStep;
+    V3 d = stocsm::normalized(quat_rotate(
+        q, v3(sinAlpha * stocsm::cos_f(theta), sinAlpha * stocsm::sin_f(theta), cosAlpha)));
+    int id = ns.indexNormal(d);
+    if (id < 0 || id >= 343) continue;
+    if (!g[id].empty()) colored.insert((unsigned)id);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct Estimator {
+  // scene (centred in place by centroid_shift, src/stocs.cpp:943-964)
+  std::vector<V3> spos, snrm;
+  std::vector<float> scls, scur;
+  std::vector<int> srow, scol;
+  Model model;
+  V3 centroid_scene, centroid_model;
+  KdTree kd;
+  const PPFMap* map = nullptr;
+  float distance_threshold = 0.005f;
+  int tr_disc = 5, rot_disc = 5;
+
+  void centroid_shift() {
+    V3 cs = v3(0, 0, 0), cm = v3(0, 0, 0);
+    for (auto& p : spos) cs = stocsm::add(cs, p);
+    for (auto& p : model.pos) cm = stocsm::add(cm, p);
+    cs = stocsm::divs(cs, (float)spos.size());
+    cm = stocsm::divs(cm, (float)model.pos.size());
+    for (auto& p : spos) p = stocsm::sub(p, cs);
+    for (auto& p : model.pos) p = stocsm::sub(p, cm);
+    centroid_scene = cs; centroid_model = cm;
+  }
+
+  bool has_key(const stocsm::Ppf4& f) const {
+    Key k = {f.f[0], f.f[1], f.f[2], f.f[3]};
+    return map->find(k) != map->end();
+  }
+  stocsm::Ppf4 scene_ppf(int a, int b) const {
+    return stocsm::ppf_compute(spos[a], snrm[a], spos[b], snrm[b], tr_disc, rot_disc);
+  }
+
+  // src/stocs.cpp:133-148 with deviation D3.
+  int sample_point(uint64_t seed, uint32_t base_no, uint32_t draw_no) const {
+    uint64_t total = 0;
+    for (float p : scur) total += stocsm::prob_weight(p);
+    if (total == 0) return -1;
+    uint64_t r = stocsm::mulhi_u64(stocsm::draw_u64(seed, base_no, draw_no), total);
+    uint64_t acc = 0;
+    for (size_t i = 0; i < scur.size(); ++i) {
+      acc += stocsm::prob_weight(scur[i]);
+      if (acc > r) return (int)i;
+    }
+    return -1;
+  }
+
+  // src/stocs.cpp:155-222 (Scalar = double, VectorType = Vector3f)
+  static double segment_distance_and_invariants(V3 p1, V3 p2, V3 q1, V3 q2, double& inv1,
+                                                double& inv2) {
+    const double kSmall = 0.0001;
+    V3 u = stocsm::sub(p2, p1), v = stocsm::sub(q2, q1), w = stocsm::sub(p1, q1);
+    double a = stocsm::dot(u, u), b = stocsm::dot(u, v), c = stocsm::dot(v, v);
+    double d = stocsm::dot(u, w), e = stocsm::dot(v, w);
+    double f = a * c - b * b;
+    double s1 = 0.0, s2 = f, t1 = 0.0, t2 = f;
+    if (f < kSmall) {
+      s1 = 0.0; s2 = 1.0; t1 = e; t2 = c;
+    } else {
+      s1 = (b * e - c * d);
+      t1 = (a * e - b * d);
+      if (s1 < 0.0) { s1 = 0.0; t1 = e; t2 = c; }
+      else if (s1 > s2) { s1 = s2; t1 = e + b; t2 = c; }
+    }
+    if (t1 < 0.0) {
+      t1 = 0.0;
+      if (-d < 0.0) s1 = 0.0;
+      else if (-d > a) s1 = s2;
+      else { s1 = -d; s2 = a; }
+    } else if (t1 > t2) {
+      t1 = t2;
+      if ((-d + b) < 0.0) s1 = 0;
+      else if ((-d + b) > a) s1 = s2;
+      else { s1 = (-d + b); s2 = a; }
+    }
+    inv1 = (std::abs(s1) < kSmall ? 0.0 : s1 / s2);
+    inv2 = (std::abs(t1) < kSmall ? 0.0 : t1 / t2);
+    V3 r = stocsm::sub(stocsm::add(w, stocsm::scale(u, (float)inv1)), stocsm::scale(v, (float)inv2));
+    return (double)stocsm::norm(r);
+  }
+
+  // src/stocs.cpp:224-268
+  bool try_sampled_base(int ids[4], float& inv1, float& inv2) const {
+    float min_distance = std::numeric_limits<float>::max();
+    int best[4] = {-1, -1, -1, -1};
+    V3 b[4] = {spos[ids[0]], spos[ids[1]], spos[ids[2]], spos[ids[3]]};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        if (i == j) continue;
+        int k = 0; while (k == i || k == j) k++;
+        int l = 0; while (l == i || l == j || l == k) l++;
+        double li1, li2;
+        float sd = (float)segment_distance_and_invariants(b[i], b[j], b[k], b[l], li1, li2);
+        if (sd < min_distance) {
+          min_distance = sd;
+          best[0] = i; best[1] = j; best[2] = k; best[3] = l;
+          inv1 = (float)li1; inv2 = (float)li2;
+        }
+      }
+    if (best[0] < 0) return false;
+    int tmp[4] = {ids[0], ids[1], ids[2], ids[3]};
+    for (int t = 0; t < 4; ++t) ids[t] = tmp[best[t]];
+    return true;
+  }
+
+  // src/stocs.cpp:363-519 (class mode: previous_segment is all zero, so the prior reset is
+  // current = class probability for every point).
+  bool sample_class_base(uint64_t seed, uint32_t base_no, int ids[4], float& inv1, float& inv2,
+                         int* stage_out) {
+    const float plane_threshold = 0.015f, min_distance_base = 0.01f;
+    const float internal_angle_threshold = 30;
+    const int S = (int)spos.size();
+    if (stage_out) *stage_out = 0;
+    for (int i = 0; i < S; ++i) scur[i] = scls[i];
+
+    int b1 = sample_point(seed, base_no, 0);
+    if (b1 < 0 || scur[b1] == 0.0f) return false;
+    if (stage_out) *stage_out = 1;
+    for (int i = 0; i < S; ++i) {
+      stocsm::Ppf4 f = scene_ppf(b1, i);
+      if (!has_key(f) || i == b1) scur[i] = 0;
+    }
+    int b2 = sample_point(seed, base_no, 1);
+    if (b2 < 0 || scur[b2] == 0.0f) return false;
+    if (stage_out) *stage_out = 2;
+    V3 v_1 = stocsm::normalized(stocsm::sub(spos[b2], spos[b1]));
+    for (int i = 0; i < S; ++i) {
+      V3 v_2 = stocsm::normalized(stocsm::sub(spos[i], spos[b1]));
+      float int_angle = (float)stocsm::rad_to_deg_ref(stocsm::acos_f(stocsm::dot(v_1, v_2)));
+      float other = 180 - int_angle;
+      int_angle = (other < int_angle) ? other : int_angle;  // std::min(int_angle, 180-int_angle)
+      stocsm::Ppf4 f = scene_ppf(b2, i);
+      if (!has_key(f) || i == b2 || int_angle < internal_angle_threshold) scur[i] = 0;
+    }
+    int b3 = sample_point(seed, base_no, 2);
+    if (b3 < 0 || scur[b3] == 0.0f) return false;
+    if (stage_out) *stage_out = 3;
+    {
+      double x1 = spos[b1].x, y1 = spos[b1].y, z1 = spos[b1].z;
+      double x2 = spos[b2].x, y2 = spos[b2].y, z2 = spos[b2].z;
+      double x3 = spos[b3].x, y3 = spos[b3].y, z3 = spos[b3].z;
+      float denom = (-x3 * y2 * z1 + x2 * y3 * z1 + x3 * y1 * z2 - x1 * y3 * z2 -
+                     x2 * y1 * z3 + x1 * y2 * z3);
+      float A = 0, B = 0, C = 0;
+      if (denom != 0) {
+        A = (-y2 * z1 + y3 * z1 + y1 * z2 - y3 * z2 - y1 * z3 + y2 * z3) / denom;
+        B = (x2 * z1 - x3 * z1 - x1 * z2 + x3 * z2 + x1 * z3 - x2 * z3) / denom;
+        C = (-x2 * y1 + x3 * y1 + x1 * y2 - x3 * y2 - x1 * y3 + x2 * y3) / denom;
+      }
+      for (int i = 0; i < S; ++i) {
+        float planar_distance = 10000;
+        if (denom != 0)
+          planar_distance = std::abs(A * spos[i].x + B * spos[i].y + C * spos[i].z - 1.0);
+        stocsm::Ppf4 f = scene_ppf(b3, i);
+        if (planar_distance > plane_threshold ||
+            stocsm::norm(stocsm::sub(spos[i], spos[b1])) < min_distance_base ||
+            stocsm::norm(stocsm::sub(spos[i], spos[b2])) < min_distance_base ||
+            stocsm::norm(stocsm::sub(spos[i], spos[b3])) < min_distance_base ||
+            !has_key(f) || i == b3)
+          scur[i] = 0;
+      }
+    }
+    int b4 = sample_point(seed, base_no, 3);
+    if (b4 < 0 || scur[b4] == 0.0f) return false;
+    if (stage_out) *stage_out = 4;
+    ids[0] = b1; ids[1] = b2; ids[2] = b3; ids[3] = b4;
+    return try_sampled_base(ids, inv1, inv2);
+  }
+
+  // src/stocs.cpp:753-869 + pairCreationFunctor.h:96-143.
+  int find_congruent(const int base[4], float invariant1, float invariant2,
+                     std::vector<std::array<int, 4>>& quads, int* nP, int* nQ) const {
+    quads.clear();
+    const int M = (int)model.pos.size();
+    // synch3DContent
+    const float big = std::numeric_limits<float>::max() / 2;
+    V3 mn = v3(big, big, big), mx = v3(-big, -big, -big);
+    for (int i = 0; i < M; ++i) {
+      const V3& q = model.pos[i];
+      if (q.x < mn.x) mn.x = q.x; if (q.y < mn.y) mn.y = q.y; if (q.z < mn.z) mn.z = q.z;
+      if (q.x > mx.x) mx.x = q.x; if (q.y > mx.y) mx.y = q.y; if (q.z > mx.z) mx.z = q.z;
+    }
+    V3 ext = stocsm::sub(mx, mn);
+    V3 gcenter = stocsm::add(mn, stocsm::divs(ext, 2.0f));
+    float ratio = (float)std::max((double)ext.z + 0.001,
+                                  std::max((double)ext.y + 0.001, (double)ext.x + 0.001));
+    std::vector<V3> pts(M);
+    for (int i = 0; i < M; ++i) {
+      V3 d = stocsm::divs(stocsm::sub(model.pos[i], gcenter), ratio);
+      pts[i] = v3(d.x + 0.5f, d.y + 0.5f, d.z + 0.5f);
+    }
+    stocsm::Ppf4 f1 = scene_ppf(base[0], base[1]);
+    stocsm::Ppf4 f2 = scene_ppf(base[2], base[3]);
+    auto it1 = map->find(Key{f1.f[0], f1.f[1], f1.f[2], f1.f[3]});
+    auto it2 = map->find(Key{f2.f[0], f2.f[1], f2.f[2], f2.f[3]});
+    static const std::vector<std::pair<int, int>> empty;
+    const auto& P = (it1 != map->end()) ? it1->second : empty;
+    const auto& Q = (it2 != map->end()) ? it2->second : empty;
+    if (nP) *nP = (int)P.size();
+    if (nQ) *nQ = (int)Q.size();
+    if (P.empty() || Q.empty()) return 0;
+
+    const float alpha = stocsm::dot(
+        stocsm::normalized(stocsm::sub(spos[base[1]], spos[base[0]])),
+        stocsm::normalized(stocsm::sub(spos[base[3]], spos[base[2]])));
+    const float eps = distance_threshold / ratio;
+    NormalSet nset(eps);
+    for (size_t i = 0; i < P.size(); ++i) {
+      const V3 p1 = pts[P[i].first], p2 = pts[P[i].second];
+      const V3 d = stocsm::sub(p2, p1);
+      const V3 n = stocsm::normalized(d);
+      nset.addElement(stocsm::add(p1, stocsm::scale(d, invariant1)), n, (unsigned)i);
+    }
+    std::set<std::pair<unsigned, unsigned>> comb;
+    for (unsigned i = 0; i < Q.size(); ++i) {
+      const V3 p1 = pts[Q[i].first], p2 = pts[Q[i].second];
+      const V3 pq1 = model.pos[Q[i].first], pq2 = model.pos[Q[i].second];
+      const V3 query = stocsm::add(p1, stocsm::scale(stocsm::sub(p2, p1), invariant2));
+      const V3 queryQ = stocsm::add(pq1, stocsm::scale(stocsm::sub(pq2, pq1), invariant2));
+      const V3 queryn = stocsm::normalized(stocsm::sub(p2, p1));
+      auto git = nset.grid.find(nset.indexPos(query));
+      if (git == nset.grid.end()) continue;
+      std::set<unsigned> colored;
+      cone_bins(nset, git->second, queryn, alpha, colored);
+      for (unsigned nb : colored)
+        for (unsigned id : git->second[nb]) {
+          const V3 pp1 = model.pos[P[id].first], pp2 = model.pos[P[id].second];
+          const V3 invPoint = stocsm::add(pp1, stocsm::scale(stocsm::sub(pp2, pp1), invariant1));
+          if (stocsm::sqnorm(stocsm::sub(queryQ, invPoint)) <= distance_threshold)
+            comb.emplace(id, i);
+        }
+    }
+    for (auto& c : comb)
+      quads.push_back({P[c.first].first, P[c.first].second, Q[c.second].first, Q[c.second].second});
+    return (int)quads.size();
+  }
+
+  // src/stocs.cpp:270-361 + :871-941.  Tc = centred transform (all_transforms), Tw = un-centred
+  // pose (PoseCandidate::transform); both column-major.  Returns false when rejected.
+  bool fit(const int base[4], const int quad[4], float* Tc, float* Tw) const {
+    const V3 p0 = spos[base[0]], p1 = spos[base[1]], p2 = spos[base[2]];
+    const V3 q0 = model.pos[quad[0]], q1 = model.pos[quad[1]], q2 = model.pos[quad[2]];
+    const V3 c1 = stocsm::divs(stocsm::add(stocsm::add(p0, p1), p2), 3.0f);
+    const V3 c2 = stocsm::divs(stocsm::add(stocsm::add(q0, q1), q2), 3.0f);
+    V3 fp[3], fq[3];
+    if (!frame(p0, p1, p2, fp)) return false;  // D1
+    if (!frame(q0, q1, q2, fq)) return false;  // D1
+    // rotation = rotate_p.transpose() * rotate_q ; rows of rotate_* are the frame vectors
+    float R[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        R[i][j] = stocsm::sum3(c(fp[0], i) * c(fq[0], j), c(fp[1], i) * c(fq[1], j),
+                               c(fp[2], i) * c(fq[2], j));
+    for (int i = 0; i < 3; ++i) {
+      float rr = stocsm::sum3(R[i][0] * R[0][i], R[i][1] * R[1][i], R[i][2] * R[2][i]);
+      if (rr - 1.0f > 1e-6f) return false;
+      if (rr != rr) return false;  // NaN => rms_ NaN => "rms >= 0" fails (src/stocs.cpp:922)
+    }
+    const V3 nc2 = v3(-c2.x, -c2.y, -c2.z);
+    float t[3];
+    const float c1a[3] = {c1.x, c1.y, c1.z};
+    for (int i = 0; i < 3; ++i)
+      t[i] = c1a[i] + stocsm::sum3(R[i][0] * nc2.x, R[i][1] * nc2.y, R[i][2] * nc2.z);
+    for (int k = 0; k < 16; ++k) Tc[k] = 0.f, Tw[k] = 0.f;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) { Tc[j * 4 + i] = R[i][j]; Tw[j * 4 + i] = R[i][j]; }
+    Tc[12] = t[0]; Tc[13] = t[1]; Tc[14] = t[2]; Tc[15] = 1.f; Tw[15] = 1.f;
+    // un-centred translation (src/stocs.cpp:932, deviation D4)
+    const V3 a = stocsm::add(c1, centroid_scene);
+    const V3 b = stocsm::add(c2, centroid_model);
+    const float aa[3] = {a.x, a.y, a.z};
+    for (int i = 0; i < 3; ++i)
+      Tw[12 + i] = aa[i] - stocsm::sum3(R[i][0] * b.x, R[i][1] * b.y, R[i][2] * b.z);
+    return true;
+  }
+  static float c(const V3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+  static bool frame(V3 a0, V3 a1, V3 a2, V3 f[3]) {
+    V3 v1 = stocsm::sub(a1, a0);
+    if (stocsm::sqnorm(v1) == 0) return false;
+    v1 = stocsm::normalized(v1);
+    V3 d = stocsm::sub(a2, a0);
+    V3 v2 = stocsm::sub(d, stocsm::scale(v1, stocsm::dot(d, v1)));
+    if (stocsm::sqnorm(v2) == 0) return false;
+    v2 = stocsm::normalized(v2);
+    f[0] = v1; f[1] = v2; f[2] = stocsm::cross(v1, v2);
+    return true;
+  }
+
+  // src/stocs.cpp:1006-1041
+  float score(const float* T, int* inliers_out) const {
+    const float sq_eps = distance_threshold * distance_threshold;
+    float weighted = 0;
+    int inl = 0;
+    const int M = (int)model.pos.size();
+    for (int i = 0; i < M; ++i) {
+      V3 q = stocsm::xform_point(T, model.pos[i]);
+      int id = kd.query(q, sq_eps);
+      if (id != -1) {
+        V3 nq = stocsm::xform_dir(T, model.nrm[i]);
+        float angle = (float)stocsm::rad_to_deg_ref(stocsm::acos_f(stocsm::dot(snrm[id], nq)));
+        if (angle < 30) { weighted += scls[id]; inl++; }
+      }
+    }
+    if (inliers_out) *inliers_out = inl;
+    return weighted / (float)M;
+  }
+};
+
+}  // namespace orc
+
+// ============================================================================================
+// C interface for ctypes (tests/, bench.py cpu_baseline).
+extern "C" {
+
+int orc_abi_version() { return 1; }
+
+// Back-projection loop, src/rgbd.cpp:208-225.  rgb packed as 0x00RRGGBB from BGR input.
+void orc_backproject(const uint16_t* depth, const uint8_t* bgr, int W, int H, float fx, float cx,
+                     float fy, float cy, float depth_scale, float* xyz, uint32_t* rgb) {
+  for (int i = 0; i < H; i++)
+    for (int j = 0; j < W; j++) {
+      size_t k = (size_t)i * W + j;
+      float d = (float)depth[k] * depth_scale;
+      xyz[3 * k + 0] = (float)((j - cx) * d / fx);
+      xyz[3 * k + 1] = (float)((i - cy) * d / fy);
+      xyz[3 * k + 2] = d;
+      if (bgr && rgb)
+        rgb[k] = ((uint32_t)bgr[3 * k + 2] << 16 | (uint32_t)bgr[3 * k + 1] << 8 |
+                  (uint32_t)bgr[3 * k + 0]);
+    }
+}
+
+void orc_ppf_compute(const float* p1, const float* n1, const float* p2, const float* n2, int n,
+                     int tr, int rot, int* out4) {
+  for (int i = 0; i < n; ++i) {
+    stocsm::Ppf4 f = stocsm::ppf_compute(v3(p1[3 * i], p1[3 * i + 1], p1[3 * i + 2]),
+                                         v3(n1[3 * i], n1[3 * i + 1], n1[3 * i + 2]),
+                                         v3(p2[3 * i], p2[3 * i + 1], p2[3 * i + 2]),
+                                         v3(n2[3 * i], n2[3 * i + 1], n2[3 * i + 2]), tr, rot);
+    for (int k = 0; k < 4; ++k) out4[4 * i + k] = f.f[k];
+  }
+}
+
+// leaf math, for pinning against libm / mpmath in tests
+void orc_math_eval(int fn, const float* x, const float* y, int n, float* out) {
+  for (int i = 0; i < n; ++i) {
+    switch (fn) {
+      case 0: out[i] = stocsm::acos_f(x[i]); break;
+      case 1: out[i] = stocsm::atan2_f(y[i], x[i]); break;
+      case 2: out[i] = stocsm::atan_f(x[i]); break;
+      case 3: out[i] = stocsm::sin_f(x[i]); break;
+      case 4: out[i] = stocsm::cos_f(x[i]); break;
+      case 5: out[i] = stocsm::log2_f(x[i]); break;
+      default: out[i] = 0;
+    }
+  }
+}
+void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                uint32_t* out4) {
+  stocsm::Philox4 o = stocsm::philox4x32_10(c0, c1, c2, c3, k0, k1);
+  for (int i = 0; i < 4; ++i) out4[i] = o.v[i];
+}
+
+// ---- PPF map ----
+void* orc_ppfmap_build(const float* pos, const float* nrm, int M, int tr, int rot) {
+  orc::Model m;
+  for (int i = 0; i < M; ++i) {
+    m.pos.push_back(v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
+    m.nrm.push_back(v3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+  }
+  auto* map = new orc::PPFMap();
+  orc::build_ppf_map(m, tr, rot, *map);
+  return map;
+}
+void orc_ppfmap_free(void* h) { delete (orc::PPFMap*)h; }
+long long orc_ppfmap_num_keys(void* h) { return (long long)((orc::PPFMap*)h)->size(); }
+long long orc_ppfmap_num_entries(void* h) {
+  long long n = 0;
+  for (auto& kv : *(orc::PPFMap*)h) n += (long long)kv.second.size();
+  return n;
+}
+// returns list length; copies up to cap pairs
+long long orc_ppfmap_lookup(void* h, const int* key4, int* pairs2, long long cap) {
+  auto* m = (orc::PPFMap*)h;
+  auto it = m->find(orc::Key{key4[0], key4[1], key4[2], key4[3]});
+  if (it == m->end()) return -1;
+  long long n = (long long)it->second.size();
+  for (long long i = 0; i < n && i < cap; ++i) {
+    pairs2[2 * i] = it->second[i].first;
+    pairs2[2 * i + 1] = it->second[i].second;
+  }
+  return n;
+}
+void orc_ppfmap_keys(void* h, int* keys4) {
+  long long i = 0;
+  for (auto& kv : *(orc::PPFMap*)h) {
+    for (int k = 0; k < 4; ++k) keys4[4 * i + k] = kv.first[k];
+    ++i;
+  }
+}
+
+// ---- estimator ----
+void* orc_est_create(const float* spos, const float* snrm, const float* scls, const int* spix,
+                     int S, const float* mpos, const float* mnrm, int M, void* ppfmap,
+                     float distance_threshold, int tr, int rot) {
+  auto* e = new orc::Estimator();
+  for (int i = 0; i < S; ++i) {
+    e->spos.push_back(v3(spos[3 * i], spos[3 * i + 1], spos[3 * i + 2]));
+    e->snrm.push_back(v3(snrm[3 * i], snrm[3 * i + 1], snrm[3 * i + 2]));
+    e->scls.push_back(scls[i]);
+    e->scur.push_back(scls[i]);
+    e->srow.push_back(spix ? spix[2 * i] : 0);
+    e->scol.push_back(spix ? spix[2 * i + 1] : 0);
+  }
+  for (int i = 0; i < M; ++i) {
+    e->model.pos.push_back(v3(mpos[3 * i], mpos[3 * i + 1], mpos[3 * i + 2]));
+    e->model.nrm.push_back(v3(mnrm[3 * i], mnrm[3 * i + 1], mnrm[3 * i + 2]));
+  }
+  e->map = (const orc::PPFMap*)ppfmap;
+  e->distance_threshold = distance_threshold;
+  e->tr_disc = tr; e->rot_disc = rot;
+  e->centroid_shift();
+  e->kd.build(e->spos);
+  return e;
+}
+void orc_est_free(void* h) { delete (orc::Estimator*)h; }
+void orc_est_centroids(void* h, float* cs3, float* cm3) {
+  auto* e = (orc::Estimator*)h;
+  cs3[0] = e->centroid_scene.x; cs3[1] = e->centroid_scene.y; cs3[2] = e->centroid_scene.z;
+  cm3[0] = e->centroid_model.x; cm3[1] = e->centroid_model.y; cm3[2] = e->centroid_model.z;
+}
+void orc_est_centred(void* h, float* spos, float* mpos) {
+  auto* e = (orc::Estimator*)h;
+  if (spos) for (size_t i = 0; i < e->spos.size(); ++i) {
+    spos[3 * i] = e->spos[i].x; spos[3 * i + 1] = e->spos[i].y; spos[3 * i + 2] = e->spos[i].z;
+  }
+  if (mpos) for (size_t i = 0; i < e->model.pos.size(); ++i) {
+    mpos[3 * i] = e->model.pos[i].x; mpos[3 * i + 1] = e->model.pos[i].y;
+    mpos[3 * i + 2] = e->model.pos[i].z;
+  }
+}
+void orc_est_kd_query(void* h, const float* q, int n, float sqdist, int* out) {
+  auto* e = (orc::Estimator*)h;
+  for (int i = 0; i < n; ++i) out[i] = e->kd.query(v3(q[3 * i], q[3 * i + 1], q[3 * i + 2]), sqdist);
+}
+int orc_est_kd_num_nodes(void* h) { return (int)((orc::Estimator*)h)->kd.nodes.size(); }
+
+// T: H column-major 4x4 matrices.  threads<=1: the reference's single-threaded loop;
+// threads>1: std::thread pool over hypotheses (the "all host cores" CPU baseline).
+void orc_est_score(void* h, const float* T, long long H, float* lcp, int* inliers, int threads) {
+  auto* e = (orc::Estimator*)h;
+  if (threads > 1) {
+    std::atomic<long long> next(0);
+    auto work = [&]() {
+      for (;;) {
+        long long b = next.fetch_add(64);
+        if (b >= H) break;
+        long long en = std::min(H, b + 64);
+        for (long long i = b; i < en; ++i) {
+          int inl; lcp[i] = e->score(T + 16 * i, &inl);
+          if (inliers) inliers[i] = inl;
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+    return;
+  }
+  for (long long i = 0; i < H; ++i) {
+    int inl; lcp[i] = e->score(T + 16 * i, &inl);
+    if (inliers) inliers[i] = inl;
+  }
+}
+// src/stocs.cpp:982-1004: first strict maximum, -1 when every score is 0.
+void orc_best(const float* lcp, long long H, long long* best_index, float* best_lcp) {
+  float mx = 0; long long idx = -1;
+  for (long long i = 0; i < H; ++i) if (lcp[i] > mx) { mx = lcp[i]; idx = i; }
+  *best_index = idx; *best_lcp = mx;
+}
+
+int orc_est_sample_class_base(void* h, unsigned long long seed, unsigned base_no, int* ids4,
+                              float* inv2, int* stage) {
+  auto* e = (orc::Estimator*)h;
+  float i1 = 0, i2 = 0;
+  ids4[0] = ids4[1] = ids4[2] = ids4[3] = -1;
+  bool ok = e->sample_class_base(seed, base_no, ids4, i1, i2, stage);
+  inv2[0] = i1; inv2[1] = i2;
+  return ok ? 1 : 0;
+}
+// probabilities left after the last executed pass of the most recent sample call
+void orc_est_current_prob(void* h, float* out) {
+  auto* e = (orc::Estimator*)h;
+  memcpy(out, e->scur.data(), e->scur.size() * sizeof(float));
+}
+long long orc_est_find_congruent(void* h, const int* base4, float inv1, float inv2, int* quads4,
+                                 long long cap, int* nPQ) {
+  auto* e = (orc::Estimator*)h;
+  std::vector<std::array<int, 4>> q;
+  int nP = 0, nQ = 0;
+  e->find_congruent(base4, inv1, inv2, q, &nP, &nQ);
+  if (nPQ) { nPQ[0] = nP; nPQ[1] = nQ; }
+  for (size_t i = 0; i < q.size() && (long long)i < cap; ++i)
+    for (int k = 0; k < 4; ++k) quads4[4 * i + k] = q[i][k];
+  return (long long)q.size();
+}
+int orc_est_fit(void* h, const int* base4, const int* quad4, float* Tc16, float* Tw16) {
+  return ((orc::Estimator*)h)->fit(base4, quad4, Tc16, Tw16) ? 1 : 0;
+}
+void orc_try_sampled_base(void* h, int* ids4, float* inv2, int* ok) {
+  auto* e = (orc::Estimator*)h;
+  float a = 0, b = 0;
+  *ok = e->try_sampled_base(ids4, a, b) ? 1 : 0;
+  inv2[0] = a; inv2[1] = b;
+}
+
+}  // extern "C"
