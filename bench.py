@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- hypotheses scored / second on the synthetic S1 workload (BASELINE.json configs[3]).
+
+One "step" = one pass of the hot path over one batch: score H = 10^6 rigid-transform hypotheses
+(|M| = 512 model points each) against the 1,048,576-point scene, then the best-pose / top-K
+reduction (and, for N > 1, the single NCCL all-gather of the per-rank top-K records).
+Weak scaling: every rank holds a replica of the scene index and scores its own 10^6 hypotheses.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is produced.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SCENE = 1 << 20
+N_MODEL = 512
+H_PER_GPU = 1_000_000
+TOPK = 32
+METRIC = "hypotheses_scored_per_second"
+UNIT = "hypotheses/s"
+
+
+def algorithmic_bytes_per_hypothesis(M):
+    # 64 B per NN query (8 cell descriptors x 4 B + one 16 B candidate
+    # position + one 16 B attribute record) x |M| queries + 48 B transform in + 8 B results out.
+    return 56 + 64 * M
+
+
+def workload(rank, H):
+    from model_matching_b200 import synth
+    sc = synth.make_scene(n_points=N_SCENE, seed=1234)
+    mpos, mnrm = synth.make_model(N_MODEL)
+    T, _ = synth.make_hypotheses(H, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=4321 + rank)
+    return sc, mpos, mnrm, T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.gpu), "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(sc, mpos, mnrm, T, seconds_target=15.0):
+    """The CPU oracle (port of the reference's kd-tree LCP loop) on all host cores, bounded sample."""
+    import oracle
+    cores = os.cpu_count() or 1
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+    n0 = min(len(T), 2000 * cores)
+    t0 = time.perf_counter()
+    est.score(T[:n0], threads=cores)
+    dt = time.perf_counter() - t0
+    n = int(min(len(T), max(n0, n0 * seconds_target / max(dt, 1e-6))))
+    t0 = time.perf_counter()
+    lcp, inl = est.score(T[:n], threads=cores)
+    dt = time.perf_counter() - t0
+    return est, {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                 "sample": f"first {n} of the {len(T)} hypotheses of the same workload, {cores} threads, {dt:.1f} s"}, (lcp, inl, n)
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; the reference
+    itself cannot be compiled here: no Eigen/PCL/OpenCV/Boost) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    cores = os.cpu_count() or 1
+    sc, mpos, mnrm, T = workload(0, 200_000)
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+    n = 2500 * cores  # per step; sized so that steps+warmup end within a few minutes
+    for w in range(args.warmup):
+        est.score(T[:n // 4], threads=cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        off = (k * n) % (len(T) - n)
+        est.score(T[off:off + n], threads=cores)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "S1: 1,048,576-point synthetic scene, |M|=512, 1e6 hypotheses/GPU (1% near-truth)",
+                      "scene_points": N_SCENE, "model_points": N_MODEL, "hypotheses_per_gpu": H_PER_GPU},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{n} hypotheses per step ({args.steps} steps) of the S1 workload, {cores} threads"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hyp", type=int, default=H_PER_GPU, help="hypotheses per GPU (default: the named config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from model_matching_b200 import Context
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libstocs_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    H = args.hyp
+    warm = max(args.warmup, 3)
+
+    sc, mpos, mnrm, T = workload(rank, H)
+    ctx = Context(local)
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+
+    # a dedicated (non-default) stream: the C ABI treats a NULL stream as "the context's own"
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+    dT = torch.from_numpy(T).to(dev)
+    dlcp = torch.empty(H, dtype=torch.float32, device=dev)
+    dinl = torch.empty(H, dtype=torch.int32, device=dev)
+    dtop_i = torch.empty(TOPK, dtype=torch.int64, device=dev)
+    dtop_v = torch.empty(TOPK, dtype=torch.float32, device=dev)
+    gather_i = torch.empty(world * TOPK, dtype=torch.int64, device=dev) if world > 1 else None
+    gather_v = torch.empty(world * TOPK, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(ev=None):
+        if ev is not None:
+            ev[0].record(stream)
+        ctx.score_lcp_device(dT.data_ptr(), H, dlcp.data_ptr(), dinl.data_ptr(), sptr)
+        if ev is not None:
+            ev[1].record(stream)
+        ctx.reduce_best_device(dlcp.data_ptr(), H, TOPK, rank * H, dtop_i.data_ptr(), dtop_v.data_ptr(), sptr)
+        if world > 1:  # the path's one collective: all-gather of K (index, lcp) records per rank
+            dist.all_gather_into_tensor(gather_i, dtop_i)
+            dist.all_gather_into_tensor(gather_v, dtop_v)
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step(kev[k])
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, kernel_ms_max = float(t[0]), float(t[1])
+    value = world * H * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: the drop-in host-buffer call (pinned host memory in, results out), every step
+    hT = torch.from_numpy(T).pin_memory()
+    hlcp = torch.empty(H, dtype=torch.float32).pin_memory()
+    hinl = torch.empty(H, dtype=torch.int32).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_step():
+        ctx.score_lcp_ptr(hT.data_ptr(), H, hlcp.data_ptr(), hinl.data_ptr())
+        return ctx.reduce_best(None, K=TOPK)
+
+    e2e_step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        best = e2e_step()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * H * e2e_steps / float(te[0])
+
+    if rank == 0:
+        M = N_MODEL
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        alg_bytes = H * algorithmic_bytes_per_hypothesis(M)
+        achieved = alg_bytes / (kernel_ms_max * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "S1: 1,048,576-point synthetic scene, |M|=512, 1e6 hypotheses/GPU (1% near-truth)",
+                          "scene_points": N_SCENE, "model_points": M, "hypotheses_per_gpu": H,
+                          "parallelism": f"hypothesis-sharded x{world}, replicated scene index, one all-gather of top-{TOPK}",
+                          "l2": "inputs larger than L2 (64 MB transforms + ~%d MB scene index per step)" % int(
+                              (ctx.counters()[3] * 16 + ctx.counters()[2] * 4 + N_SCENE * 16) / 1e6)},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": H * 64, "d2h_bytes_per_step": H * 8,
+                       "steps": e2e_steps, "best_index": int(best[0]), "best_lcp": float(best[1])},
+               "gpu_launches": args.steps * 3,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                            "kernel": "score_lcp_kernel", "kernel_ms": kernel_ms_max,
+                            "algorithmic_bytes_per_launch": alg_bytes},
+               "clocks": clocks,
+               "ties_resolved_by_kdtree": int(ctx.counters()[1])}
+        if world == 1 and not args.no_cpu_baseline:
+            est, cb, (olcp, oinl, n) = cpu_baseline(sc, mpos, mnrm, T)
+            out["cpu_baseline"] = cb
+            # parity gate run with the measurement: the sample must match bit for bit
+            glcp, ginl = hlcp.numpy()[:n], hinl.numpy()[:n]
+            out["parity"] = {"checked": int(n), "inliers_equal": bool(np.array_equal(ginl, oinl)),
+                             "lcp_bits_equal": bool(np.array_equal(glcp.view(np.uint32), olcp.view(np.uint32)))}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+/* stocs_b200.h -- C ABI of libstocs_b200.so: the B200 (sm_100a) implementation of the
+ * data-parallel core of StoCS pose estimation (kuwt/model_matching, src/stocs.cpp).
+ *
+ * The reference has no FFI layer: its boundary is the C++ class stocs::stocs_estimator
+ * (include/stocs.hpp:16-180).  This header is what the drop-in shim of that class
+ * (model_matching_b200/host/stocs.hpp) binds; each entry point cites the reference code it
+ * replaces.  Conventions: plain pointers and sizes only; every function returns an int status
+ * (0 = ok, negative = error, text via stocs_b200_last_error); the caller owns every host buffer,
+ * the context owns every device buffer and stream; calls on one context must be serialised by
+ * the caller (the reference estimator is not thread-safe either); there
+ * is NO CPU fallback: without a usable sm_100 device stocs_b200_create fails.
+ *
+ * Matrices are 16 floats in column-major order (Eigen::Matrix4f memory layout,
+ * include/stocs.hpp:9).  Points are tightly packed xyz float triples.  Pixels are (row, col).
+ */
+#ifndef STOCS_B200_H_
+#define STOCS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct stocs_b200_ctx stocs_b200_ctx;
+
+enum {
+  STOCS_OK = 0,
+  STOCS_E_ARG = -1,        /* bad argument */
+  STOCS_E_CUDA = -2,       /* CUDA runtime error (see last_error) */
+  STOCS_E_STATE = -3,      /* call order violated (e.g. score before upload_scene) */
+  STOCS_E_NODEVICE = -4,   /* no sm_100 device / driver */
+  STOCS_E_CAPACITY = -5    /* caller-provided output capacity too small */
+};
+
+#define STOCS_B200_ABI_VERSION 1
+int stocs_b200_abi_version(void);
+
+/* One context per GPU (one process per GPU in multi-GPU runs).  device = CUDA ordinal. */
+int stocs_b200_create(stocs_b200_ctx** out, int device);
+void stocs_b200_destroy(stocs_b200_ctx* ctx);
+const char* stocs_b200_last_error(stocs_b200_ctx* ctx);
+
+/* Estimator parameters (constructor arguments of stocs::stocs_estimator, include/stocs.hpp:18-30;
+ * defaults = src/stocs_match_one_object.cpp:7-10). */
+int stocs_b200_set_params(stocs_b200_ctx* ctx, float distance_threshold, int ppf_tr_discretization,
+                          int ppf_rot_discretization);
+
+/* ---- a1: depth back-projection (src/rgbd.cpp:208-225) -------------------------------------
+ * depth: H*W uint16 row-major; bgr: H*W*3 uint8 (may be NULL); intrinsics order {fx,cx,fy,cy}
+ * as in src/stocs_match_one_object.cpp:20.  xyz_out: H*W*3 floats; rgb_out: H*W packed
+ * 0x00RRGGBB (may be NULL).  Every pixel is emitted, including depth 0. */
+int stocs_b200_backproject(stocs_b200_ctx* ctx, const uint16_t* depth, const uint8_t* bgr, int W,
+                           int H, float fx, float cx, float fy, float cy, float depth_scale,
+                           float* xyz_out, uint32_t* rgb_out);
+
+/* ---- a2/a11: model and scene upload --------------------------------------------------------
+ * upload_model replaces load_object_info's point part (src/stocs.cpp:86-97) and the model half of
+ * centroid_shift (src/stocs.cpp:951-962); it also builds the compact own-bin PPF table that
+ * replaces PPFMapType (include/rgbd.hpp:23; src/stocs.cpp:62-78; src/rgbd.cpp:123-154).
+ * upload_scene replaces the scene half of centroid_shift (src/stocs.cpp:948-960) and
+ * kdtree_initialize (src/stocs.cpp:966-980): the scene is centred with the reference's sequential
+ * fp32 centroid and indexed by a voxel grid (+ the reference kd-tree, used only to break exact
+ * distance ties the way kdtree.h:416-428 does).  pixel_rc may be NULL. */
+int stocs_b200_upload_model(stocs_b200_ctx* ctx, const float* pos3, const float* nrm3, int M);
+int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float* nrm3,
+                            const float* class_probability, const int32_t* pixel_rc, int S);
+int stocs_b200_get_centroids(stocs_b200_ctx* ctx, float* scene3, float* model3);
+/* centred point sets as the estimator holds them after centroid_shift (for visualize_best_pose,
+ * include/stocs.hpp:136-149).  Either pointer may be NULL. */
+int stocs_b200_get_centred(stocs_b200_ctx* ctx, float* scene_pos3, float* model_pos3);
+
+/* PPF table queries (replace ppf_map.find, src/stocs.cpp:403,780-786).
+ * ppf_lookup: number of pairs stored under key4 in the reference's expanded map, -1 if the key is
+ * absent; copies up to cap pairs (id1,id2) in the reference's list order. */
+int stocs_b200_ppf_num_pairs(stocs_b200_ctx* ctx, int64_t* own_bin_pairs, int64_t* own_bin_keys);
+int stocs_b200_ppf_lookup(stocs_b200_ctx* ctx, const int32_t* key4, int32_t* pairs2, int64_t cap,
+                          int64_t* count);
+
+/* ---- a5/a6/a8: probability-weighted base sampling, class mode (src/stocs.cpp:133-268,363-519)
+ * Samples n_bases bases numbered first_base_no.. with the counter-based stream keyed by seed.
+ * base_idx4: n_bases*4 scene indices (reordered by try_sampled_base); inv2: n_bases*2
+ * invariants; valid: n_bases flags (0 = the reference's "return false"). */
+int stocs_b200_sample_bases(stocs_b200_ctx* ctx, uint64_t seed, uint32_t first_base_no, int n_bases,
+                            int32_t* base_idx4, float* inv2, uint8_t* valid);
+
+/* ---- a9: congruent-set lookup (src/stocs.cpp:753-869) --------------------------------------
+ * For each of n_bases bases returns its quadrilaterals (4 model indices each) in the reference's
+ * std::set order; quad_offsets has n_bases+1 entries (CSR).  quads4 holds up to cap quads;
+ * returns STOCS_E_CAPACITY (with quad_offsets filled) when more are needed. */
+int stocs_b200_find_congruent(stocs_b200_ctx* ctx, int n_bases, const int32_t* base_idx4,
+                              const float* inv2, int32_t* quads4, int64_t cap,
+                              int64_t* quad_offsets);
+
+/* ---- a10: rigid transform per (base, quad) (src/stocs.cpp:270-361, 871-941) ----------------
+ * n items; base_idx4 and quads4 are n*4 each.  T_centred16 = all_transforms entry, T_world16 =
+ * PoseCandidate::transform; ok[i] = 0 when the reference would not push a transform. */
+int stocs_b200_fit_transforms(stocs_b200_ctx* ctx, int64_t n, const int32_t* base_idx4,
+                              const int32_t* quads4, float* T_centred16, float* T_world16,
+                              uint8_t* ok);
+
+/* ---- a12: LCP scoring (src/stocs.cpp:1006-1041 + kdtree.h:394-459) -------------------------
+ * Scores H centred transforms; lcp[i] is bit-identical to the reference's sequential fp32 sum,
+ * inliers[i] the number of model points passing both tests (may be NULL).  Host buffers. */
+int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float* lcp,
+                         int32_t* inliers);
+/* Same, all pointers are device pointers; runs on the context stream (or `stream` if non-NULL,
+ * a cudaStream_t) and does not synchronise.  */
+int stocs_b200_score_lcp_device(stocs_b200_ctx* ctx, const float* d_T16, int64_t H, float* d_lcp,
+                                int32_t* d_inliers, void* stream);
+
+/* ---- a13: best pose / top-K reduction (src/stocs.cpp:982-1004) -----------------------------
+ * Over the lcp array of the most recent score call (or an explicit device array for the _device
+ * variant): best = first strict maximum (index -1 and lcp 0 when all are 0); top-K ordered by
+ * (lcp desc, index asc).  topk arrays hold K entries (unused entries: index -1, lcp 0). */
+int stocs_b200_reduce_best(stocs_b200_ctx* ctx, const float* lcp, int64_t H, int K,
+                           int64_t* best_index, float* best_lcp, int64_t* topk_index,
+                           float* topk_lcp);
+int stocs_b200_reduce_best_device(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K,
+                                  int64_t index_offset, int64_t* d_topk_index, float* d_topk_lcp,
+                                  void* stream);
+
+/* ---- fused online pipeline (run_stocs_estimation, src/stocs_match_one_object.cpp:79-165) ----
+ * sample n_bases bases -> congruent sets -> at most max_sets transforms per base (the first
+ * max_sets quads in set order when a base has more; see DESIGN.md on quirk 5) -> score -> best.
+ * Everything stays on the device; only the summary comes back.  Outputs may be NULL. */
+typedef struct stocs_b200_pipeline_result {
+  int32_t n_valid_bases;
+  int64_t n_congruent_sets;
+  int64_t n_transforms;
+  int64_t best_index;        /* index into the transform list, -1 = no pose */
+  float best_lcp;
+  int32_t best_base;         /* PoseCandidate::base_index of the winner */
+  float best_T_centred[16];
+  float best_T_world[16];
+} stocs_b200_pipeline_result;
+int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets,
+                            stocs_b200_pipeline_result* result);
+
+/* ---- diagnostics ---------------------------------------------------------------------------
+ * counters of the most recent score call: [0] kernels launched, [1] NN queries resolved by the
+ * kd-tree tie path, [2] grid cells, [3] replicated candidate records. */
+int stocs_b200_get_counters(stocs_b200_ctx* ctx, int64_t* counters, int n);
+/* name + average duration (ms, CUDA events on the context stream) of the dominant kernel of the
+ * most recent score call; used by bench.py for the roofline line. */
+int stocs_b200_last_kernel_ms(stocs_b200_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STOCS_B200_H_ */

@@ -1,0 +1,254 @@
+"""ctypes binding of libstocs_b200.so (include/stocs_b200.h).
+
+The library is the product; this module only marshals numpy / torch buffers into it.  There is
+no CPU fallback: importing works without a GPU (so that the symbol table can be checked), but
+creating a Context without a B200 raises, and a missing .so raises at import of `lib()`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstocs_b200.so")
+_LIB = None
+
+# every symbol include/stocs_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "stocs_b200_abi_version", "stocs_b200_create", "stocs_b200_destroy", "stocs_b200_last_error",
+    "stocs_b200_set_params", "stocs_b200_backproject", "stocs_b200_upload_model",
+    "stocs_b200_upload_scene", "stocs_b200_get_centroids", "stocs_b200_get_centred",
+    "stocs_b200_ppf_num_pairs", "stocs_b200_ppf_lookup", "stocs_b200_sample_bases",
+    "stocs_b200_find_congruent", "stocs_b200_fit_transforms", "stocs_b200_score_lcp",
+    "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device",
+    "stocs_b200_run_pipeline", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
+]
+
+
+class StocsError(RuntimeError):
+    pass
+
+
+class PipelineResult(C.Structure):
+    _fields_ = [("n_valid_bases", C.c_int32), ("n_congruent_sets", C.c_int64),
+                ("n_transforms", C.c_int64), ("best_index", C.c_int64), ("best_lcp", C.c_float),
+                ("best_base", C.c_int32), ("best_T_centred", C.c_float * 16),
+                ("best_T_world", C.c_float * 16)]
+
+
+def lib():
+    """Load libstocs_b200.so; raise loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise StocsError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, u64, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_uint32
+    L.stocs_b200_abi_version.restype = i32
+    L.stocs_b200_create.argtypes = [C.POINTER(vp), i32]
+    L.stocs_b200_destroy.argtypes = [vp]
+    L.stocs_b200_destroy.restype = None
+    L.stocs_b200_last_error.argtypes = [vp]
+    L.stocs_b200_last_error.restype = C.c_char_p
+    L.stocs_b200_set_params.argtypes = [vp, f32, i32, i32]
+    L.stocs_b200_backproject.argtypes = [vp, vp, vp, i32, i32, f32, f32, f32, f32, f32, vp, vp]
+    L.stocs_b200_upload_model.argtypes = [vp, vp, vp, i32]
+    L.stocs_b200_upload_scene.argtypes = [vp, vp, vp, vp, vp, i32]
+    L.stocs_b200_get_centroids.argtypes = [vp, vp, vp]
+    L.stocs_b200_get_centred.argtypes = [vp, vp, vp]
+    L.stocs_b200_ppf_num_pairs.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.stocs_b200_ppf_lookup.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
+    L.stocs_b200_sample_bases.argtypes = [vp, u64, u32, i32, vp, vp, vp]
+    L.stocs_b200_find_congruent.argtypes = [vp, i32, vp, vp, vp, i64, vp]
+    L.stocs_b200_fit_transforms.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.stocs_b200_score_lcp.argtypes = [vp, vp, i64, vp, vp]
+    L.stocs_b200_score_lcp_device.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.stocs_b200_reduce_best.argtypes = [vp, vp, i64, i32, C.POINTER(i64), C.POINTER(f32), vp, vp]
+    L.stocs_b200_reduce_best_device.argtypes = [vp, vp, i64, i32, i64, vp, vp, vp]
+    L.stocs_b200_run_pipeline.argtypes = [vp, u64, i32, i32, C.POINTER(PipelineResult)]
+    L.stocs_b200_get_counters.argtypes = [vp, vp, i32]
+    L.stocs_b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+class Context:
+    """One stocs_b200_ctx (one GPU)."""
+
+    def __init__(self, device=0, distance_threshold=0.005, ppf_tr_discretization=5,
+                 ppf_rot_discretization=5):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.stocs_b200_create(C.byref(h), int(device))
+        if rc != 0:
+            msg = self._L.stocs_b200_last_error(None)
+            raise StocsError(f"stocs_b200_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.h = h
+        self.device = device
+        self._check(self._L.stocs_b200_set_params(self.h, distance_threshold, ppf_tr_discretization,
+                                                   ppf_rot_discretization))
+        self.M = self.S = 0
+        self._last_H = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.stocs_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.stocs_b200_last_error(self.h)
+            raise StocsError(f"libstocs_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    # ---- a1
+    def backproject(self, depth, bgr, fx, cx, fy, cy, depth_scale):
+        depth = np.ascontiguousarray(depth, np.uint16)
+        H, W = depth.shape
+        bgr = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        xyz = np.empty((H * W, 3), np.float32)
+        rgb = np.empty(H * W, np.uint32) if bgr is not None else None
+        self._check(self._L.stocs_b200_backproject(self.h, _ptr(depth), _ptr(bgr), W, H, fx, cx, fy, cy,
+                                                    depth_scale, _ptr(xyz), _ptr(rgb)))
+        return xyz, rgb
+
+    # ---- uploads
+    def upload_model(self, pos, nrm):
+        pos, nrm = _f32(pos, (-1, 3)), _f32(nrm, (-1, 3))
+        assert pos.shape == nrm.shape
+        self._check(self._L.stocs_b200_upload_model(self.h, _ptr(pos), _ptr(nrm), pos.shape[0]))
+        self.M = pos.shape[0]
+
+    def upload_scene(self, pos, nrm, cls, pix=None):
+        pos, nrm, cls = _f32(pos, (-1, 3)), _f32(nrm, (-1, 3)), _f32(cls, (-1,))
+        pix = None if pix is None else np.ascontiguousarray(pix, np.int32).reshape(-1, 2)
+        assert pos.shape == nrm.shape and cls.shape[0] == pos.shape[0]
+        self._check(self._L.stocs_b200_upload_scene(self.h, _ptr(pos), _ptr(nrm), _ptr(cls), _ptr(pix),
+                                                     pos.shape[0]))
+        self.S = pos.shape[0]
+
+    def centroids(self):
+        s, m = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self._check(self._L.stocs_b200_get_centroids(self.h, _ptr(s) if self.S else None,
+                                                      _ptr(m) if self.M else None))
+        return s, m
+
+    def centred(self):
+        s = np.empty((self.S, 3), np.float32) if self.S else None
+        m = np.empty((self.M, 3), np.float32) if self.M else None
+        self._check(self._L.stocs_b200_get_centred(self.h, _ptr(s), _ptr(m)))
+        return s, m
+
+    # ---- PPF table
+    def ppf_num_pairs(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.stocs_b200_ppf_num_pairs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def ppf_lookup(self, key):
+        key = np.ascontiguousarray(key, np.int32).reshape(4)
+        n = C.c_int64(0)
+        self._check(self._L.stocs_b200_ppf_lookup(self.h, _ptr(key), None, 0, C.byref(n)))
+        if n.value < 0:
+            return None
+        out = np.empty((max(n.value, 1), 2), np.int32)
+        self._check(self._L.stocs_b200_ppf_lookup(self.h, _ptr(key), _ptr(out), n.value, C.byref(n)))
+        return out[:n.value]
+
+    # ---- sampling / congruent sets / fit
+    def sample_bases(self, seed, first_base_no, n_bases):
+        ids = np.empty((n_bases, 4), np.int32)
+        inv = np.empty((n_bases, 2), np.float32)
+        valid = np.empty(n_bases, np.uint8)
+        self._check(self._L.stocs_b200_sample_bases(self.h, int(seed), int(first_base_no), n_bases,
+                                                     _ptr(ids), _ptr(inv), _ptr(valid)))
+        return ids, inv, valid.astype(bool)
+
+    def find_congruent(self, base_idx, inv, cap=1 << 20):
+        base_idx = np.ascontiguousarray(base_idx, np.int32).reshape(-1, 4)
+        inv = _f32(inv, (-1, 2))
+        nb = base_idx.shape[0]
+        offs = np.zeros(nb + 1, np.int64)
+        while True:
+            quads = np.empty((max(cap, 1), 4), np.int32)
+            rc = self._L.stocs_b200_find_congruent(self.h, nb, _ptr(base_idx), _ptr(inv), _ptr(quads), cap,
+                                                   _ptr(offs))
+            if rc == -5:  # STOCS_E_CAPACITY: offsets are filled, retry with the exact size
+                cap = int(offs[-1])
+                continue
+            self._check(rc)
+            return quads[:offs[-1]].copy(), offs
+
+    def fit_transforms(self, base_idx, quads):
+        base_idx = np.ascontiguousarray(base_idx, np.int32).reshape(-1, 4)
+        quads = np.ascontiguousarray(quads, np.int32).reshape(-1, 4)
+        n = quads.shape[0]
+        assert base_idx.shape[0] == n
+        Tc, Tw = np.empty((n, 16), np.float32), np.empty((n, 16), np.float32)
+        ok = np.empty(n, np.uint8)
+        self._check(self._L.stocs_b200_fit_transforms(self.h, n, _ptr(base_idx), _ptr(quads), _ptr(Tc),
+                                                       _ptr(Tw), _ptr(ok)))
+        return Tc, Tw, ok.astype(bool)
+
+    # ---- scoring
+    def score_lcp(self, T):
+        """Host buffers in, host buffers out (the drop-in call)."""
+        T = _f32(T, (-1, 16))
+        H = T.shape[0]
+        lcp, inl = np.empty(H, np.float32), np.empty(H, np.int32)
+        self._check(self._L.stocs_b200_score_lcp(self.h, _ptr(T), H, _ptr(lcp), _ptr(inl)))
+        self._last_H = H
+        return lcp, inl
+
+    def score_lcp_ptr(self, T_ptr, H, lcp_ptr, inl_ptr):
+        """Raw host pointers (e.g. pinned torch tensors)."""
+        self._check(self._L.stocs_b200_score_lcp(self.h, T_ptr, H, lcp_ptr, inl_ptr))
+        self._last_H = H
+
+    def score_lcp_device(self, dT_ptr, H, dlcp_ptr, dinl_ptr, stream=None):
+        self._check(self._L.stocs_b200_score_lcp_device(self.h, dT_ptr, H, dlcp_ptr, dinl_ptr, stream))
+
+    def reduce_best(self, lcp, K=32):
+        lcp = None if lcp is None else _f32(lcp, (-1,))
+        H = self._last_H if lcp is None else lcp.shape[0]
+        bi, bl = C.c_int64(0), C.c_float(0)
+        ti, tl = np.empty(K, np.int64), np.empty(K, np.float32)
+        self._check(self._L.stocs_b200_reduce_best(self.h, _ptr(lcp), H, K, C.byref(bi), C.byref(bl),
+                                                    _ptr(ti), _ptr(tl)))
+        return bi.value, bl.value, ti, tl
+
+    def reduce_best_device(self, dlcp_ptr, H, K, index_offset, didx_ptr, dval_ptr, stream=None):
+        self._check(self._L.stocs_b200_reduce_best_device(self.h, dlcp_ptr, H, K, index_offset, didx_ptr,
+                                                           dval_ptr, stream))
+
+    def run_pipeline(self, seed, n_bases=100, max_sets=200):
+        r = PipelineResult()
+        self._check(self._L.stocs_b200_run_pipeline(self.h, int(seed), n_bases, max_sets, C.byref(r)))
+        return r
+
+    def counters(self):
+        c = np.zeros(8, np.int64)
+        self._check(self._L.stocs_b200_get_counters(self.h, _ptr(c), 8))
+        return c
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        self._check(self._L.stocs_b200_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,332 @@
+// capi.cu -- the C ABI of libstocs_b200.so (include/stocs_b200.h): context, uploads, host-buffer
+// wrappers around the kernels.  No CPU fallback anywhere: every compute entry point launches
+// sm_100a kernels, and stocs_b200_create refuses to run without a compute-capability-10 device.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "stocs_ctx.h"
+
+int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
+                      int64_t* d_idx, float* d_val, cudaStream_t st);  // reduce.cu
+int stocs_build_ppf_table(stocs_b200_ctx* ctx);                         // ppf_table.cu
+
+// "acos(d)*180/pi < 30" (src/stocs.cpp:1028-1032) is monotone in d: find the smallest binary32 d
+// for which it holds by bisection over bit patterns, using the same math header as the oracle.
+float stocs_angle_threshold_dot() {
+  auto pred = [](float d) { return (float)stocsm::rad_to_deg_ref(stocsm::acos_f(d)) < 30.0f; };
+  uint32_t lo = stocsm::fbits(0.0f), hi = stocsm::fbits(1.0f);
+  while (hi - lo > 1) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (pred(stocsm::bitsf(mid))) hi = mid; else lo = mid;
+  }
+  return stocsm::bitsf(hi);
+}
+
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+int stocs_b200_abi_version(void) { return STOCS_B200_ABI_VERSION; }
+
+int stocs_b200_create(stocs_b200_ctx** out, int device) {
+  if (!out) return STOCS_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return STOCS_E_NODEVICE;
+  }
+  if (device < 0 || device >= ndev) { g_create_err = "bad device ordinal"; return STOCS_E_ARG; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return STOCS_E_CUDA;
+  if (prop.major != 10) {
+    g_create_err = "libstocs_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor);
+    return STOCS_E_NODEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return STOCS_E_CUDA;
+  stocs_b200_ctx* ctx = new (std::nothrow) stocs_b200_ctx();
+  if (!ctx) return STOCS_E_ARG;
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->chunk_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->chunk_ev[1], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { g_create_err = "stream/event creation failed"; delete ctx; return STOCS_E_CUDA; }
+  ctx->dot_thr = stocs_angle_threshold_dot();
+  if (ctx->d_small.ensure(4096) != cudaSuccess || cudaMemset(ctx->d_small.p, 0, 4096) != cudaSuccess) {
+    g_create_err = "device allocation failed";
+    stocs_b200_destroy(ctx);
+    return STOCS_E_CUDA;
+  }
+  if (!stocs_fmad_selftest(ctx)) {
+    g_create_err = "self-test failed: kernels were built with fused multiply-add contraction";
+    stocs_b200_destroy(ctx);
+    return STOCS_E_CUDA;
+  }
+  *out = ctx;
+  return STOCS_OK;
+}
+
+void stocs_b200_destroy(stocs_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->d_model, &ctx->d_mpos4, &ctx->d_mnrm4, &ctx->d_spos4, &ctx->d_sattr, &ctx->d_spix,
+                    &ctx->d_cell_start, &ctx->d_cand, &ctx->d_kd_nodes, &ctx->d_kd_pts, &ctx->d_ppf_bin_start,
+                    &ctx->d_ppf_pairs, &ctx->d_ppf_keybits, &ctx->d_T, &ctx->d_lcp, &ctx->d_inl, &ctx->d_work,
+                    &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_small};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 2; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* stocs_b200_last_error(stocs_b200_ctx* ctx) {
+  if (!ctx) return g_create_err.c_str();
+  return ctx->err.c_str();
+}
+
+int stocs_b200_set_params(stocs_b200_ctx* ctx, float distance_threshold, int tr, int rot) {
+  if (!ctx) return STOCS_E_ARG;
+  if (!(distance_threshold > 0.f) || tr <= 0 || rot <= 0) STOCS_FAIL(ctx, STOCS_E_ARG, "set_params: bad value");
+  if (ctx->S > 0 || ctx->M > 0) STOCS_FAIL(ctx, STOCS_E_STATE, "set_params must precede upload_model/upload_scene");
+  ctx->eps = distance_threshold;
+  ctx->tr = tr;
+  ctx->rot = rot;
+  return STOCS_OK;
+}
+
+int stocs_b200_backproject(stocs_b200_ctx* ctx, const uint16_t* depth, const uint8_t* bgr, int W, int H,
+                           float fx, float cx, float fy, float cy, float depth_scale, float* xyz_out,
+                           uint32_t* rgb_out) {
+  if (!ctx) return STOCS_E_ARG;
+  if (!depth || !xyz_out || W <= 0 || H <= 0) STOCS_FAIL(ctx, STOCS_E_ARG, "backproject: bad argument");
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)W * H;
+  const bool color = bgr && rgb_out;
+  // layout in d_tmp: depth (2n) | bgr (3n) ; d_tmp2: xyz (12n) | rgb (4n)
+  STOCS_CUDA(ctx, ctx->d_tmp.ensure(n * 2 + n * 3 + 64));
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure(n * 12 + n * 4));
+  uint16_t* d_depth = ctx->d_tmp.as<uint16_t>();
+  uint8_t* d_bgr = ctx->d_tmp.as<uint8_t>() + ((n * 2 + 15) / 16) * 16;
+  float* d_xyz = ctx->d_tmp2.as<float>();
+  uint32_t* d_rgb = (uint32_t*)(ctx->d_tmp2.as<char>() + n * 12);
+  cudaStream_t st = ctx->stream;
+  STOCS_CUDA(ctx, cudaMemcpyAsync(d_depth, depth, n * 2, cudaMemcpyHostToDevice, st));
+  if (color) STOCS_CUDA(ctx, cudaMemcpyAsync(d_bgr, bgr, n * 3, cudaMemcpyHostToDevice, st));
+  int rc = stocs_launch_backproject(ctx, d_depth, color ? d_bgr : nullptr, W, H, fx, cx, fy, cy, depth_scale,
+                                    d_xyz, color ? d_rgb : nullptr, st);
+  if (rc) return rc;
+  STOCS_CUDA(ctx, cudaMemcpyAsync(xyz_out, d_xyz, n * 12, cudaMemcpyDeviceToHost, st));
+  if (color) STOCS_CUDA(ctx, cudaMemcpyAsync(rgb_out, d_rgb, n * 4, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  return STOCS_OK;
+}
+
+int stocs_b200_upload_model(stocs_b200_ctx* ctx, const float* pos3, const float* nrm3, int M) {
+  if (!ctx) return STOCS_E_ARG;
+  if (!pos3 || !nrm3 || M <= 0) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_model: bad argument");
+  if (M > 6144) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_model: at most 6144 model points are supported");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  STOCS_CUDA(ctx, ctx->d_tmp.ensure((size_t)M * 12));
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)M * 12));
+  STOCS_CUDA(ctx, ctx->d_mpos4.ensure((size_t)M * 16));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp.p, pos3, (size_t)M * 12, cudaMemcpyHostToDevice, st));
+  int rc = stocs_centre_points(ctx, ctx->d_tmp.as<float>(), M, ctx->d_mpos4.as<float4>(), ctx->d_tmp2.as<float>(),
+                               ctx->cm, nullptr);
+  if (rc) return rc;
+  ctx->h_mpos.resize((size_t)M * 3);
+  ctx->h_mnrm.assign(nrm3, nrm3 + (size_t)M * 3);
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_mpos.data(), ctx->d_tmp2.p, (size_t)M * 12, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  const int Mpad = ((M + 31) / 32) * 32;
+  std::vector<float> soa((size_t)6 * Mpad, 0.f);
+  std::vector<float> n4((size_t)4 * M, 0.f);
+  for (int i = 0; i < M; ++i)
+    for (int k = 0; k < 3; ++k) {
+      soa[(size_t)k * Mpad + i] = ctx->h_mpos[3 * (size_t)i + k];
+      soa[(size_t)(3 + k) * Mpad + i] = nrm3[3 * (size_t)i + k];
+      n4[4 * (size_t)i + k] = nrm3[3 * (size_t)i + k];
+    }
+  STOCS_CUDA(ctx, ctx->d_model.ensure(soa.size() * 4));
+  STOCS_CUDA(ctx, ctx->d_mnrm4.ensure(n4.size() * 4));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_model.p, soa.data(), soa.size() * 4, cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_mnrm4.p, n4.data(), n4.size() * 4, cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->M = M;
+  ctx->Mpad = Mpad;
+  return stocs_build_ppf_table(ctx);
+}
+
+int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float* nrm3,
+                            const float* class_probability, const int32_t* pixel_rc, int S) {
+  if (!ctx) return STOCS_E_ARG;
+  if (!pos3 || !nrm3 || !class_probability || S <= 0) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_scene: bad argument");
+  if (S > (1 << 27)) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_scene: at most 2^27 scene points are supported");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  ctx->S = S;
+  // attributes: d_tmp = nrm3 | cls
+  STOCS_CUDA(ctx, ctx->d_tmp.ensure((size_t)S * 16));
+  float* d_n = ctx->d_tmp.as<float>();
+  float* d_c = d_n + (size_t)S * 3;
+  STOCS_CUDA(ctx, cudaMemcpyAsync(d_n, nrm3, (size_t)S * 12, cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(d_c, class_probability, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  int rc = stocs_pack_scene_attr(ctx, d_n, d_c, S);
+  if (rc) return rc;
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  STOCS_CUDA(ctx, ctx->d_spix.ensure((size_t)S * 8));
+  if (pixel_rc) STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_spix.p, pixel_rc, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  else STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_spix.p, 0, (size_t)S * 8, st));
+  // positions -> centre -> index
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp.p, pos3, (size_t)S * 12, cudaMemcpyHostToDevice, st));
+  rc = stocs_build_scene_index(ctx);
+  if (rc) { ctx->S = 0; return rc; }
+  return STOCS_OK;
+}
+
+int stocs_b200_get_centroids(stocs_b200_ctx* ctx, float* scene3, float* model3) {
+  if (!ctx) return STOCS_E_ARG;
+  if (scene3) { if (ctx->S <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "no scene"); memcpy(scene3, ctx->cs, 12); }
+  if (model3) { if (ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "no model"); memcpy(model3, ctx->cm, 12); }
+  return STOCS_OK;
+}
+
+int stocs_b200_get_centred(stocs_b200_ctx* ctx, float* scene_pos3, float* model_pos3) {
+  if (!ctx) return STOCS_E_ARG;
+  if (scene_pos3) {
+    if (ctx->S <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "no scene");
+    memcpy(scene_pos3, ctx->h_spos.data(), (size_t)ctx->S * 12);
+  }
+  if (model_pos3) {
+    if (ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "no model");
+    memcpy(model_pos3, ctx->h_mpos.data(), (size_t)ctx->M * 12);
+  }
+  return STOCS_OK;
+}
+
+int stocs_b200_score_lcp_device(stocs_b200_ctx* ctx, const float* d_T16, int64_t H, float* d_lcp,
+                                int32_t* d_inliers, void* stream) {
+  if (!ctx) return STOCS_E_ARG;
+  if (ctx->S <= 0 || ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "score_lcp: upload_model and upload_scene first");
+  if (H < 0 || (H > 0 && (!d_T16 || !d_lcp))) STOCS_FAIL(ctx, STOCS_E_ARG, "score_lcp: bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return stocs_launch_score(ctx, d_T16, H, d_lcp, d_inliers, st, true);
+}
+
+int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float* lcp, int32_t* inliers) {
+  if (!ctx) return STOCS_E_ARG;
+  if (ctx->S <= 0 || ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "score_lcp: upload_model and upload_scene first");
+  if (H < 0 || (H > 0 && (!T16 || !lcp))) STOCS_FAIL(ctx, STOCS_E_ARG, "score_lcp: bad argument");
+  if (H == 0) return STOCS_OK;
+  cudaSetDevice(ctx->device);
+  STOCS_CUDA(ctx, ctx->d_T.ensure((size_t)H * 64));
+  STOCS_CUDA(ctx, ctx->d_lcp.ensure((size_t)H * 4));
+  STOCS_CUDA(ctx, ctx->d_inl.ensure((size_t)H * 4));
+  // chunked: the H2D copy of chunk k+1 (copy stream) overlaps the scoring of chunk k
+  const int64_t chunk = 1 << 17;
+  int64_t nchunks = (H + chunk - 1) / chunk;
+  std::vector<cudaEvent_t> evs((size_t)nchunks, nullptr);
+  int rc = STOCS_OK;
+  for (int64_t c = 0; c < nchunks && rc == STOCS_OK; ++c) {
+    const int64_t off = c * chunk, n = (H - off < chunk) ? (H - off) : chunk;
+    cudaError_t e = cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_T.as<float>() + off * 16, T16 + off * 16, (size_t)n * 64,
+                                              cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(evs[c], ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, evs[c], 0);
+    if (e != cudaSuccess) { ctx->err = std::string("score_lcp copy: ") + cudaGetErrorString(e); rc = STOCS_E_CUDA; break; }
+    rc = stocs_launch_score(ctx, ctx->d_T.as<float>() + off * 16, n, ctx->d_lcp.as<float>() + off,
+                            ctx->d_inl.as<int32_t>() + off, ctx->stream, false);
+  }
+  if (rc == STOCS_OK) {
+    cudaError_t e = cudaMemcpyAsync(lcp, ctx->d_lcp.p, (size_t)H * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && inliers)
+      e = cudaMemcpyAsync(inliers, ctx->d_inl.p, (size_t)H * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("score_lcp: ") + cudaGetErrorString(e); rc = STOCS_E_CUDA; }
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+  }
+  for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+  ctx->last_H = H;
+  return rc;
+}
+
+int stocs_b200_reduce_best_device(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
+                                  int64_t* d_topk_index, float* d_topk_lcp, void* stream) {
+  if (!ctx) return STOCS_E_ARG;
+  if (!d_lcp || H < 0 || !d_topk_index || !d_topk_lcp) STOCS_FAIL(ctx, STOCS_E_ARG, "reduce_best: bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return stocs_launch_topk(ctx, d_lcp, H, K, index_offset, d_topk_index, d_topk_lcp, st);
+}
+
+int stocs_b200_reduce_best(stocs_b200_ctx* ctx, const float* lcp, int64_t H, int K, int64_t* best_index,
+                           float* best_lcp, int64_t* topk_index, float* topk_lcp) {
+  if (!ctx) return STOCS_E_ARG;
+  if (H < 0 || K < 1 || K > 32) STOCS_FAIL(ctx, STOCS_E_ARG, "reduce_best: bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const float* d_src = nullptr;
+  if (lcp) {
+    STOCS_CUDA(ctx, ctx->d_lcp.ensure((size_t)(H ? H : 1) * 4));
+    if (H) STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_lcp.p, lcp, (size_t)H * 4, cudaMemcpyHostToDevice, st));
+    d_src = ctx->d_lcp.as<float>();
+  } else {
+    if (ctx->last_H != H || !ctx->d_lcp.p) STOCS_FAIL(ctx, STOCS_E_STATE, "reduce_best: no resident lcp array of that size");
+    d_src = ctx->d_lcp.as<float>();
+  }
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure(32 * 12));
+  int64_t* d_idx = ctx->d_tmp2.as<int64_t>();
+  float* d_val = (float*)(d_idx + 32);
+  int rc = stocs_launch_topk(ctx, d_src, H, K, 0, d_idx, d_val, st);
+  if (rc) return rc;
+  int64_t hidx[32];
+  float hval[32];
+  STOCS_CUDA(ctx, cudaMemcpyAsync(hidx, d_idx, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(hval, d_val, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (best_index) *best_index = hidx[0];
+  if (best_lcp) *best_lcp = hval[0];
+  for (int k = 0; k < K; ++k) {
+    if (topk_index) topk_index[k] = hidx[k];
+    if (topk_lcp) topk_lcp[k] = hval[k];
+  }
+  return STOCS_OK;
+}
+
+int stocs_b200_get_counters(stocs_b200_ctx* ctx, int64_t* counters, int n) {
+  if (!ctx || !counters) return STOCS_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_small.p) {
+    unsigned long long t = 0;
+    STOCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    STOCS_CUDA(ctx, cudaMemcpy(&t, ctx->d_small.as<char>() + 200, 8, cudaMemcpyDeviceToHost));
+    ctx->counters[1] = (int64_t)t;
+  }
+  for (int i = 0; i < n && i < 8; ++i) counters[i] = ctx->counters[i];
+  return STOCS_OK;
+}
+
+int stocs_b200_last_kernel_ms(stocs_b200_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return STOCS_E_ARG;
+  if (!ctx->timing_valid) STOCS_FAIL(ctx, STOCS_E_STATE, "no timed launch");
+  cudaSetDevice(ctx->device);
+  STOCS_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  STOCS_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return STOCS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,398 @@
+// congruent.cu -- congruent-set extraction on the model for a batch of bases.
+//
+// Replaces stocs_estimator::find_congruent_sets_on_model (reference src/stocs.cpp:753-869) with
+// PairCreationFunctor::synch3DContent / getNormalizedEpsilon (pairCreationFunctor.h:96-143) and
+// IndexedNormalSet (accelerators/normalset.h:86-122, normalset.hpp:116-131,168-214,
+// utils.h:139-148).
+//
+// The reference inserts the P pairs into a 6-D grid (position cell x 7^3 normal bin) and, for
+// every Q pair, rasterises a cone of directions into normal bins of the query's own position
+// cell.  A (P,Q) combination is emitted iff
+//     cell(P) == cell(Q)  and  normal_bin(P) in cone_bins(Q)  and  |queryQ - invPoint|^2 <= thr
+// and the result is ordered by (rank of P in its list, rank of Q in its list).  That predicate
+// needs no grid at all: one thread computes (cell, normal bin, invPoint) per P entry, one thread
+// computes (cell, 343-bit cone mask, queryQ) per Q entry, and one warp per P entry sweeps its
+// base's Q list (cheap 4-byte cell compare first), counting, then writing in ballot order, which
+// is exactly the std::set order of the reference.
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
+
+#include <cfloat>
+#include <cmath>
+
+#include "ppf_device.cuh"
+#include "stocs_ctx.h"
+
+using namespace stocsm;
+
+PpfView stocs_ppf_view(const stocs_b200_ctx* ctx);
+
+namespace {
+
+struct ModelNorm {   // pairCreationFunctor.h:96-132 + normalset.h:114-122
+  float gx, gy, gz;  // bbox centre
+  float ratio;       // max extent + 0.001
+  float epsilon;     // 1 / egSize
+  float nepsilon;    // 1/7 + 1e-5
+  int egSize;
+};
+
+struct BaseInfo {
+  Ppf4 f1, f2;
+  float inv1, inv2, cos_alpha;
+  uint32_t nP, nQ;
+};
+
+__device__ __forceinline__ V3 ld3(const float4* p, int i) { const float4 v = p[i]; return v3(v.x, v.y, v.z); }
+
+// per base: PPF keys of the two base segments, alpha, list lengths
+__global__ void cong_count_kernel(const float4* __restrict__ spos4, const float4* __restrict__ sattr, PpfView v,
+                                  const int* __restrict__ base_idx4, const float* __restrict__ inv2, int n_bases,
+                                  BaseInfo* __restrict__ info) {
+  const int b = blockIdx.x;
+  const int j = threadIdx.x;  // 256 threads: 0..127 -> P bins, 128..255 -> Q bins
+  __shared__ BaseInfo s;
+  __shared__ uint32_t s_cnt[256];
+  if (j == 0) {
+    const int* id = base_idx4 + 4 * b;
+    const V3 p0 = ld3(spos4, id[0]), p1 = ld3(spos4, id[1]), p2 = ld3(spos4, id[2]), p3 = ld3(spos4, id[3]);
+    s.f1 = ppf_compute(p0, ld3(sattr, id[0]), p1, ld3(sattr, id[1]), v.tr, v.rot);
+    s.f2 = ppf_compute(p2, ld3(sattr, id[2]), p3, ld3(sattr, id[3]), v.tr, v.rot);
+    s.inv1 = inv2[2 * b]; s.inv2 = inv2[2 * b + 1];
+    s.cos_alpha = dot(normalized(sub(p1, p0)), normalized(sub(p3, p2)));
+  }
+  __syncthreads();
+  const Ppf4 f = (j < 128) ? s.f1 : s.f2;
+  uint32_t c = 0;
+  if (!(f.f[0] <= 5 || f.f[1] < 0 || f.f[2] < 0 || f.f[3] < 0)) {
+    const uint32_t bin = ppf_source_bin(v, f.f[0] / v.tr, f.f[1] / v.rot, f.f[2] / v.rot, f.f[3] / v.rot, j & 127);
+    if (bin != 0xffffffffu) c = v.bin_start[bin + 1] - v.bin_start[bin];
+  }
+  s_cnt[j] = c;
+  __syncthreads();
+  if (j == 0) {
+    uint32_t nP = 0, nQ = 0;
+    for (int k = 0; k < 128; ++k) { nP += s_cnt[k]; nQ += s_cnt[128 + k]; }
+    // src/stocs.cpp:788: either list empty => no congruent set
+    if (nP == 0 || nQ == 0) { nP = 0; nQ = 0; }
+    s.nP = nP; s.nQ = nQ;
+    info[b] = s;
+  }
+}
+
+// copy the source-bin ranges of both lists into the flat code buffer (unsorted)
+__global__ void cong_gather_kernel(PpfView v, const BaseInfo* __restrict__ info, const uint32_t* __restrict__ seg_off,
+                                   int n_bases, uint32_t* __restrict__ codes) {
+  const int b = blockIdx.x;
+  const int j = threadIdx.x;
+  __shared__ uint32_t s_start[256], s_cnt[256], s_off[256];
+  const BaseInfo bi = info[b];
+  if (bi.nP == 0) return;
+  const Ppf4 f = (j < 128) ? bi.f1 : bi.f2;
+  uint32_t st = 0, c = 0;
+  const uint32_t bin = ppf_source_bin(v, f.f[0] / v.tr, f.f[1] / v.rot, f.f[2] / v.rot, f.f[3] / v.rot, j & 127);
+  if (bin != 0xffffffffu) { st = v.bin_start[bin]; c = v.bin_start[bin + 1] - st; }
+  s_start[j] = st; s_cnt[j] = c;
+  __syncthreads();
+  if (j == 0 || j == 128) {
+    uint32_t acc = seg_off[(j == 0) ? b : (n_bases + b)];
+    for (int k = 0; k < 128; ++k) { s_off[j + k] = acc; acc += s_cnt[j + k]; }
+  }
+  __syncthreads();
+  for (int k = 0; k < 256; ++k)
+    for (uint32_t e = j; e < s_cnt[k]; e += 256) codes[s_off[k] + e] = v.pairs[s_start[k] + e];
+}
+
+__device__ __forceinline__ int index_normal(const ModelNorm& mn, V3 n) {
+  const float cx = (n.x / 2.0f + 0.5f) / mn.nepsilon, cy = (n.y / 2.0f + 0.5f) / mn.nepsilon,
+              cz = (n.z / 2.0f + 0.5f) / mn.nepsilon;
+  return (int)cz * 49 + ((int)cy * 7 + (int)cx);
+}
+__device__ __forceinline__ int index_pos(const ModelNorm& mn, V3 p) {
+  const V3 c = divs(p, mn.epsilon);
+  return (int)c.z * mn.egSize * mn.egSize + ((int)c.y * mn.egSize + (int)c.x);
+}
+__device__ __forceinline__ V3 to_unit(const ModelNorm& mn, V3 p) {
+  const V3 d = divs(sub(p, v3(mn.gx, mn.gy, mn.gz)), mn.ratio);
+  return v3(d.x + 0.5f, d.y + 0.5f, d.z + 0.5f);
+}
+
+struct PEntry { float ix, iy, iz; int cell; int nbin; };          // invPoint (model frame)
+struct QEntry { float qx, qy, qz; uint32_t mask[11]; };          // queryQ (model frame), cone bins
+
+// entry e of the flat (sorted) code buffer: P entries first, then Q entries
+__global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
+                                    const BaseInfo* __restrict__ info, int n_bases, uint32_t totalP, uint32_t total,
+                                    const float4* __restrict__ mpos4, ModelNorm mn, PEntry* __restrict__ pe,
+                                    QEntry* __restrict__ qe, int* __restrict__ qcell) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const bool isP = e < totalP;
+  // find the base (segment) by binary search in seg_off (2*n_bases+1 entries)
+  int lo = isP ? 0 : n_bases, hi = isP ? n_bases : 2 * n_bases;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (seg_off[mid] <= e) lo = mid; else hi = mid;
+  }
+  const int b = isP ? lo : lo - n_bases;
+  const BaseInfo bi = info[b];
+  const uint32_t code = codes[e];
+  const int i1 = (int)(code >> 16), i2 = (int)(code & 0xffffu);
+  const V3 w1 = ld3(mpos4, i1), w2 = ld3(mpos4, i2);
+  const V3 u1 = to_unit(mn, w1), u2 = to_unit(mn, w2);
+  const V3 du = sub(u2, u1);
+  const V3 dirn = normalized(du);
+  if (isP) {
+    PEntry o;
+    const V3 pos = add(u1, scale(du, bi.inv1));
+    o.cell = index_pos(mn, pos);
+    o.nbin = index_normal(mn, dirn);
+    const V3 ip = add(w1, scale(sub(w2, w1), bi.inv1));
+    o.ix = ip.x; o.iy = ip.y; o.iz = ip.z;
+    pe[e] = o;
+  } else {
+    QEntry o;
+    const V3 query = add(u1, scale(du, bi.inv2));
+    const V3 qq = add(w1, scale(sub(w2, w1), bi.inv2));
+    o.qx = qq.x; o.qy = qq.y; o.qz = qq.z;
+    for (int k = 0; k < 11; ++k) o.mask[k] = 0u;
+    // normalset.hpp:178-195 (cosAlpha clamped: deviation D2)
+    float cosAlpha = bi.cos_alpha;
+    if (cosAlpha > 1.0f) cosAlpha = 1.0f;
+    if (cosAlpha < -1.0f) cosAlpha = -1.0f;
+    const float alpha = acos_f(cosAlpha);
+    const float perimeter = (float)((double)2.0f * kPi * (double)atan_f(alpha));
+    const unsigned nbSample = (unsigned)(2.0f * ceilf(perimeter * 7.0f / 2.0f));
+    const float angleStep = (float)((double)2.0f * kPi / (double)(float)nbSample);
+    const float sinAlpha = sin_f(alpha);
+    // Quaternion::setFromTwoVectors((0,0,1), dirn)  (deviation D5 on the antiparallel branch)
+    const V3 v0 = v3(0.f, 0.f, 1.f);
+    const V3 v1 = normalized(dirn);
+    float c = dot(v1, v0);
+    V3 qv; float qw;
+    if (c < -1.0f + 1e-5f) {
+      c = c > -1.0f ? c : -1.0f;
+      V3 ax = cross(v0, v1);
+      if (sqnorm(ax) > 0.0f) ax = normalized(ax); else ax = v3(1.f, 0.f, 0.f);
+      const float w2q = (1.0f + c) * 0.5f;
+      qw = sqrtf(w2q);
+      qv = scale(ax, sqrtf(1.0f - w2q));
+    } else {
+      const V3 axis = cross(v0, v1);
+      const float s = sqrtf((1.0f + c) * 2.0f);
+      const float invs = 1.0f / s;
+      qv = scale(axis, invs);
+      qw = s * 0.5f;
+    }
+    for (unsigned a = 0; a != nbSample; a++) {
+      const float theta = (float)a * angleStep;
+      const V3 d0 = v3(sinAlpha * cos_f(theta), sinAlpha * sin_f(theta), cosAlpha);
+      V3 uv = cross(qv, d0);
+      uv = add(uv, uv);
+      const V3 rot = add(add(d0, scale(uv, qw)), cross(qv, uv));
+      const int id = index_normal(mn, normalized(rot));
+      if (id >= 0 && id < 343) o.mask[id >> 5] |= 1u << (id & 31);
+    }
+    qe[e - totalP] = o;
+    qcell[e - totalP] = index_pos(mn, query);
+  }
+}
+
+// one warp per P entry; WRITE=false counts, WRITE=true emits quads
+template <bool WRITE>
+__global__ void cong_match_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
+                                  int n_bases, uint32_t totalP, const PEntry* __restrict__ pe,
+                                  const QEntry* __restrict__ qe, const int* __restrict__ qcell, float thr,
+                                  uint32_t* __restrict__ counts, const uint32_t* __restrict__ out_off,
+                                  int* __restrict__ quads) {
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= totalP) return;
+  int lo = 0, hi = n_bases;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (seg_off[mid] <= wid) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const uint32_t q0 = seg_off[n_bases + b] - totalP, q1 = seg_off[n_bases + b + 1] - totalP;
+  const PEntry p = pe[wid];
+  const bool pvalid = p.nbin >= 0 && p.nbin < 343;  // std::array::at would throw otherwise
+  const uint32_t pcode = codes[wid];
+  uint32_t cnt = 0;
+  uint32_t wpos = WRITE ? out_off[wid] : 0;
+  for (uint32_t base = q0; base < q1; base += 32) {
+    const uint32_t i = base + lane;
+    bool m = false;
+    if (i < q1 && pvalid && qcell[i] == p.cell) {
+      const QEntry& q = qe[i];
+      if ((q.mask[p.nbin >> 5] >> (p.nbin & 31)) & 1u) {
+        const float dx = q.qx - p.ix, dy = q.qy - p.iy, dz = q.qz - p.iz;
+        m = (dx * dx + (dy * dy + dz * dz)) <= thr;  // squared distance vs UNSQUARED threshold (quirk 1)
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (WRITE) {
+      if (m) {
+        const uint32_t o = wpos + __popc(bal & ((1u << lane) - 1u));
+        const uint32_t qcode = codes[totalP + i];
+        quads[4 * (size_t)o + 0] = (int)(pcode >> 16);
+        quads[4 * (size_t)o + 1] = (int)(pcode & 0xffffu);
+        quads[4 * (size_t)o + 2] = (int)(qcode >> 16);
+        quads[4 * (size_t)o + 3] = (int)(qcode & 0xffffu);
+      }
+      wpos += __popc(bal);
+    } else {
+      cnt += __popc(bal);
+    }
+  }
+  if (!WRITE && lane == 0) counts[wid] = cnt;
+}
+
+__global__ void cong_base_offsets_kernel(const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ pscan,
+                                         int n_bases, uint32_t totalP, uint32_t total_quads,
+                                         long long* __restrict__ quad_off) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_bases) return;
+  const uint32_t e = (b < n_bases) ? seg_off[b] : totalP;
+  quad_off[b] = (e < totalP) ? (long long)pscan[e] : (long long)total_quads;
+}
+
+}  // namespace
+
+// Derives the unit-cube normalisation of the model (host scalars; exact IEEE ops, same as the
+// device would do) -- pairCreationFunctor.h:96-132, normalset.h:114-122.
+static ModelNorm model_norm(const stocs_b200_ctx* ctx) {
+  const float big = FLT_MAX / 2;
+  float mn[3] = {big, big, big}, mx[3] = {-big, -big, -big};
+  for (int i = 0; i < ctx->M; ++i)
+    for (int k = 0; k < 3; ++k) {
+      const float c = ctx->h_mpos[3 * (size_t)i + k];
+      if (c < mn[k]) mn[k] = c;
+      if (c > mx[k]) mx[k] = c;
+    }
+  ModelNorm m;
+  const float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+  m.gx = mn[0] + (ex / 2.0f); m.gy = mn[1] + (ey / 2.0f); m.gz = mn[2] + (ez / 2.0f);
+  const double r = std::max((double)ez + 0.001, std::max((double)ey + 0.001, (double)ex + 0.001));
+  m.ratio = (float)r;
+  const float eps = ctx->eps / m.ratio;
+  const int gridDepth = (int)(-stocsm::log2_f(eps));
+  m.egSize = 1 << (gridDepth < 0 ? 0 : (gridDepth > 10 ? 10 : gridDepth));
+  m.epsilon = 1.f / (float)m.egSize;
+  m.nepsilon = (float)((double)(1.0f / 7.0f) + 0.00001);
+  return m;
+}
+
+// Device-resident congruent-set search.  d_base_idx4 / d_inv2: n_bases entries on the device.
+// On return *d_quads_out points to ctx-owned device memory holding total quads (int4 each) and
+// h_quad_off (n_bases+1) is filled on the host.
+int stocs_congruent_device(stocs_b200_ctx* ctx, int n_bases, const int* d_base_idx4, const float* d_inv2,
+                           DevBuf& quads_buf, std::vector<long long>& h_quad_off, cudaStream_t st) {
+  h_quad_off.assign((size_t)n_bases + 1, 0);
+  if (n_bases == 0) return STOCS_OK;
+  const PpfView v = stocs_ppf_view(ctx);
+  DevBuf d_info, d_seg, d_codes_a, d_codes_b, d_tmp, d_pe, d_qe, d_qcell, d_cnt, d_scan, d_qoff;
+  auto cleanup = [&]() {
+    DevBuf* all[] = {&d_info, &d_seg, &d_codes_a, &d_codes_b, &d_tmp, &d_pe, &d_qe, &d_qcell, &d_cnt, &d_scan, &d_qoff};
+    for (DevBuf* b : all) b->release();
+  };
+#define CG(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
+  CG(d_info.ensure((size_t)n_bases * sizeof(BaseInfo)));
+  cong_count_kernel<<<n_bases, 256, 0, st>>>(ctx->d_spos4.as<float4>(), ctx->d_sattr.as<float4>(), v, d_base_idx4, d_inv2,
+                                             n_bases, d_info.as<BaseInfo>());
+  std::vector<BaseInfo> h_info((size_t)n_bases);
+  CG(cudaMemcpyAsync(h_info.data(), d_info.p, (size_t)n_bases * sizeof(BaseInfo), cudaMemcpyDeviceToHost, st));
+  CG(cudaStreamSynchronize(st));
+  // segment offsets: [P_0..P_{n-1} | Q_0..Q_{n-1}] (index bookkeeping only)
+  std::vector<uint32_t> seg((size_t)2 * n_bases + 1, 0);
+  uint64_t acc = 0;
+  for (int b = 0; b < n_bases; ++b) { seg[b] = (uint32_t)acc; acc += h_info[b].nP; }
+  const uint32_t totalP = (uint32_t)acc;
+  for (int b = 0; b < n_bases; ++b) { seg[n_bases + b] = (uint32_t)acc; acc += h_info[b].nQ; }
+  seg[2 * n_bases] = (uint32_t)acc;
+  if (acc >= (1ull << 31)) { ctx->err = "find_congruent: pair lists too long"; cleanup(); return STOCS_E_ARG; }
+  const uint32_t total = (uint32_t)acc;
+  if (totalP == 0) { cleanup(); return STOCS_OK; }
+  const uint32_t totalQ = total - totalP;
+  CG(d_seg.ensure(seg.size() * 4));
+  CG(cudaMemcpyAsync(d_seg.p, seg.data(), seg.size() * 4, cudaMemcpyHostToDevice, st));
+  CG(d_codes_a.ensure((size_t)total * 4));
+  CG(d_codes_b.ensure((size_t)total * 4));
+  cong_gather_kernel<<<n_bases, 256, 0, st>>>(v, d_info.as<BaseInfo>(), d_seg.as<uint32_t>(), n_bases, d_codes_a.as<uint32_t>());
+  // per-list sort by (id1, id2): the reference's list order (insertion order of the pair loop)
+  size_t tb = 0;
+  cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, d_codes_a.as<uint32_t>(), d_codes_b.as<uint32_t>(), (int)total,
+                                          2 * n_bases, d_seg.as<uint32_t>(), d_seg.as<uint32_t>() + 1, 0, 32, st);
+  CG(d_tmp.ensure(tb));
+  cub::DeviceSegmentedRadixSort::SortKeys(d_tmp.p, tb, d_codes_a.as<uint32_t>(), d_codes_b.as<uint32_t>(), (int)total,
+                                          2 * n_bases, d_seg.as<uint32_t>(), d_seg.as<uint32_t>() + 1, 0, 32, st);
+  const uint32_t* codes = d_codes_b.as<uint32_t>();
+  CG(d_pe.ensure((size_t)totalP * sizeof(PEntry)));
+  CG(d_qe.ensure((size_t)totalQ * sizeof(QEntry)));
+  CG(d_qcell.ensure((size_t)totalQ * 4));
+  const ModelNorm mn = model_norm(ctx);
+  cong_prepare_kernel<<<(total + 127) / 128, 128, 0, st>>>(codes, d_seg.as<uint32_t>(), d_info.as<BaseInfo>(), n_bases, totalP,
+                                                           total, ctx->d_mpos4.as<float4>(), mn, d_pe.as<PEntry>(),
+                                                           d_qe.as<QEntry>(), d_qcell.as<int>());
+  CG(d_cnt.ensure((size_t)(totalP + 1) * 4));
+  CG(d_scan.ensure((size_t)(totalP + 1) * 4));
+  CG(cudaMemsetAsync(d_cnt.p, 0, (size_t)(totalP + 1) * 4, st));
+  const unsigned mblocks = (unsigned)(((size_t)totalP * 32 + 255) / 256);
+  cong_match_kernel<false><<<mblocks, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, totalP, d_pe.as<PEntry>(),
+                                                    d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, d_cnt.as<uint32_t>(),
+                                                    nullptr, nullptr);
+  size_t tb2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(totalP + 1), st);
+  CG(d_tmp.ensure(tb2));
+  cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(totalP + 1), st);
+  uint32_t total_quads = 0;
+  CG(cudaMemcpyAsync(&total_quads, d_scan.as<uint32_t>() + totalP, 4, cudaMemcpyDeviceToHost, st));
+  CG(cudaStreamSynchronize(st));
+  CG(quads_buf.ensure((size_t)(total_quads ? total_quads : 1) * 16));
+  if (total_quads)
+    cong_match_kernel<true><<<mblocks, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, totalP, d_pe.as<PEntry>(),
+                                                     d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, nullptr,
+                                                     d_scan.as<uint32_t>(), quads_buf.as<int>());
+  CG(d_qoff.ensure((size_t)(n_bases + 1) * 8));
+  cong_base_offsets_kernel<<<(n_bases + 1 + 127) / 128, 128, 0, st>>>(d_seg.as<uint32_t>(), d_scan.as<uint32_t>(), n_bases,
+                                                                      totalP, total_quads, d_qoff.as<long long>());
+  CG(cudaMemcpyAsync(h_quad_off.data(), d_qoff.p, (size_t)(n_bases + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CG(cudaStreamSynchronize(st));
+  CG(cudaGetLastError());
+#undef CG
+  cleanup();
+  return STOCS_OK;
+}
+
+extern "C" int stocs_b200_find_congruent(stocs_b200_ctx* ctx, int n_bases, const int32_t* base_idx4, const float* inv2,
+                                         int32_t* quads4, int64_t cap, int64_t* quad_offsets) {
+  if (!ctx) return STOCS_E_ARG;
+  if (ctx->S <= 0 || ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "find_congruent: upload_model and upload_scene first");
+  if (n_bases < 0 || !quad_offsets || cap < 0 || (n_bases > 0 && (!base_idx4 || !inv2)))
+    STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: bad argument");
+  for (int i = 0; i < 4 * n_bases; ++i)
+    if (base_idx4[i] < 0 || base_idx4[i] >= ctx->S) STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: base index out of range");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)(n_bases ? n_bases : 1) * 24));
+  int* d_ids = ctx->d_tmp2.as<int>();
+  float* d_inv = (float*)(d_ids + 4 * (size_t)n_bases);
+  if (n_bases) {
+    STOCS_CUDA(ctx, cudaMemcpyAsync(d_ids, base_idx4, (size_t)n_bases * 16, cudaMemcpyHostToDevice, st));
+    STOCS_CUDA(ctx, cudaMemcpyAsync(d_inv, inv2, (size_t)n_bases * 8, cudaMemcpyHostToDevice, st));
+  }
+  DevBuf quads;
+  std::vector<long long> off;
+  int rc = stocs_congruent_device(ctx, n_bases, d_ids, d_inv, quads, off, st);
+  if (rc) { quads.release(); return rc; }
+  for (int b = 0; b <= n_bases; ++b) quad_offsets[b] = off[b];
+  const long long total = off[n_bases];
+  if (total > cap) { quads.release(); STOCS_FAIL(ctx, STOCS_E_CAPACITY, "find_congruent: quads4 capacity too small"); }
+  if (total > 0) {
+    if (!quads4) { quads.release(); STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: quads4 is NULL"); }
+    STOCS_CUDA(ctx, cudaMemcpyAsync(quads4, quads.p, (size_t)total * 16, cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  quads.release();
+  return STOCS_OK;
+}

@@ -1,0 +1,64 @@
+// ppf_device.cuh -- device view of the compact PPF table.
+//
+// The reference stores every ordered model pair under up to 2*4*4*4 = 128 keys of a std::map
+// (src/rgbd.cpp:123-154: keys {f1-tr, f1} x {f-2rot, f-rot, f, f+rot}^3, skipping p1 <= 5 and
+// negative angles).  Here every ordered pair is stored ONCE, under its own bin
+// (f1/tr, f2/rot, f3/rot, f4/rot), in a CSR sorted by (bin, id1, id2); a map lookup of key K
+// becomes the union of the <= 128 own bins whose expansion contains K:
+//   f1 in {K1, K1+tr},  f_j in {K_j - rot, K_j, K_j + rot, K_j + 2rot}.
+// Key existence (map.find != end, src/stocs.cpp:403-405) is a bitmap over the expanded keys.
+#pragma once
+#include <stdint.h>
+
+#include "stocs_math.h"
+
+struct PpfView {
+  const uint32_t* __restrict__ bin_start;  // [n1*na^3 + 1]
+  const uint32_t* __restrict__ pairs;      // (id1 << 16) | id2, sorted by (bin, id1, id2)
+  const uint32_t* __restrict__ keybits;    // [(n1+1)*(na+1)^3 bits]
+  int n1, na, tr, rot;
+};
+
+__device__ __forceinline__ bool ppf_key_exists(const PpfView& v, const stocsm::Ppf4& f) {
+  if (f.f[0] <= 5 || f.f[1] < 0 || f.f[2] < 0 || f.f[3] < 0) return false;
+  const int k1 = f.f[0] / v.tr, k2 = f.f[1] / v.rot, k3 = f.f[2] / v.rot, k4 = f.f[3] / v.rot;
+  const int nb = v.na + 1;
+  if (k1 > v.n1 || k2 >= nb || k3 >= nb || k4 >= nb) return false;
+  const uint32_t bit = (uint32_t)(((k1 * nb + k2) * nb + k3) * nb + k4);
+  return (__ldg(v.keybits + (bit >> 5)) >> (bit & 31)) & 1u;
+}
+
+// Enumerates the own bins whose expansion contains key f; calls fn(bin_index) for each valid one
+// (at most 128).  Returns false when the key cannot exist (p1 <= 5).
+template <class Fn>
+__device__ __forceinline__ bool ppf_for_each_source_bin(const PpfView& v, const stocsm::Ppf4& f, Fn fn) {
+  if (f.f[0] <= 5 || f.f[1] < 0 || f.f[2] < 0 || f.f[3] < 0) return false;
+  const int k1 = f.f[0] / v.tr, k2 = f.f[1] / v.rot, k3 = f.f[2] / v.rot, k4 = f.f[3] / v.rot;
+  for (int a = 0; a < 2; ++a) {
+    const int b1 = k1 + a;
+    if (b1 >= v.n1) continue;
+    for (int b = -1; b <= 2; ++b) {
+      const int b2 = k2 + b;
+      if (b2 < 0 || b2 >= v.na) continue;
+      for (int c = -1; c <= 2; ++c) {
+        const int b3 = k3 + c;
+        if (b3 < 0 || b3 >= v.na) continue;
+        for (int d = -1; d <= 2; ++d) {
+          const int b4 = k4 + d;
+          if (b4 < 0 || b4 >= v.na) continue;
+          fn((uint32_t)(((b1 * v.na + b2) * v.na + b3) * v.na + b4));
+        }
+      }
+    }
+  }
+  return true;
+}
+
+// The j-th (0..127) source bin of key (k1..k4), or 0xffffffff when out of range.
+__device__ __forceinline__ uint32_t ppf_source_bin(const PpfView& v, int k1, int k2, int k3, int k4, int j) {
+  const int b1 = k1 + (j >> 6), b2 = k2 + ((j >> 4) & 3) - 1, b3 = k3 + ((j >> 2) & 3) - 1, b4 = k4 + (j & 3) - 1;
+  if (b1 >= v.n1 || b2 < 0 || b2 >= v.na || b3 < 0 || b3 >= v.na || b4 < 0 || b4 >= v.na) return 0xffffffffu;
+  return (uint32_t)(((b1 * v.na + b2) * v.na + b3) * v.na + b4);
+}
+
+inline PpfView stocs_ppf_view(const struct stocs_b200_ctx* ctx);

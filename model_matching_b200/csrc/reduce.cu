@@ -1,0 +1,93 @@
+// reduce.cu -- best-pose argmax and top-K candidates over the LCP array.
+//
+// Replaces the argmax loop of stocs_estimator::compute_best_transform (reference
+// src/stocs.cpp:987-1001: FIRST strict maximum wins, index -1 when every score is 0) and produces
+// the K best candidates that feed clustering::greedy_clustering (src/pose_clustering.cpp:79-122).
+// Keys are (lcp bits << 32) | ~index, so a larger key is a larger score or, at equal score, a
+// smaller index.  Each warp keeps a sorted top-32 across its lanes (lane j = j-th best) and
+// inserts with one ballot + shuffle per surviving key; a single-warp kernel merges the per-warp
+// lists.  Memory traffic: one read of the LCP array.
+#include "stocs_ctx.h"
+
+namespace {
+
+__device__ __forceinline__ void warp_insert(unsigned long long& mine, unsigned long long key, int lane) {
+  // list is sorted descending across lanes; insert key, drop the smallest
+  const unsigned ge = __ballot_sync(0xffffffffu, mine >= key);  // lanes that stay in front of key
+  const int pos = __popc(ge);                                   // insertion position
+  const unsigned long long up = __shfl_up_sync(0xffffffffu, mine, 1);
+  if (lane == pos) mine = key;
+  else if (lane > pos) mine = up;
+}
+
+__device__ __forceinline__ unsigned long long make_key(float v, unsigned long long idx) {
+  return ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffull - (idx & 0xffffffffull));
+}
+
+__global__ void topk_partial_kernel(const float* __restrict__ lcp, long long H, unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long mine = 0ull;  // key 0 == "empty" (lcp 0 never qualifies: strict > 0)
+  for (long long base = warp * 32; base < H; base += nwarps * 32) {
+    const long long i = base + lane;
+    float v = (i < H) ? lcp[i] : 0.f;
+    unsigned long long key = (v > 0.f) ? make_key(v, (unsigned long long)i) : 0ull;
+    const unsigned long long kth = __shfl_sync(0xffffffffu, mine, 31);
+    unsigned pass = __ballot_sync(0xffffffffu, key > kth);
+    while (pass) {
+      const int b = __ffs(pass) - 1;
+      const unsigned long long k = __shfl_sync(0xffffffffu, key, b);
+      const unsigned long long cur_kth = __shfl_sync(0xffffffffu, mine, 31);
+      if (k > cur_kth) warp_insert(mine, k, lane);
+      pass &= pass - 1;
+    }
+  }
+  out[warp * 32 + lane] = mine;
+}
+
+__global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, long long n, int K,
+                                  long long index_offset, long long* __restrict__ out_idx,
+                                  float* __restrict__ out_lcp) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long mine = 0ull;
+  for (long long base = 0; base < n; base += 32) {
+    const long long i = base + lane;
+    unsigned long long key = (i < n) ? keys[i] : 0ull;
+    const unsigned long long kth = __shfl_sync(0xffffffffu, mine, 31);
+    unsigned pass = __ballot_sync(0xffffffffu, key > kth);
+    while (pass) {
+      const int b = __ffs(pass) - 1;
+      const unsigned long long k = __shfl_sync(0xffffffffu, key, b);
+      const unsigned long long cur_kth = __shfl_sync(0xffffffffu, mine, 31);
+      if (k > cur_kth) warp_insert(mine, k, lane);
+      pass &= pass - 1;
+    }
+  }
+  if (lane < K) {
+    if (mine == 0ull) { out_idx[lane] = -1; out_lcp[lane] = 0.f; }
+    else {
+      out_idx[lane] = (long long)(0xffffffffull - (mine & 0xffffffffull)) + index_offset;
+      out_lcp[lane] = __uint_as_float((unsigned)(mine >> 32));
+    }
+  }
+}
+
+}  // namespace
+
+int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
+                      int64_t* d_idx, float* d_val, cudaStream_t st) {
+  if (K < 1 || K > 32) STOCS_FAIL(ctx, STOCS_E_ARG, "reduce_best: K must be in 1..32");
+  if (H >= (1ll << 32)) STOCS_FAIL(ctx, STOCS_E_ARG, "reduce_best: H must be < 2^32");
+  int blocks = ctx->num_sms * 2;
+  long long need = (H + 255) / 256;
+  if (need < 1) need = 1;
+  if (blocks > need) blocks = (int)need;
+  const long long nwarps = (long long)blocks * 8;
+  STOCS_CUDA(ctx, ctx->d_work.ensure((size_t)nwarps * 32 * 8));
+  topk_partial_kernel<<<blocks, 256, 0, st>>>(d_lcp, H, ctx->d_work.as<unsigned long long>());
+  topk_merge_kernel<<<1, 32, 0, st>>>(ctx->d_work.as<unsigned long long>(), nwarps * 32, K, index_offset,
+                                      (long long*)d_idx, d_val);
+  STOCS_CUDA(ctx, cudaGetLastError());
+  return STOCS_OK;
+}

@@ -1,0 +1,267 @@
+// sample.cu -- probability-weighted 4-point base sampling, class mode.
+//
+// Replaces stocs_estimator::sample_class_base (reference src/stocs.cpp:363-519),
+// sample_point_from_distribution (:133-148), try_sampled_base (:224-268) and
+// segment_distance_and_invariants (:155-222).  One CTA (32 warps) per base, bases are
+// independent in class mode.  Each of the four draws is an exact categorical draw over
+// fixed-point weights floor(p * 2^40): integer sums are associative, so the block-parallel
+// reduction + the selected warp's scan pick exactly the index a sequential CDF walk picks
+// (documented deviation D3: counter-based Philox stream instead of a wall-clock seed).
+// Between draws one pass over the scene zeroes candidates by the reference's predicates
+// (PPF key present in the model map, internal angle >= 30 deg, coplanarity <= 0.015,
+// >= 0.01 m from the chosen points); survivors are kept as one bit per point.
+#include "ppf_device.cuh"
+#include "stocs_ctx.h"
+
+using namespace stocsm;
+
+namespace {
+
+struct SampleArgs {
+  const float4* __restrict__ spos4;
+  const float4* __restrict__ sattr;
+  int S;
+  PpfView ppf;
+  unsigned long long seed;
+  uint32_t first_base;
+  uint32_t* alive;  // n_bases * words
+  int words;
+  int* out_ids;
+  float* out_inv;
+  uint8_t* out_valid;
+};
+
+__device__ double seg_dist_inv(V3 p1, V3 p2, V3 q1, V3 q2, double& inv1, double& inv2) {
+  const double kSmall = 0.0001;
+  const V3 u = sub(p2, p1), v = sub(q2, q1), w = sub(p1, q1);
+  const double a = dot(u, u), b = dot(u, v), c = dot(v, v), d = dot(u, w), e = dot(v, w);
+  const double f = a * c - b * b;
+  double s1 = 0.0, s2 = f, t1 = 0.0, t2 = f;
+  if (f < kSmall) {
+    s1 = 0.0; s2 = 1.0; t1 = e; t2 = c;
+  } else {
+    s1 = (b * e - c * d);
+    t1 = (a * e - b * d);
+    if (s1 < 0.0) { s1 = 0.0; t1 = e; t2 = c; }
+    else if (s1 > s2) { s1 = s2; t1 = e + b; t2 = c; }
+  }
+  if (t1 < 0.0) {
+    t1 = 0.0;
+    if (-d < 0.0) s1 = 0.0;
+    else if (-d > a) s1 = s2;
+    else { s1 = -d; s2 = a; }
+  } else if (t1 > t2) {
+    t1 = t2;
+    if ((-d + b) < 0.0) s1 = 0;
+    else if ((-d + b) > a) s1 = s2;
+    else { s1 = (-d + b); s2 = a; }
+  }
+  inv1 = (fabs(s1) < kSmall ? 0.0 : s1 / s2);
+  inv2 = (fabs(t1) < kSmall ? 0.0 : t1 / t2);
+  const V3 r = sub(add(w, scale(u, (float)inv1)), scale(v, (float)inv2));
+  return (double)norm(r);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(1024) sample_bases_kernel(SampleArgs a) {
+  const int base = blockIdx.x;
+  const uint32_t base_no = a.first_base + (uint32_t)base;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  uint32_t* alive = a.alive + (size_t)base * a.words;
+  const int tiles = a.words;
+  const int tpw = (tiles + 31) / 32;
+  const int t0 = w * tpw, t1 = min(tiles, t0 + tpw);
+  __shared__ unsigned long long s_wsum[32];
+  __shared__ unsigned long long s_rem;
+  __shared__ int s_b[4];
+  __shared__ int s_pw;
+
+  V3 pb[3], nb[3];
+  V3 v_1 = v3(0, 0, 0);
+  float pA = 0, pB = 0, pC = 0, denom = 0;
+  const float plane_threshold = 0.015f, min_distance_base = 0.01f, internal_angle_threshold = 30.0f;
+
+  for (int stage = 0; stage < 4; ++stage) {
+    if (stage >= 1) {
+      const float4 p = a.spos4[s_b[stage - 1]], n = a.sattr[s_b[stage - 1]];
+      pb[stage - 1] = v3(p.x, p.y, p.z);
+      nb[stage - 1] = v3(n.x, n.y, n.z);
+    }
+    if (stage == 2) v_1 = normalized(sub(pb[1], pb[0]));
+    if (stage == 3) {
+      const double x1 = pb[0].x, y1 = pb[0].y, z1 = pb[0].z;
+      const double x2 = pb[1].x, y2 = pb[1].y, z2 = pb[1].z;
+      const double x3 = pb[2].x, y3 = pb[2].y, z3 = pb[2].z;
+      denom = (float)(-x3 * y2 * z1 + x2 * y3 * z1 + x3 * y1 * z2 - x1 * y3 * z2 - x2 * y1 * z3 + x1 * y2 * z3);
+      if (denom != 0) {
+        pA = (float)((-y2 * z1 + y3 * z1 + y1 * z2 - y3 * z2 - y1 * z3 + y2 * z3) / denom);
+        pB = (float)((x2 * z1 - x3 * z1 - x1 * z2 + x3 * z2 + x1 * z3 - x2 * z3) / denom);
+        pC = (float)((-x2 * y1 + x3 * y1 + x1 * y2 - x3 * y2 - x1 * y3 + x2 * y3) / denom);
+      }
+    }
+    unsigned long long lsum = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int i = t * 32 + lane;
+      bool al = false;
+      float cls = 0.f;
+      if (i < a.S) {
+        if (stage == 0) {
+          al = true;
+          cls = a.sattr[i].w;
+        } else if ((alive[t] >> lane) & 1u) {
+          const float4 p4 = a.spos4[i], n4 = a.sattr[i];
+          const V3 p = v3(p4.x, p4.y, p4.z), n = v3(n4.x, n4.y, n4.z);
+          cls = n4.w;
+          const int bsel = s_b[stage - 1];
+          const Ppf4 f = ppf_compute(pb[stage - 1], nb[stage - 1], p, n, a.ppf.tr, a.ppf.rot);
+          bool zero = !ppf_key_exists(a.ppf, f) || i == bsel;
+          if (stage == 2) {
+            const V3 v_2 = normalized(sub(p, pb[0]));
+            float ang = (float)rad_to_deg_ref(acos_f(dot(v_1, v_2)));
+            const float other = 180.0f - ang;
+            ang = (other < ang) ? other : ang;
+            zero = zero || (ang < internal_angle_threshold);
+          } else if (stage == 3) {
+            float planar = 10000.0f;
+            if (denom != 0) planar = (float)fabs((double)((pA * p.x + pB * p.y) + pC * p.z) - 1.0);
+            zero = zero || (planar > plane_threshold) || (norm(sub(p, pb[0])) < min_distance_base) ||
+                   (norm(sub(p, pb[1])) < min_distance_base) || (norm(sub(p, pb[2])) < min_distance_base);
+          }
+          al = !zero;
+        }
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, al);
+      if (lane == 0) alive[t] = word;
+      if (al) lsum += prob_weight(cls);
+    }
+    lsum = warp_sum_u64(lsum);
+    if (lane == 0) s_wsum[w] = lsum;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long total = 0;
+      for (int k = 0; k < 32; ++k) total += s_wsum[k];
+      if (total == 0) {
+        s_pw = -1;
+      } else {
+        unsigned long long r = mulhi_u64(draw_u64(a.seed, base_no, (uint32_t)stage), total);
+        int k = 0;
+        while (k < 31 && r >= s_wsum[k]) { r -= s_wsum[k]; ++k; }
+        s_pw = k;
+        s_rem = r;
+      }
+    }
+    __syncthreads();
+    if (s_pw < 0) {  // the reference's "FAILED SAMPLING:: Zero probability returned" => return false
+      if (tid == 0) {
+        a.out_valid[base] = 0;
+        for (int k = 0; k < 4; ++k) a.out_ids[4 * base + k] = -1;
+        a.out_inv[2 * base] = 0.f; a.out_inv[2 * base + 1] = 0.f;
+      }
+      return;
+    }
+    if (w == s_pw) {
+      unsigned long long rem = s_rem;
+      for (int t = t0; t < t1; ++t) {
+        const int i = t * 32 + lane;
+        unsigned long long wt = 0;
+        if (i < a.S && ((alive[t] >> lane) & 1u)) wt = prob_weight(a.sattr[i].w);
+        unsigned long long inc = wt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += up;
+        }
+        const unsigned long long tile_total = __shfl_sync(0xffffffffu, inc, 31);
+        if (rem < tile_total) {
+          const unsigned hit = __ballot_sync(0xffffffffu, inc > rem);
+          if (lane == 0) s_b[stage] = t * 32 + (__ffs(hit) - 1);
+          break;
+        }
+        rem -= tile_total;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int ids[4] = {s_b[0], s_b[1], s_b[2], s_b[3]};
+    V3 b[4];
+    for (int k = 0; k < 4; ++k) { const float4 p = a.spos4[ids[k]]; b[k] = v3(p.x, p.y, p.z); }
+    float min_distance = 3.402823466e+38f, inv1 = 0.f, inv2 = 0.f;
+    int best[4] = {-1, -1, -1, -1};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        if (i == j) continue;
+        int k = 0; while (k == i || k == j) k++;
+        int l = 0; while (l == i || l == j || l == k) l++;
+        double li1, li2;
+        const float sd = (float)seg_dist_inv(b[i], b[j], b[k], b[l], li1, li2);
+        if (sd < min_distance) {
+          min_distance = sd;
+          best[0] = i; best[1] = j; best[2] = k; best[3] = l;
+          inv1 = (float)li1; inv2 = (float)li2;
+        }
+      }
+    const bool ok = best[0] >= 0;
+    for (int k = 0; k < 4; ++k) a.out_ids[4 * base + k] = ok ? ids[best[k]] : ids[k];
+    a.out_inv[2 * base] = inv1; a.out_inv[2 * base + 1] = inv2;
+    a.out_valid[base] = ok ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+PpfView stocs_ppf_view(const stocs_b200_ctx* ctx);
+
+// device outputs: d_ids (n*4 int), d_inv (n*2 float), d_valid (n bytes)
+int stocs_launch_sample(stocs_b200_ctx* ctx, uint64_t seed, uint32_t first_base_no, int n_bases, int* d_ids,
+                        float* d_inv, uint8_t* d_valid, cudaStream_t st) {
+  SampleArgs a;
+  a.spos4 = ctx->d_spos4.as<float4>();
+  a.sattr = ctx->d_sattr.as<float4>();
+  a.S = ctx->S;
+  a.ppf = stocs_ppf_view(ctx);
+  a.seed = seed;
+  a.words = (ctx->S + 31) / 32;
+  a.out_ids = d_ids; a.out_inv = d_inv; a.out_valid = d_valid;
+  // survivors bitmap: batches of at most 4 * num_sms bases
+  const int batch = ctx->num_sms * 4;
+  STOCS_CUDA(ctx, ctx->d_work.ensure((size_t)batch * a.words * 4));
+  a.alive = ctx->d_work.as<uint32_t>();
+  for (int off = 0; off < n_bases; off += batch) {
+    const int n = (n_bases - off < batch) ? (n_bases - off) : batch;
+    SampleArgs b = a;
+    b.first_base = first_base_no + (uint32_t)off;
+    b.out_ids = d_ids + 4 * (size_t)off;
+    b.out_inv = d_inv + 2 * (size_t)off;
+    b.out_valid = d_valid + off;
+    sample_bases_kernel<<<n, 1024, 0, st>>>(b);
+  }
+  STOCS_CUDA(ctx, cudaGetLastError());
+  return STOCS_OK;
+}
+
+extern "C" int stocs_b200_sample_bases(stocs_b200_ctx* ctx, uint64_t seed, uint32_t first_base_no, int n_bases,
+                                       int32_t* base_idx4, float* inv2, uint8_t* valid) {
+  if (!ctx) return STOCS_E_ARG;
+  if (ctx->S <= 0 || ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "sample_bases: upload_model and upload_scene first");
+  if (n_bases < 0 || (n_bases > 0 && (!base_idx4 || !inv2 || !valid))) STOCS_FAIL(ctx, STOCS_E_ARG, "sample_bases: bad argument");
+  if (n_bases == 0) return STOCS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)n_bases * (16 + 8 + 1) + 64));
+  int* d_ids = ctx->d_tmp2.as<int>();
+  float* d_inv = (float*)(d_ids + 4 * (size_t)n_bases);
+  uint8_t* d_valid = (uint8_t*)(d_inv + 2 * (size_t)n_bases);
+  int rc = stocs_launch_sample(ctx, seed, first_base_no, n_bases, d_ids, d_inv, d_valid, st);
+  if (rc) return rc;
+  STOCS_CUDA(ctx, cudaMemcpyAsync(base_idx4, d_ids, (size_t)n_bases * 16, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(inv2, d_inv, (size_t)n_bases * 8, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(valid, d_valid, (size_t)n_bases, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  return STOCS_OK;
+}

@@ -1,0 +1,299 @@
+// scene_index.cu -- scene centring and nearest-neighbour index construction on the device.
+//
+// Replaces stocs_estimator::centroid_shift (reference src/stocs.cpp:943-964) and
+// stocs_estimator::kdtree_initialize (src/stocs.cpp:966-980).  The NN index the scoring kernel
+// reads is a dense voxel grid whose cells carry eps-DILATED candidate lists: cell C lists every
+// scene point within eps (plus a rounding margin) of C's box, so an exact radius-eps query reads
+// ONE cell descriptor and one contiguous run of float4 candidates.  The reference kd-tree
+// (kdtree.h:355-370,522-641) is also built -- on the host, once per frame -- and uploaded; the
+// scoring kernel walks it only when two candidates are at exactly the same squared distance, to
+// reproduce the reference's traversal-order tie rule (kdtree.h:416-428).
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+#include "stocs_ctx.h"
+
+namespace {
+
+// Sequential fp32 centroid in index order (src/stocs.cpp:945-956).  The sums are order
+// dependent, so the chain is serial: 256 threads stage 2048-point chunks into shared memory with
+// coalesced loads and lanes 0..2 of warp 0 run the three dependent add chains out of it.
+__global__ void centroid_seq_kernel(const float* __restrict__ pos3, int n, float* __restrict__ out3) {
+  constexpr int CH = 2048;
+  __shared__ float buf[CH * 3];
+  float acc = 0.f;
+  for (int base = 0; base < n; base += CH) {
+    int cnt = min(CH, n - base);
+    for (int t = threadIdx.x; t < cnt * 3; t += blockDim.x) buf[t] = pos3[(size_t)base * 3 + t];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      for (int i = 0; i < cnt; ++i) acc += buf[i * 3 + threadIdx.x];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) out3[threadIdx.x] = acc / (float)n;
+}
+
+__device__ __forceinline__ int f2ord(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ord2f(int i) {
+  int b = i >= 0 ? i : i ^ 0x7fffffff;
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+
+// pos -= centroid (src/stocs.cpp:958-963); pack float4(x,y,z,bits(idx)); AABB via ordered ints.
+__global__ void centre_pack_kernel(const float* __restrict__ pos3, int n, const float* __restrict__ c3,
+                                   float4* __restrict__ out4, float* __restrict__ out3,
+                                   int* __restrict__ aabb6) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float cx = c3[0], cy = c3[1], cz = c3[2];
+  int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+  if (i < n) {
+    float x = pos3[3 * (size_t)i] - cx, y = pos3[3 * (size_t)i + 1] - cy, z = pos3[3 * (size_t)i + 2] - cz;
+    out4[i] = make_float4(x, y, z, __int_as_float(i));
+    if (out3) { out3[3 * (size_t)i] = x; out3[3 * (size_t)i + 1] = y; out3[3 * (size_t)i + 2] = z; }
+    mn[0] = mx[0] = f2ord(x); mn[1] = mx[1] = f2ord(y); mn[2] = mx[2] = f2ord(z);
+  }
+  if (aabb6) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int a = __reduce_min_sync(0xffffffffu, mn[k]);
+      int b = __reduce_max_sync(0xffffffffu, mx[k]);
+      if ((threadIdx.x & 31) == 0) { atomicMin(&aabb6[k], a); atomicMax(&aabb6[3 + k], b); }
+    }
+  }
+}
+
+__global__ void pack_attr_kernel(const float* __restrict__ nrm3, const float* __restrict__ cls, int n,
+                                 float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(nrm3[3 * (size_t)i], nrm3[3 * (size_t)i + 1], nrm3[3 * (size_t)i + 2], cls[i]);
+}
+
+struct CellRange { int x0, x1, y0, y1, z0, z1; };
+__device__ __forceinline__ CellRange dilated_range(const GridDesc& g, float4 p, float r) {
+  CellRange c;
+  c.x0 = max(0, (int)floorf((p.x - r - g.ox) * g.inv_cell));
+  c.x1 = min(g.nx - 1, (int)floorf((p.x + r - g.ox) * g.inv_cell));
+  c.y0 = max(0, (int)floorf((p.y - r - g.oy) * g.inv_cell));
+  c.y1 = min(g.ny - 1, (int)floorf((p.y + r - g.oy) * g.inv_cell));
+  c.z0 = max(0, (int)floorf((p.z - r - g.oz) * g.inv_cell));
+  c.z1 = min(g.nz - 1, (int)floorf((p.z + r - g.oz) * g.inv_cell));
+  return c;
+}
+
+__global__ void grid_count_kernel(const float4* __restrict__ pts, int n, GridDesc g, float r,
+                                  uint32_t* __restrict__ counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CellRange c = dilated_range(g, pts[i], r);
+  for (int z = c.z0; z <= c.z1; ++z)
+    for (int y = c.y0; y <= c.y1; ++y)
+      for (int x = c.x0; x <= c.x1; ++x)
+        atomicAdd(&counts[((size_t)z * g.ny + y) * g.nx + x], 1u);
+}
+
+__global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc g, float r,
+                                 const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cursor,
+                                 float4* __restrict__ cand) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  CellRange c = dilated_range(g, p, r);
+  for (int z = c.z0; z <= c.z1; ++z)
+    for (int y = c.y0; y <= c.y1; ++y)
+      for (int x = c.x0; x <= c.x1; ++x) {
+        size_t cell = ((size_t)z * g.ny + y) * g.nx + x;
+        uint32_t slot = cell_start[cell] + atomicAdd(&cursor[cell], 1u);
+        cand[slot] = p;
+      }
+}
+
+// Host construction of the reference kd-tree (explicit work stack instead of recursion; node
+// numbering differs from the reference, tree shape and leaf point order do not).
+struct KdBuild {
+  std::vector<float> x, y, z;
+  std::vector<int> idx;
+  std::vector<KdNodeDev> nodes;
+  const float* comp(unsigned d) const { return d == 0 ? x.data() : (d == 1 ? y.data() : z.data()); }
+
+  unsigned partition(int start, int end, unsigned dim, float sv) {
+    const float* c = comp(dim);
+    int l = start, r = end - 1;
+    for (; l < r; ++l, --r) {
+      while (l < end && c[l] < sv) l++;
+      while (r >= start && c[r] >= sv) r--;
+      if (l > r) break;
+      std::swap(x[l], x[r]); std::swap(y[l], y[r]); std::swap(z[l], z[r]);
+      std::swap(idx[l], idx[r]);
+    }
+    if (l >= end) return (unsigned)end;
+    return c[l] < sv ? (unsigned)(l + 1) : (unsigned)l;
+  }
+
+  void build(const float* pos3, int n) {
+    x.resize(n); y.resize(n); z.resize(n); idx.resize(n);
+    for (int i = 0; i < n; ++i) { x[i] = pos3[3 * i]; y[i] = pos3[3 * i + 1]; z[i] = pos3[3 * i + 2]; idx[i] = i; }
+    nodes.clear();
+    nodes.push_back(KdNodeDev{0.f, 0u, 0u, 0u});
+    struct Job { unsigned node, start, end, level; };
+    std::vector<Job> todo;
+    todo.push_back({0u, 0u, (unsigned)n, 1u});
+    while (!todo.empty()) {
+      Job j = todo.back();
+      todo.pop_back();
+      const float big = FLT_MAX / 2;
+      float mn[3] = {big, big, big}, mx[3] = {-big, -big, -big};
+      for (unsigned i = j.start; i < j.end; ++i) {
+        if (x[i] < mn[0]) mn[0] = x[i]; if (x[i] > mx[0]) mx[0] = x[i];
+        if (y[i] < mn[1]) mn[1] = y[i]; if (y[i] > mx[1]) mx[1] = y[i];
+        if (z[i] < mn[2]) mn[2] = z[i]; if (z[i] > mx[2]) mx[2] = z[i];
+      }
+      float hd[3] = {0.5f * (mx[0] - mn[0]), 0.5f * (mx[1] - mn[1]), 0.5f * (mx[2] - mn[2])};
+      unsigned dim = 0;
+      if (hd[1] > hd[dim]) dim = 1;
+      if (hd[2] > hd[dim]) dim = 2;
+      float sv = mn[dim] + ((mx[dim] - mn[dim]) / 2.0f);
+      unsigned mid = partition((int)j.start, (int)j.end, dim, sv);
+      unsigned first = (unsigned)nodes.size();
+      nodes[j.node].split = sv;
+      nodes[j.node].first_or_start = first;
+      nodes[j.node].dim_or_size = dim;
+      nodes[j.node].leaf = 0;
+      nodes.push_back(KdNodeDev{0.f, 0u, 0u, 0u});
+      nodes.push_back(KdNodeDev{0.f, 0u, 0u, 0u});
+      unsigned lo[2] = {j.start, mid}, hi[2] = {mid, j.end};
+      for (int c = 0; c < 2; ++c) {
+        unsigned cnt = hi[c] - lo[c];
+        if (cnt <= 64u || j.level >= 32u) {
+          nodes[first + c].leaf = 1;
+          nodes[first + c].first_or_start = lo[c];
+          nodes[first + c].dim_or_size = cnt;
+        } else {
+          todo.push_back({first + (unsigned)c, lo[c], hi[c], j.level + 1});
+        }
+      }
+    }
+  }
+};
+
+}  // namespace
+
+// Centre n points with the reference's sequential fp32 centroid; optional float4 / float3 device
+// outputs, centroid and AABB (min xyz, max xyz of the centred points) returned to the host.
+int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4* d_out4,
+                        float* d_out3, float* h_centroid3, float* h_aabb6) {
+  cudaStream_t st = ctx->stream;
+  STOCS_CUDA(ctx, ctx->d_small.ensure(256));
+  float* d_c = ctx->d_small.as<float>();
+  int* d_aabb = (int*)(d_c + 4);
+  centroid_seq_kernel<<<1, 256, 0, st>>>(d_pos3, n, d_c);
+  int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  STOCS_CUDA(ctx, cudaMemcpyAsync(d_aabb, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  centre_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_pos3, n, d_c, d_out4, d_out3, d_aabb);
+  STOCS_CUDA(ctx, cudaGetLastError());
+  int haabb[6];
+  STOCS_CUDA(ctx, cudaMemcpyAsync(h_centroid3, d_c, 12, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(haabb, d_aabb, 24, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (h_aabb6)
+    for (int k = 0; k < 6; ++k) h_aabb6[k] = ord2f(haabb[k]);
+  return STOCS_OK;
+}
+
+int stocs_build_scene_index(stocs_b200_ctx* ctx) {
+  // expects ctx->d_tmp = raw pos3 (S*3 floats)
+  const int S = ctx->S;
+  cudaStream_t st = ctx->stream;
+  STOCS_CUDA(ctx, ctx->d_spos4.ensure((size_t)S * 16));
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)S * 12));
+  int nb = (S + 255) / 256;
+  float aabb[6];
+  int rc = stocs_centre_points(ctx, ctx->d_tmp.as<float>(), S, ctx->d_spos4.as<float4>(),
+                               ctx->d_tmp2.as<float>(), ctx->cs, aabb);
+  if (rc) return rc;
+  ctx->h_spos.resize((size_t)S * 3);
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_spos.data(), ctx->d_tmp2.p, (size_t)S * 12, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  float mn[3] = {aabb[0], aabb[1], aabb[2]}, mx[3] = {aabb[3], aabb[4], aabb[5]};
+  for (int k = 0; k < 3; ++k)
+    if (!(mn[k] <= mx[k]) || !std::isfinite(mn[k]) || !std::isfinite(mx[k]))
+      STOCS_FAIL(ctx, STOCS_E_ARG, "upload_scene: scene contains non-finite coordinates");
+
+  // grid geometry: cell edge = 2*eps unless that needs more than kMaxCells cells
+  const double eps = ctx->eps;
+  const double kMaxCells = 96.0 * 1024 * 1024;
+  double cell = 2.0 * eps;
+  double ext[3] = {(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]};
+  for (;;) {
+    double n = (floor(ext[0] / cell) + 3) * (floor(ext[1] / cell) + 3) * (floor(ext[2] / cell) + 3);
+    if (n <= kMaxCells) break;
+    cell *= 1.25;
+  }
+  GridDesc g;
+  g.ox = (float)(mn[0] - cell); g.oy = (float)(mn[1] - cell); g.oz = (float)(mn[2] - cell);
+  g.inv_cell = (float)(1.0 / cell);
+  g.nx = (int)floor(ext[0] / cell) + 3; g.ny = (int)floor(ext[1] / cell) + 3; g.nz = (int)floor(ext[2] / cell) + 3;
+  g.ncells = (uint32_t)((size_t)g.nx * g.ny * g.nz);
+  ctx->grid = g;
+  // dilation radius: eps plus a margin that absorbs the rounding of both cell-index computations
+  const float r = (float)(eps * (1.0 + 1.0 / 1024.0) + cell / 1024.0);
+
+  size_t nc1 = (size_t)g.ncells + 1;
+  STOCS_CUDA(ctx, ctx->d_cell_start.ensure(nc1 * 4));
+  STOCS_CUDA(ctx, ctx->d_work.ensure(nc1 * 4));
+  uint32_t* counts = ctx->d_work.as<uint32_t>();
+  STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
+  grid_count_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, ctx->d_cell_start.as<uint32_t>(), (int)nc1, st);
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, counts, ctx->d_cell_start.as<uint32_t>(), (int)nc1, st);
+  uint32_t total = 0;
+  STOCS_CUDA(ctx, cudaMemcpyAsync(&total, ctx->d_cell_start.as<uint32_t>() + g.ncells, 4, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->ncand = total;
+  STOCS_CUDA(ctx, ctx->d_cand.ensure((size_t)(total ? total : 1) * 16));
+  STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
+  grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, ctx->d_cell_start.as<uint32_t>(),
+                                       counts, ctx->d_cand.as<float4>());
+  STOCS_CUDA(ctx, cudaGetLastError());
+
+  // reference kd-tree (tie resolution only)
+  KdBuild kb;
+  kb.build(ctx->h_spos.data(), S);
+  std::vector<float4> kp(S);
+  for (int i = 0; i < S; ++i) {
+    float w;
+    int id = kb.idx[i];
+    memcpy(&w, &id, 4);
+    kp[i] = make_float4(kb.x[i], kb.y[i], kb.z[i], w);
+  }
+  ctx->kd_nodes = (int)kb.nodes.size();
+  STOCS_CUDA(ctx, ctx->d_kd_nodes.ensure(kb.nodes.size() * sizeof(KdNodeDev)));
+  STOCS_CUDA(ctx, ctx->d_kd_pts.ensure((size_t)S * 16));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_nodes.p, kb.nodes.data(), kb.nodes.size() * sizeof(KdNodeDev),
+                                  cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_pts.p, kp.data(), (size_t)S * 16, cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->counters[2] = g.ncells;
+  ctx->counters[3] = total;
+  return STOCS_OK;
+}
+
+// used by upload_scene in capi.cu
+int stocs_pack_scene_attr(stocs_b200_ctx* ctx, const float* d_nrm3, const float* d_cls, int S) {
+  STOCS_CUDA(ctx, ctx->d_sattr.ensure((size_t)S * 16));
+  pack_attr_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(d_nrm3, d_cls, S, ctx->d_sattr.as<float4>());
+  STOCS_CUDA(ctx, cudaGetLastError());
+  return STOCS_OK;
+}

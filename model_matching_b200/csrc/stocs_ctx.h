@@ -1,0 +1,128 @@
+// stocs_ctx.h -- internal context shared by the translation units of libstocs_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/stocs_b200.h"
+#include "stocs_math.h"
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    size_t cap = need < 256 ? 256 : need;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e == cudaSuccess) bytes = cap;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+// Device kd-tree node (16 B).  Inner: split/first/dim; leaf: start/size.
+struct KdNodeDev {
+  float split;
+  uint32_t first_or_start;
+  uint32_t dim_or_size;
+  uint32_t leaf;
+};
+
+// Dense voxel grid over the centred scene with eps-dilated per-cell candidate lists.
+struct GridDesc {
+  float ox, oy, oz;   // origin (lower corner of cell 0)
+  float inv_cell;     // 1 / cell edge
+  int nx, ny, nz;
+  uint32_t ncells;
+};
+
+struct PpfTableDesc {
+  int n1, na;          // bins along the distance axis / each angle axis
+  int tr, rot;
+  int64_t npairs;      // ordered pairs stored (own bin)
+  int64_t nkeys;       // occupied own bins
+};
+
+struct stocs_b200_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
+  std::string err;
+
+  // parameters
+  float eps = 0.005f;
+  int tr = 5, rot = 5;
+  float dot_thr = 0.f;  // "angle < 30" <=> dot_thr < dot <= 1 (see angle_threshold_dot)
+
+  // model (centred)
+  int M = 0, Mpad = 0;
+  float cm[3] = {0, 0, 0};
+  std::vector<float> h_mpos, h_mnrm;  // centred positions, normals (M*3)
+  DevBuf d_model;                      // SoA 6*Mpad floats: px,py,pz,nx,ny,nz
+  DevBuf d_mpos4;                      // float4 (x,y,z,0) centred
+  DevBuf d_mnrm4;                      // float4 (nx,ny,nz,0)
+
+  // scene (centred)
+  int S = 0;
+  float cs[3] = {0, 0, 0};
+  std::vector<float> h_spos;           // centred positions (S*3)
+  DevBuf d_spos4;                      // float4 (x,y,z,bits(idx))
+  DevBuf d_sattr;                      // float4 (nx,ny,nz,class probability)
+  DevBuf d_spix;                       // int2 (row, col)
+  GridDesc grid{};
+  DevBuf d_cell_start;                 // uint32[ncells+1]
+  DevBuf d_cand;                       // float4 (x,y,z,bits(idx)) replicated per dilated cell
+  int64_t ncand = 0;
+  DevBuf d_kd_nodes, d_kd_pts;         // reference kd-tree for exact-tie resolution
+  int kd_nodes = 0;
+
+  // PPF table
+  PpfTableDesc ppf{};
+  DevBuf d_ppf_bin_start;              // uint32[nbins+1]  CSR over own bins
+  DevBuf d_ppf_pairs;                  // uint32 (id1<<16|id2) sorted by (bin, id1, id2)
+  DevBuf d_ppf_keybits;                // bitmap of keys present in the reference's expanded map
+  std::vector<uint32_t> h_ppf_bin_start, h_ppf_pairs;
+
+  // scratch
+  DevBuf d_T, d_lcp, d_inl, d_work, d_tmp, d_tmp2, d_small;
+  void* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+
+  // last score call
+  int64_t last_H = 0;
+  int64_t counters[8] = {0};
+  bool timing_valid = false;
+};
+
+#define STOCS_CUDA(ctx, call)                                                            \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                   \
+      return STOCS_E_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define STOCS_FAIL(ctx, code, msg) \
+  do { (ctx)->err = (msg); return (code); } while (0)
+
+// kernels / stages implemented in the other translation units
+int stocs_build_scene_index(stocs_b200_ctx* ctx);                         // scene_index.cu
+int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4* d_out4,
+                        float* d_out3, float* h_centroid3, float* h_aabb6);
+int stocs_pack_scene_attr(stocs_b200_ctx* ctx, const float* d_nrm3, const float* d_cls, int S);
+int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp,
+                       int32_t* d_inl, cudaStream_t st, bool time_it);     // score.cu
+int stocs_launch_backproject(stocs_b200_ctx* ctx, const uint16_t* d_depth, const uint8_t* d_bgr,
+                             int W, int H, float fx, float cx, float fy, float cy, float scale,
+                             float* d_xyz, uint32_t* d_rgb, cudaStream_t st);  // backproject.cu
+bool stocs_fmad_selftest(stocs_b200_ctx* ctx);                             // score.cu
+float stocs_angle_threshold_dot();                                         // capi.cu (host)

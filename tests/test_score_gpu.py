@@ -1,0 +1,131 @@
+"""GPU parity of LCP scoring (reference src/stocs.cpp:1006-1041) against the CPU oracle:
+inlier counts AND LCP bit-exact (stricter than the 1e-5 relative the north star asks for)."""
+import numpy as np
+import pytest
+
+import oracle
+from model_matching_b200 import Context, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, sc, mpos, mnrm, T):
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+    cs, cm = ctx.centroids()
+    ocs, ocm = est.centroids()
+    assert np.array_equal(cs, ocs) and np.array_equal(cm, ocm)
+    s, m = ctx.centred()
+    os_, om = est.centred()
+    assert np.array_equal(s, os_) and np.array_equal(m, om)
+    lcp, inl = ctx.score_lcp(T)
+    olcp, oinl = est.score(T, threads=8)
+    assert np.array_equal(inl, oinl)
+    assert np.array_equal(lcp.view(np.uint32), olcp.view(np.uint32))
+    return lcp, inl
+
+
+def test_score_small_scene(gpu_ctx, small_scene):
+    sc, mpos, mnrm = small_scene
+    T, near = synth.make_hypotheses(4000, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=11, near_fraction=0.05)
+    lcp, inl = _check(gpu_ctx, sc, mpos, mnrm, T)
+    assert inl[near].min() > 100 and inl.max() <= len(mpos)
+
+
+@pytest.mark.parametrize("M", [1, 31, 33, 500])
+def test_score_ragged_model_sizes(gpu_ctx, small_scene, M):
+    sc, _, _ = small_scene
+    mpos, mnrm = synth.make_model(M)
+    T, _ = synth.make_hypotheses(600, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=5, near_fraction=0.2)
+    _check(gpu_ctx, sc, mpos, mnrm, T)
+
+
+def test_score_exact_ties_use_kdtree_rule(gpu_ctx):
+    """Scene points on an exact lattice, queries exactly between them: many exact d^2 ties whose
+    winner decides the normal test.  The GPU must pick the kd-tree's winner."""
+    g = np.arange(-8, 9, dtype=np.float32) * np.float32(0.0078125)   # 2^-7 spacing, exact
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    pos = np.stack([X.ravel(), Y.ravel(), np.zeros(X.size, np.float32)], -1)
+    rng = np.random.default_rng(3)
+    nrm = rng.normal(size=pos.shape).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    cls = rng.integers(1000, 10001, size=len(pos)).astype(np.float32) / np.float32(10000)
+    # symmetric scene => centroid exactly 0; model points at lattice midpoints (two or four
+    # scene points at exactly the same distance)
+    assert np.all(pos.sum(0) == 0)
+    h = np.float32(0.00390625)
+    mp_ = np.array([[h, 0, 0], [-h, 0, 0], [h, h, 0], [0, h, 0], [3 * h, h, 0], [h, -3 * h, 0]], np.float32)
+    mp_ = np.concatenate([mp_, -mp_])   # centroid exactly 0
+    mn = np.tile(np.array([[0, 0, 1]], np.float32), (len(mp_), 1))
+    ctx = gpu_ctx
+    ctx.upload_model(mp_, mn)
+    ctx.upload_scene(pos, nrm, cls)
+    # pure lattice translations keep the ties exact
+    T = []
+    for i in range(-4, 5):
+        for j in range(-4, 5):
+            M4 = np.eye(4, dtype=np.float32)
+            M4[0, 3] = i * 2 * h
+            M4[1, 3] = j * 2 * h
+            T.append(M4.T.reshape(16))
+    T = np.array(T, np.float32)
+    est = oracle.Estimator(pos, nrm, cls, mp_, mn, distance_threshold=0.008)
+    ctx2 = Context(0, distance_threshold=0.008)
+    ctx2.upload_model(mp_, mn)
+    ctx2.upload_scene(pos, nrm, cls)
+    before = ctx2.counters()[1]
+    lcp, inl = ctx2.score_lcp(T)
+    olcp, oinl = est.score(T)
+    assert ctx2.counters()[1] - before > 100, "the test must actually exercise the tie path"
+    assert np.array_equal(inl, oinl)
+    assert np.array_equal(lcp.view(np.uint32), olcp.view(np.uint32))
+    ctx2.close()
+
+
+def test_score_empty_and_out_of_grid(gpu_ctx, small_scene):
+    sc, mpos, mnrm = small_scene
+    gpu_ctx.upload_model(mpos, mnrm)
+    gpu_ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    lcp, inl = gpu_ctx.score_lcp(np.zeros((0, 16), np.float32))
+    assert lcp.size == 0
+    far = np.eye(4, dtype=np.float32)
+    far[:3, 3] = [1e6, -1e6, 3e5]
+    nanT = np.full(16, np.nan, np.float32)
+    T = np.stack([far.T.reshape(16), nanT, np.zeros(16, np.float32)])
+    lcp, inl = gpu_ctx.score_lcp(T)
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+    olcp, oinl = est.score(T)
+    assert np.array_equal(inl, oinl) and np.array_equal(lcp.view(np.uint32), olcp.view(np.uint32))
+
+
+def test_reduce_best_matches_reference_rule(gpu_ctx):
+    rng = np.random.default_rng(0)
+    lcp = rng.uniform(0, 1, 100000).astype(np.float32)
+    lcp[rng.integers(0, lcp.size, 50)] = lcp.max()          # ties on the maximum: first wins
+    bi, bl, ti, tl = gpu_ctx.reduce_best(lcp, K=32)
+    assert (bi, bl) == oracle.best(lcp)
+    order = np.lexsort((np.arange(lcp.size), -lcp.astype(np.float64)))[:32]
+    assert np.array_equal(ti, order) and np.array_equal(tl, lcp[order])
+    z = np.zeros(1000, np.float32)
+    bi, bl, ti, tl = gpu_ctx.reduce_best(z, K=4)
+    assert bi == -1 and bl == 0 and np.all(ti == -1)
+    few = np.array([0, 0.5, 0, 0.25], np.float32)
+    bi, bl, ti, tl = gpu_ctx.reduce_best(few, K=4)
+    assert bi == 1 and list(ti) == [1, 3, -1, -1]
+
+
+def test_backproject_bit_exact(gpu_ctx):
+    rng = np.random.default_rng(1234)
+    depth = rng.integers(0, 20000, size=(480, 640)).astype(np.uint16)
+    depth[rng.uniform(size=depth.shape) < 0.1] = 0
+    bgr = rng.integers(0, 256, size=(480, 640, 3)).astype(np.uint8)
+    fx, cx, fy, cy = 572.4114, 325.2611, 573.57043, 242.04899
+    xyz, rgb = gpu_ctx.backproject(depth, bgr, fx, cx, fy, cy, 1 / 1000.0)
+    oxyz, orgb = oracle.backproject(depth, bgr, fx, cx, fy, cy, 1 / 1000.0)
+    assert np.array_equal(xyz.view(np.uint32), oxyz.view(np.uint32))
+    assert np.array_equal(rgb, orgb)
+    xyz2, none = gpu_ctx.backproject(depth[:7, :5].copy(), None, fx, cx, fy, cy, 1 / 8000.0)
+    assert none is None
+    oxyz2, _ = oracle.backproject(depth[:7, :5].copy(), None, fx, cx, fy, cy, 1 / 8000.0)
+    assert np.array_equal(xyz2.view(np.uint32), oxyz2.view(np.uint32))
