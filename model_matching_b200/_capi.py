@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstocs_b200.so")
+LIB_PATH = os.environ.get("STOCS_B200_LIB", os.path.join(_HERE, "libstocs_b200.so"))
 _LIB = None
 
 # every symbol include/stocs_b200.h declares (checked by tests/test_abi.py)

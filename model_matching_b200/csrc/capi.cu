@@ -77,7 +77,7 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->d_model, &ctx->d_mpos4, &ctx->d_mnrm4, &ctx->d_spos4, &ctx->d_sattr, &ctx->d_spix,
-                    &ctx->d_cell_start, &ctx->d_cand, &ctx->d_kd_nodes, &ctx->d_kd_pts, &ctx->d_ppf_bin_start,
+                    &ctx->d_bricks, &ctx->d_cell_start, &ctx->d_cand, &ctx->d_kd_nodes, &ctx->d_kd_pts, &ctx->d_ppf_bin_start,
                     &ctx->d_ppf_pairs, &ctx->d_ppf_keybits, &ctx->d_T, &ctx->d_lcp, &ctx->d_inl, &ctx->d_work,
                     &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_small};
   for (DevBuf* b : bufs) b->release();
@@ -149,13 +149,14 @@ int stocs_b200_upload_model(stocs_b200_ctx* ctx, const float* pos3, const float*
   ctx->h_mnrm.assign(nrm3, nrm3 + (size_t)M * 3);
   STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_mpos.data(), ctx->d_tmp2.p, (size_t)M * 12, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
-  const int Mpad = ((M + 31) / 32) * 32;
-  std::vector<float> soa((size_t)6 * Mpad, 0.f);
+  const int Mpad = ((M + 63) / 64) * 64;  // the scoring kernel consumes 64 points per iteration
+  // scoring-kernel layout: float4 centred positions (4*Mpad floats), then normals as SoA
+  std::vector<float> soa((size_t)7 * Mpad, 0.f);
   std::vector<float> n4((size_t)4 * M, 0.f);
   for (int i = 0; i < M; ++i)
     for (int k = 0; k < 3; ++k) {
-      soa[(size_t)k * Mpad + i] = ctx->h_mpos[3 * (size_t)i + k];
-      soa[(size_t)(3 + k) * Mpad + i] = nrm3[3 * (size_t)i + k];
+      soa[4 * (size_t)i + k] = ctx->h_mpos[3 * (size_t)i + k];
+      soa[(size_t)(4 + k) * Mpad + i] = nrm3[3 * (size_t)i + k];
       n4[4 * (size_t)i + k] = nrm3[3 * (size_t)i + k];
     }
   STOCS_CUDA(ctx, ctx->d_model.ensure(soa.size() * 4));

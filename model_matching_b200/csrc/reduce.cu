@@ -24,46 +24,52 @@ __device__ __forceinline__ unsigned long long make_key(float v, unsigned long lo
   return ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffull - (idx & 0xffffffffull));
 }
 
-__global__ void topk_partial_kernel(const float* __restrict__ lcp, long long H, unsigned long long* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+// offer one key per lane to the warp's sorted list
+__device__ __forceinline__ void warp_offer(unsigned long long& mine, unsigned long long key, int lane) {
+  const unsigned long long kth = __shfl_sync(0xffffffffu, mine, 31);
+  unsigned pass = __ballot_sync(0xffffffffu, key > kth);
+  while (pass) {
+    const int b = __ffs(pass) - 1;
+    const unsigned long long k = __shfl_sync(0xffffffffu, key, b);
+    const unsigned long long cur_kth = __shfl_sync(0xffffffffu, mine, 31);
+    if (k > cur_kth) warp_insert(mine, k, lane);
+    pass &= pass - 1;
+  }
+}
+
+// one sorted top-32 list per CTA: per-warp lists, merged through shared memory by warp 0
+__global__ void __launch_bounds__(256) topk_partial_kernel(const float* __restrict__ lcp, long long H,
+                                                           unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long s_keys[8 * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long warp = (long long)blockIdx.x * 8 + w;
+  const long long nwarps = (long long)gridDim.x * 8;
   unsigned long long mine = 0ull;  // key 0 == "empty" (lcp 0 never qualifies: strict > 0)
   for (long long base = warp * 32; base < H; base += nwarps * 32) {
     const long long i = base + lane;
-    float v = (i < H) ? lcp[i] : 0.f;
-    unsigned long long key = (v > 0.f) ? make_key(v, (unsigned long long)i) : 0ull;
-    const unsigned long long kth = __shfl_sync(0xffffffffu, mine, 31);
-    unsigned pass = __ballot_sync(0xffffffffu, key > kth);
-    while (pass) {
-      const int b = __ffs(pass) - 1;
-      const unsigned long long k = __shfl_sync(0xffffffffu, key, b);
-      const unsigned long long cur_kth = __shfl_sync(0xffffffffu, mine, 31);
-      if (k > cur_kth) warp_insert(mine, k, lane);
-      pass &= pass - 1;
-    }
+    const float v = (i < H) ? lcp[i] : 0.f;
+    warp_offer(mine, (v > 0.f) ? make_key(v, (unsigned long long)i) : 0ull, lane);
   }
-  out[warp * 32 + lane] = mine;
+  s_keys[w * 32 + lane] = mine;
+  __syncthreads();
+  if (w == 0) {
+    for (int k = 1; k < 8; ++k) warp_offer(mine, s_keys[k * 32 + lane], lane);
+    out[(long long)blockIdx.x * 32 + lane] = mine;
+  }
 }
 
-__global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, long long n, int K,
-                                  long long index_offset, long long* __restrict__ out_idx,
-                                  float* __restrict__ out_lcp) {
-  const int lane = threadIdx.x & 31;
+// final merge of nlists sorted lists: 32 warps take a strided share each, warp 0 merges the rest
+__global__ void __launch_bounds__(1024) topk_merge_kernel(const unsigned long long* __restrict__ keys, long long nlists,
+                                                          int K, long long index_offset, long long* __restrict__ out_idx,
+                                                          float* __restrict__ out_lcp) {
+  __shared__ unsigned long long s_keys[32 * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned long long mine = 0ull;
-  for (long long base = 0; base < n; base += 32) {
-    const long long i = base + lane;
-    unsigned long long key = (i < n) ? keys[i] : 0ull;
-    const unsigned long long kth = __shfl_sync(0xffffffffu, mine, 31);
-    unsigned pass = __ballot_sync(0xffffffffu, key > kth);
-    while (pass) {
-      const int b = __ffs(pass) - 1;
-      const unsigned long long k = __shfl_sync(0xffffffffu, key, b);
-      const unsigned long long cur_kth = __shfl_sync(0xffffffffu, mine, 31);
-      if (k > cur_kth) warp_insert(mine, k, lane);
-      pass &= pass - 1;
-    }
-  }
+  for (long long l = w; l < nlists; l += 32) warp_offer(mine, keys[l * 32 + lane], lane);
+  s_keys[w * 32 + lane] = mine;
+  __syncthreads();
+  if (w != 0) return;
+  for (int k = 1; k < 32; ++k) warp_offer(mine, s_keys[k * 32 + lane], lane);
   if (lane < K) {
     if (mine == 0ull) { out_idx[lane] = -1; out_lcp[lane] = 0.f; }
     else {
@@ -83,11 +89,10 @@ int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K,
   long long need = (H + 255) / 256;
   if (need < 1) need = 1;
   if (blocks > need) blocks = (int)need;
-  const long long nwarps = (long long)blocks * 8;
-  STOCS_CUDA(ctx, ctx->d_work.ensure((size_t)nwarps * 32 * 8));
+  STOCS_CUDA(ctx, ctx->d_work.ensure((size_t)blocks * 32 * 8));
   topk_partial_kernel<<<blocks, 256, 0, st>>>(d_lcp, H, ctx->d_work.as<unsigned long long>());
-  topk_merge_kernel<<<1, 32, 0, st>>>(ctx->d_work.as<unsigned long long>(), nwarps * 32, K, index_offset,
-                                      (long long*)d_idx, d_val);
+  topk_merge_kernel<<<1, 1024, 0, st>>>(ctx->d_work.as<unsigned long long>(), blocks, K, index_offset,
+                                        (long long*)d_idx, d_val);
   STOCS_CUDA(ctx, cudaGetLastError());
   return STOCS_OK;
 }

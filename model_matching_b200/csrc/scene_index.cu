@@ -1,5 +1,10 @@
 // scene_index.cu -- scene centring and nearest-neighbour index construction on the device.
 //
+// Layout in HBM: cells are grouped in 4x4x4 bricks; the brick table holds {64-bit occupancy mask,
+// rank of the brick's first occupied cell} (16 B per brick, ~1 MB for the 1M-point scene, the
+// only structure every query touches), `starts` holds one offset per OCCUPIED cell, and the
+// float4 candidate records follow in the same order.
+//
 // Replaces stocs_estimator::centroid_shift (reference src/stocs.cpp:943-964) and
 // stocs_estimator::kdtree_initialize (src/stocs.cpp:966-980).  The NN index the scoring kernel
 // reads is a dense voxel grid whose cells carry eps-DILATED candidate lists: cell C lists every
@@ -79,6 +84,13 @@ __global__ void pack_attr_kernel(const float* __restrict__ nrm3, const float* __
   if (i < n) out[i] = make_float4(nrm3[3 * (size_t)i], nrm3[3 * (size_t)i + 1], nrm3[3 * (size_t)i + 2], cls[i]);
 }
 
+// Cells are numbered brick-major: 4x4x4 bricks, 64 consecutive cell numbers per brick, so that a
+// brick's occupancy fits one 64-bit mask and its candidate lists are contiguous.
+__device__ __forceinline__ size_t cell_number(const GridDesc& g, int x, int y, int z) {
+  const size_t brick = ((size_t)(z >> 2) * g.nby + (y >> 2)) * g.nbx + (x >> 2);
+  return brick * 64 + (size_t)(((z & 3) << 4) | ((y & 3) << 2) | (x & 3));
+}
+
 struct CellRange { int x0, x1, y0, y1, z0, z1; };
 __device__ __forceinline__ CellRange dilated_range(const GridDesc& g, float4 p, float r) {
   CellRange c;
@@ -99,7 +111,7 @@ __global__ void grid_count_kernel(const float4* __restrict__ pts, int n, GridDes
   for (int z = c.z0; z <= c.z1; ++z)
     for (int y = c.y0; y <= c.y1; ++y)
       for (int x = c.x0; x <= c.x1; ++x)
-        atomicAdd(&counts[((size_t)z * g.ny + y) * g.nx + x], 1u);
+        atomicAdd(&counts[cell_number(g, x, y, z)], 1u);
 }
 
 __global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc g, float r,
@@ -112,10 +124,46 @@ __global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc
   for (int z = c.z0; z <= c.z1; ++z)
     for (int y = c.y0; y <= c.y1; ++y)
       for (int x = c.x0; x <= c.x1; ++x) {
-        size_t cell = ((size_t)z * g.ny + y) * g.nx + x;
+        size_t cell = cell_number(g, x, y, z);
         uint32_t slot = cell_start[cell] + atomicAdd(&cursor[cell], 1u);
         cand[slot] = p;
       }
+}
+
+// per brick: occupancy mask and number of occupied cells
+__global__ void brick_mask_kernel(const uint32_t* __restrict__ cell_start, uint32_t nbricks,
+                                  unsigned long long* __restrict__ masks, uint32_t* __restrict__ occ) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbricks) return;
+  unsigned long long m = 0ull;
+  const uint32_t* cs = cell_start + (size_t)b * 64;
+  uint32_t prev = cs[0];
+  for (int k = 0; k < 64; ++k) {
+    const uint32_t nxt = cs[k + 1];
+    if (nxt != prev) m |= 1ull << k;
+    prev = nxt;
+  }
+  masks[b] = m;
+  occ[b] = (uint32_t)__popcll(m);
+}
+
+// brick table {mask lo, mask hi, index of the brick's first occupied cell, 0} + compact starts
+__global__ void brick_table_kernel(const uint32_t* __restrict__ cell_start, const unsigned long long* __restrict__ masks,
+                                   const uint32_t* __restrict__ occ_scan, uint32_t nbricks, uint32_t total_cand,
+                                   uint4* __restrict__ bricks, uint32_t* __restrict__ starts) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbricks) return;
+  const unsigned long long m = masks[b];
+  const uint32_t base = occ_scan[b];
+  bricks[b] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), base, 0u);
+  unsigned long long r = m;
+  uint32_t k = base;
+  while (r) {
+    const int bit = __ffsll((long long)r) - 1;
+    starts[k++] = cell_start[(size_t)b * 64 + bit];
+    r &= r - 1;
+  }
+  if (b == nbricks - 1) starts[occ_scan[nbricks]] = total_cand;
 }
 
 // Host construction of the reference kd-tree (explicit work stack instead of recursion; node
@@ -243,30 +291,54 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   g.ox = (float)(mn[0] - cell); g.oy = (float)(mn[1] - cell); g.oz = (float)(mn[2] - cell);
   g.inv_cell = (float)(1.0 / cell);
   g.nx = (int)floor(ext[0] / cell) + 3; g.ny = (int)floor(ext[1] / cell) + 3; g.nz = (int)floor(ext[2] / cell) + 3;
-  g.ncells = (uint32_t)((size_t)g.nx * g.ny * g.nz);
+  g.nbx = (g.nx + 3) / 4; g.nby = (g.ny + 3) / 4; g.nbz = (g.nz + 3) / 4;
+  g.nbricks = (uint32_t)((size_t)g.nbx * g.nby * g.nbz);
+  g.ncells = g.nbricks * 64u;
   ctx->grid = g;
   // dilation radius: eps plus a margin that absorbs the rounding of both cell-index computations
   const float r = (float)(eps * (1.0 + 1.0 / 1024.0) + cell / 1024.0);
 
   size_t nc1 = (size_t)g.ncells + 1;
-  STOCS_CUDA(ctx, ctx->d_cell_start.ensure(nc1 * 4));
+  DevBuf d_dense;  // dense per-cell starts (temporary)
+  STOCS_CUDA(ctx, d_dense.ensure(nc1 * 4));
   STOCS_CUDA(ctx, ctx->d_work.ensure(nc1 * 4));
   uint32_t* counts = ctx->d_work.as<uint32_t>();
+  uint32_t* dense_start = d_dense.as<uint32_t>();
   STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
   grid_count_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
   size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, ctx->d_cell_start.as<uint32_t>(), (int)nc1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, dense_start, (int)nc1, st);
   STOCS_CUDA(ctx, ctx->d_tmp2.ensure(tmp_bytes));
-  cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, counts, ctx->d_cell_start.as<uint32_t>(), (int)nc1, st);
+  cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, counts, dense_start, (int)nc1, st);
   uint32_t total = 0;
-  STOCS_CUDA(ctx, cudaMemcpyAsync(&total, ctx->d_cell_start.as<uint32_t>() + g.ncells, 4, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(&total, dense_start + g.ncells, 4, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->ncand = total;
   STOCS_CUDA(ctx, ctx->d_cand.ensure((size_t)(total ? total : 1) * 16));
   STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
-  grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, ctx->d_cell_start.as<uint32_t>(),
-                                       counts, ctx->d_cand.as<float4>());
+  grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>());
+  // brick table + compact starts
+  DevBuf d_masks, d_occ, d_occ_scan;
+  STOCS_CUDA(ctx, d_masks.ensure((size_t)g.nbricks * 8));
+  STOCS_CUDA(ctx, d_occ.ensure((size_t)(g.nbricks + 1) * 4));
+  STOCS_CUDA(ctx, d_occ_scan.ensure((size_t)(g.nbricks + 1) * 4));
+  STOCS_CUDA(ctx, cudaMemsetAsync(d_occ.p, 0, (size_t)(g.nbricks + 1) * 4, st));
+  const unsigned bb = (g.nbricks + 127) / 128;
+  brick_mask_kernel<<<bb, 128, 0, st>>>(dense_start, g.nbricks, d_masks.as<unsigned long long>(), d_occ.as<uint32_t>());
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
+  uint32_t n_occ = 0;
+  STOCS_CUDA(ctx, cudaMemcpyAsync(&n_occ, d_occ_scan.as<uint32_t>() + g.nbricks, 4, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  STOCS_CUDA(ctx, ctx->d_bricks.ensure((size_t)g.nbricks * 16));
+  STOCS_CUDA(ctx, ctx->d_cell_start.ensure((size_t)(n_occ + 1) * 4));
+  brick_table_kernel<<<bb, 128, 0, st>>>(dense_start, d_masks.as<unsigned long long>(), d_occ_scan.as<uint32_t>(), g.nbricks,
+                                         total, ctx->d_bricks.as<uint4>(), ctx->d_cell_start.as<uint32_t>());
   STOCS_CUDA(ctx, cudaGetLastError());
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  d_dense.release(); d_masks.release(); d_occ.release(); d_occ_scan.release();
+  ctx->counters[4] = n_occ;
 
   // reference kd-tree (tie resolution only)
   KdBuild kb;

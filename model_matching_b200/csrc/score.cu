@@ -5,30 +5,49 @@
 // (include/super4pcs/accelerators/kdtree.h:394-459).
 //
 // One warp per hypothesis, persistent CTAs, dynamic work counter.  Model points live in shared
-// memory (SoA, conflict-free).  Per round of 32 model points each lane transforms its point and
-// reads ONE cell descriptor of the eps-dilated voxel grid; lanes whose cell is non-empty are
-// compacted (ballot + rank) into a per-warp shared-memory queue, and 8-lane groups then scan one
-// queued query each, so the candidate float4 records of a query are read by adjacent lanes
-// (coalesced 128 B lines instead of one line per lane).  The nearest candidate is found with
-// redux.sync min on the bit pattern of d^2; an exact d^2 tie falls through to a walk of the
-// reference kd-tree so that the tie is broken the way kdtree.h:416-428 breaks it.  Matched
-// class probabilities are accumulated in model-point order (ballot order == index order), which
-// makes the LCP bit-identical to the reference's sequential fp32 sum.
+// memory (SoA, conflict-free).
+//   Phase A (per 32 model points): every lane transforms one point and reads ONE 16-byte brick
+//     record of the eps-dilated voxel grid (64-bit occupancy mask + rank base).  Lanes whose
+//     cell is occupied are compacted (ballot + popc rank) into a per-warp shared-memory queue that
+//     runs ACROSS rounds, in model-point order.
+//   Phase B (queue nearly full, or end of the model):
+//     1. 32 lanes fetch the candidate-list offsets of 32 queued queries at once;
+//     2. 8-lane groups scan one queued query each: the float4 candidate records of a query are
+//        read by adjacent lanes (coalesced), the nearest is found with redux.sync min on the bit
+//        pattern of d^2, and an exact d^2 tie falls through to a walk of the reference kd-tree so
+//        that it is broken the way kdtree.h:416-428 breaks it;
+//     3. 32 lanes fetch the matched scene points' normal + class probability, apply the
+//        30-degree test and accumulate the class probabilities in queue order == model-point
+//        order, which makes the LCP bit-identical to the reference's sequential fp32 sum.
+// All memory-dependent steps are batched 32 wide, so the latency chain
+// brick -> offsets -> candidates -> attributes is paid once per drain, not once per model point.
 #include "stocs_ctx.h"
 
 using namespace stocsm;
 
 namespace {
 
-constexpr int kWarps = 8;          // warps per CTA
-constexpr int kGroup = 8;          // lanes cooperating on one NN query
+#ifndef SCORE_GROUP
+#define SCORE_GROUP 8
+#endif
+#ifndef SCORE_QUEUE
+#define SCORE_QUEUE 128
+#endif
+#ifndef SCORE_MIN_BLOCKS
+#define SCORE_MIN_BLOCKS 5
+#endif
+constexpr int kWarps = 8;           // warps per CTA
+constexpr int kGroup = SCORE_GROUP; // lanes cooperating on one NN query
 constexpr int kGroupsPerWarp = 32 / kGroup;
+constexpr int kQueue = SCORE_QUEUE; // queued queries per warp
+constexpr int kQueueArrays = 6;     // qx qy qz a0 a1 pi
 
 struct ScoreArgs {
+  const uint4* __restrict__ bricks;
+  const uint32_t* __restrict__ starts;
   const float4* __restrict__ cand;
-  const uint32_t* __restrict__ cell_start;
   const float4* __restrict__ sattr;
-  const float* __restrict__ model;   // SoA 6*Mpad
+  const float* __restrict__ model;   // 7*Mpad floats: float4 positions, then nx[], ny[], nz[]
   const KdNodeDev* __restrict__ kd_nodes;
   const float4* __restrict__ kd_pts;
   const float* __restrict__ T;
@@ -40,12 +59,6 @@ struct ScoreArgs {
   GridDesc g;
   int M, Mpad;
   float sq_eps, dot_thr;
-};
-
-struct HitEntry {
-  float x, y, z;
-  uint32_t start, count;
-  int result;
 };
 
 // kdtree.h:394-459 on the device (tie path only).
@@ -92,106 +105,92 @@ __device__ __noinline__ int kd_query_dev(const KdNodeDev* __restrict__ nodes, co
   return cl_id;
 }
 
-__global__ void __launch_bounds__(kWarps * 32) score_lcp_kernel(ScoreArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* s_model = reinterpret_cast<float*>(smem_raw);
-  const int Mpad = a.Mpad;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  HitEntry* s_q = reinterpret_cast<HitEntry*>(s_model + 6 * Mpad) + warp * 32;
-  for (int i = threadIdx.x; i < 6 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
-  __syncthreads();
-  const float* mpx = s_model;
-  const float* mpy = mpx + Mpad;
-  const float* mpz = mpy + Mpad;
-  const float* mnx = mpz + Mpad;
-  const float* mny = mnx + Mpad;
-  const float* mnz = mny + Mpad;
+struct WarpQueue {
+  float* qx; float* qy; float* qz;
+  uint32_t* a0;   // occupied-cell rank -> candidate offset -> matched scene index (or -1)
+  uint32_t* a1;   // candidate count
+  uint32_t* pi;   // model point index
+};
 
-  const int sub = lane % kGroup;
-  const int grp = lane / kGroup;
-  const unsigned gmask = ((kGroup == 32) ? 0xffffffffu : ((1u << kGroup) - 1u)) << (grp * kGroup);
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const float ox = a.g.ox, oy = a.g.oy, oz = a.g.oz, inv = a.g.inv_cell;
-  const float fnx = (float)a.g.nx, fny = (float)a.g.ny, fnz = (float)a.g.nz;
-  const int gnx = a.g.nx, gny = a.g.ny;
-  const int M = a.M;
+struct Acc { float acc; int inl; unsigned long long ties; };
+
+__device__ __forceinline__ void drain_queue(const ScoreArgs& a, const WarpQueue& q, int qn, int lane, int sub, int grp,
+                                            const float4& c0, const float4& c1, const float4& c2,
+                                            const float* __restrict__ mnx, const float* __restrict__ mny,
+                                            const float* __restrict__ mnz, Acc& r) {
+  __syncwarp();
+  // 1. candidate-list offsets, 32 queries at a time
+  for (int e = lane; e < qn; e += 32) {
+    const uint32_t k = q.a0[e];
+    const uint32_t s = __ldg(a.starts + k);
+    const uint32_t t = __ldg(a.starts + k + 1);
+    q.a0[e] = s;
+    q.a1[e] = t - s;
+  }
+  __syncwarp();
+  // 2. nearest neighbour within eps: kGroupsPerWarp queries per trip, one per kGroup-lane group.
+  //    Warp-synchronous (the trip count is warp-uniform, every collective uses the full mask:
+  //    sub-warp masks would serialise the groups); the first candidate of the NEXT trip's query
+  //    is fetched before the current one is reduced.
   const float sq_eps = a.sq_eps;
-  unsigned long long ties = 0;
-
-  long long h = 0;
-  if (lane == 0) h = (long long)atomicAdd(a.work_counter, 1ull);
-  h = __shfl_sync(0xffffffffu, h, 0);
-  while (h < a.H) {
-    long long h_next = 0;
-    if (lane == 0) h_next = (long long)atomicAdd(a.work_counter, 1ull);
-    const float4* Tp = reinterpret_cast<const float4*>(a.T + 16 * h);
-    const float4 c0 = __ldg(Tp), c1 = __ldg(Tp + 1), c2 = __ldg(Tp + 2), c3 = __ldg(Tp + 3);
-    float acc = 0.f;
-    int inl = 0;
-    for (int base = 0; base < M; base += 32) {
-      const int i = base + lane;
-      const float px = mpx[i], py = mpy[i], pz = mpz[i];
-      // (mat * p.homogeneous()).head<3>()  -- see stocs_math.h xform_point
-      const float qx = ((c0.x * px + c1.x * py) + c2.x * pz) + c3.x;
-      const float qy = ((c0.y * px + c1.y * py) + c2.y * pz) + c3.y;
-      const float qz = ((c0.z * px + c1.z * py) + c2.z * pz) + c3.z;
-      const float fx = (qx - ox) * inv, fy = (qy - oy) * inv, fz = (qz - oz) * inv;
-      const bool inb = (i < M) && (fx >= 0.f) && (fx < fnx) && (fy >= 0.f) && (fy < fny) && (fz >= 0.f) && (fz < fnz);
-      uint32_t start = 0, cnt = 0;
-      if (inb) {
-        const uint32_t cell = ((uint32_t)(int)fz * (uint32_t)gny + (uint32_t)(int)fy) * (uint32_t)gnx + (uint32_t)(int)fx;
-        start = __ldg(a.cell_start + cell);
-        cnt = __ldg(a.cell_start + cell + 1) - start;
+  const int gshift = grp * kGroup;
+  float nx_x = 0.f, nx_y = 0.f, nx_z = 0.f;
+  uint32_t nx_s = 0, nx_c = 0;
+  float4 nx_cand = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (grp < qn) {
+    nx_x = q.qx[grp]; nx_y = q.qy[grp]; nx_z = q.qz[grp];
+    nx_s = q.a0[grp]; nx_c = q.a1[grp];
+    if ((uint32_t)sub < nx_c) nx_cand = __ldg(a.cand + nx_s + sub);
+  }
+  for (int e0 = 0; e0 < qn; e0 += kGroupsPerWarp) {
+    const int e = e0 + grp;
+    const float ex = nx_x, ey = nx_y, ez = nx_z;
+    const uint32_t es = nx_s, ec = (e < qn) ? nx_c : 0u;
+    float4 c = nx_cand;
+    const int en = e + kGroupsPerWarp;
+    if (en < qn) {
+      nx_x = q.qx[en]; nx_y = q.qy[en]; nx_z = q.qz[en];
+      nx_s = q.a0[en]; nx_c = q.a1[en];
+      if ((uint32_t)sub < nx_c) nx_cand = __ldg(a.cand + nx_s + sub);
+    }
+    uint32_t best = 0x7f800000u;  // +inf
+    int best_idx = -1;
+    bool ltie = false;
+    for (uint32_t j = sub; j < ec; j += kGroup) {
+      if (j != (uint32_t)sub) c = __ldg(a.cand + es + j);
+      const float dx = ex - c.x, dy = ey - c.y, dz = ez - c.z;
+      const float d = dx * dx + (dy * dy + dz * dz);
+      if (d <= sq_eps) {
+        const uint32_t b = __float_as_uint(d);
+        if (b < best) { best = b; best_idx = __float_as_int(c.w); ltie = false; }
+        else if (b == best) { ltie = true; }
       }
-      const bool has = cnt > 0;
-      const unsigned hm = __ballot_sync(0xffffffffu, has);
-      if (hm == 0) continue;
-      const int rank = __popc(hm & lt_mask);
-      if (has) {
-        HitEntry e;
-        e.x = qx; e.y = qy; e.z = qz; e.start = start; e.count = cnt; e.result = -1;
-        s_q[rank] = e;
-      }
-      __syncwarp();
-      const int nh = __popc(hm);
-      for (int e = grp; e < nh; e += kGroupsPerWarp) {
-        const float ex = s_q[e].x, ey = s_q[e].y, ez = s_q[e].z;
-        const uint32_t es = s_q[e].start, ec = s_q[e].count;
-        uint32_t best = 0x7f800000u;  // +inf
-        int best_idx = -1;
-        bool ltie = false;
-        for (uint32_t j = sub; j < ec; j += kGroup) {
-          const float4 c = __ldg(a.cand + es + j);
-          const float dx = ex - c.x, dy = ey - c.y, dz = ez - c.z;
-          const float d = dx * dx + (dy * dy + dz * dz);
-          if (d <= sq_eps) {
-            const uint32_t b = __float_as_uint(d);
-            if (b < best) { best = b; best_idx = __float_as_int(c.w); ltie = false; }
-            else if (b == best) { ltie = true; }
-          }
-        }
-        const uint32_t dmin = __reduce_min_sync(gmask, best);
-        const unsigned winners = __ballot_sync(gmask, best == dmin && best != 0x7f800000u) & gmask;
-        const unsigned lties = __ballot_sync(gmask, ltie && best == dmin) & gmask;
-        int widx = -1;
-        if (winners) {
-          widx = __shfl_sync(gmask, best_idx, __ffs(winners) - 1);
-          if (__popc(winners) > 1 || lties) {
-            if (sub == 0) {
-              widx = kd_query_dev(a.kd_nodes, a.kd_pts, ex, ey, ez, sq_eps);
-              ties++;
-            }
-          }
-        }
-        if (sub == 0) s_q[e].result = widx;
-      }
-      __syncwarp();
-      const int res = has ? s_q[rank].result : -1;
-      bool match = false;
-      float w = 0.f;
+    }
+    uint32_t dmin = best;
+#pragma unroll
+    for (int o = 1; o < kGroup; o <<= 1) dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    const bool iswin = (best == dmin) && (best != 0x7f800000u);
+    const unsigned winners = (__ballot_sync(0xffffffffu, iswin) >> gshift) & ((1u << kGroup) - 1u);
+    const unsigned lties = (__ballot_sync(0xffffffffu, ltie && iswin) >> gshift) & ((1u << kGroup) - 1u);
+    int widx = __shfl_sync(0xffffffffu, best_idx, gshift + (winners ? __ffs(winners) - 1 : 0));
+    if (!winners) widx = -1;
+    if ((__popc(winners) > 1 || lties) && sub == 0) {
+      widx = kd_query_dev(a.kd_nodes, a.kd_pts, ex, ey, ez, sq_eps);
+      r.ties++;
+    }
+    if (sub == 0 && e < qn) q.a0[e] = (uint32_t)widx;
+  }
+  __syncwarp();
+  // 3. normal test + ordered accumulation, 32 queries at a time
+  for (int e0 = 0; e0 < qn; e0 += 32) {
+    const int e = e0 + lane;
+    bool match = false;
+    float w = 0.f;
+    if (e < qn) {
+      const int res = (int)q.a0[e];
       if (res >= 0) {
         const float4 sa = __ldg(a.sattr + res);
+        const int i = (int)q.pi[e];
         const float nx = mnx[i], ny = mny[i], nz = mnz[i];
         // mat.block<3,3>(0,0) * n  -- see stocs_math.h xform_dir
         const float rx = c0.x * nx + (c1.x * ny + c2.x * nz);
@@ -202,22 +201,100 @@ __global__ void __launch_bounds__(kWarps * 32) score_lcp_kernel(ScoreArgs a) {
         match = (dt >= a.dot_thr) && (dt <= 1.0f);
         w = sa.w;
       }
-      unsigned mm = __ballot_sync(0xffffffffu, match);
-      inl += __popc(mm);
-      while (mm) {  // ordered fp32 accumulation == the reference's sequential loop
-        const int b = __ffs(mm) - 1;
-        acc += __shfl_sync(0xffffffffu, w, b);
-        mm &= mm - 1;
+    }
+    unsigned mm = __ballot_sync(0xffffffffu, match);
+    r.inl += __popc(mm);
+    while (mm) {  // ordered fp32 accumulation == the reference's sequential loop
+      const int b = __ffs(mm) - 1;
+      r.acc += __shfl_sync(0xffffffffu, w, b);
+      mm &= mm - 1;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kernel(ScoreArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_model = reinterpret_cast<float*>(smem_raw);
+  const int Mpad = a.Mpad;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_model + 7 * Mpad) + warp * (kQueue * kQueueArrays);
+  WarpQueue q;
+  q.qx = reinterpret_cast<float*>(s_queue);
+  q.qy = q.qx + kQueue;
+  q.qz = q.qy + kQueue;
+  q.a0 = s_queue + 3 * kQueue;
+  q.a1 = q.a0 + kQueue;
+  q.pi = q.a1 + kQueue;
+  for (int i = threadIdx.x; i < 7 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
+  __syncthreads();
+  const float4* mp4 = reinterpret_cast<const float4*>(s_model);  // positions as float4 (one LDS.128 per point)
+  const float* mnx = s_model + 4 * Mpad;
+  const float* mny = mnx + Mpad;
+  const float* mnz = mny + Mpad;
+
+  const int sub = lane % kGroup;
+  const int grp = lane / kGroup;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const float ox = a.g.ox, oy = a.g.oy, oz = a.g.oz, inv = a.g.inv_cell;
+  const unsigned gnx = (unsigned)a.g.nx, gny = (unsigned)a.g.ny, gnz = (unsigned)a.g.nz;
+  const int nbx = a.g.nbx, nby = a.g.nby;
+  const int M = a.M;
+  Acc r;
+  r.ties = 0;
+
+  long long h = 0;
+  if (lane == 0) h = (long long)atomicAdd(a.work_counter, 1ull);
+  h = __shfl_sync(0xffffffffu, h, 0);
+  while (h < a.H) {
+    long long h_next = 0;
+    if (lane == 0) h_next = (long long)atomicAdd(a.work_counter, 1ull);
+    const float4* Tp = reinterpret_cast<const float4*>(a.T + 16 * h);
+    const float4 c0 = __ldg(Tp), c1 = __ldg(Tp + 1), c2 = __ldg(Tp + 2), c3 = __ldg(Tp + 3);
+    r.acc = 0.f;
+    r.inl = 0;
+    int qn = 0;
+    // one loop, one drain call site: u-th half-round of 32 points per trip
+    for (int base = 0; base < M; base += 32) {
+      const int i = base + lane;
+      const float4 mp = mp4[i];
+      const float px = mp.x, py = mp.y, pz = mp.z;
+      // (mat * p.homogeneous()).head<3>()  -- see stocs_math.h xform_point
+      const float qx = ((c0.x * px + c1.x * py) + c2.x * pz) + c3.x;
+      const float qy = ((c0.y * px + c1.y * py) + c2.y * pz) + c3.y;
+      const float qz = ((c0.z * px + c1.z * py) + c2.z * pz) + c3.z;
+      // floor to int saturates (NaN -> 0 lands in a border cell; the d^2 tests reject NaN anyway)
+      const int ix = __float2int_rd((qx - ox) * inv), iy = __float2int_rd((qy - oy) * inv),
+                iz = __float2int_rd((qz - oz) * inv);
+      const bool inb = (i < M) && ((unsigned)ix < gnx) && ((unsigned)iy < gny) && ((unsigned)iz < gnz);
+      const int bit = ((iz & 3) << 4) | ((iy & 3) << 2) | (ix & 3);
+      uint4 br = make_uint4(0u, 0u, 0u, 0u);
+      if (inb) br = __ldg(a.bricks + ((iz >> 2) * nby + (iy >> 2)) * nbx + (ix >> 2));
+      const unsigned long long mask = ((unsigned long long)br.y << 32) | br.x;
+      const bool has = (mask >> bit) & 1ull;
+      const unsigned hm = __ballot_sync(0xffffffffu, has);
+      if (hm) {
+        if (has) {
+          const int slot = qn + __popc(hm & lt_mask);
+          q.qx[slot] = qx; q.qy[slot] = qy; q.qz[slot] = qz;
+          q.a0[slot] = br.z + (uint32_t)__popcll(mask & ((1ull << bit) - 1ull));
+          q.pi[slot] = (uint32_t)i;
+        }
+        qn += __popc(hm);
       }
-      __syncwarp();
+      if (qn > kQueue - 32 || (base + 32 >= M && qn > 0)) {
+        drain_queue(a, q, qn, lane, sub, grp, c0, c1, c2, mnx, mny, mnz, r);
+        qn = 0;
+      }
     }
     if (lane == 0) {
-      a.lcp[h] = acc / (float)M;
-      if (a.inl) a.inl[h] = inl;
+      a.lcp[h] = r.acc / (float)M;
+      if (a.inl) a.inl[h] = r.inl;
     }
     h = __shfl_sync(0xffffffffu, h_next, 0);
   }
-  if (ties) atomicAdd(a.tie_counter, ties);
+  if (r.ties) atomicAdd(a.tie_counter, r.ties);
 }
 
 __global__ void fmad_selftest_kernel(float a, float b, float c, float* out) { out[0] = a * b + c; }
@@ -240,8 +317,9 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
                        cudaStream_t st, bool time_it) {
   if (H <= 0) return STOCS_OK;
   ScoreArgs a;
+  a.bricks = ctx->d_bricks.as<uint4>();
+  a.starts = ctx->d_cell_start.as<uint32_t>();
   a.cand = ctx->d_cand.as<float4>();
-  a.cell_start = ctx->d_cell_start.as<uint32_t>();
   a.sattr = ctx->d_sattr.as<float4>();
   a.model = ctx->d_model.as<float>();
   a.kd_nodes = ctx->d_kd_nodes.as<KdNodeDev>();
@@ -249,7 +327,6 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.T = d_T;
   a.lcp = d_lcp;
   a.inl = d_inl;
-  STOCS_CUDA(ctx, ctx->d_small.ensure(256));
   unsigned long long* ctr = (unsigned long long*)(ctx->d_small.as<char>() + 192);
   a.work_counter = ctr;
   a.tie_counter = ctr + 1;
@@ -259,7 +336,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.Mpad = ctx->Mpad;
   a.sq_eps = ctx->eps * ctx->eps;
   a.dot_thr = ctx->dot_thr;
-  size_t smem = (size_t)6 * ctx->Mpad * 4 + (size_t)kWarps * 32 * sizeof(HitEntry);
+  size_t smem = (size_t)7 * ctx->Mpad * 4 + (size_t)kWarps * kQueue * kQueueArrays * 4;
   static bool attr_set = false;
   if (!attr_set) {
     STOCS_CUDA(ctx, cudaFuncSetAttribute(score_lcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -38,7 +38,9 @@ struct GridDesc {
   float ox, oy, oz;   // origin (lower corner of cell 0)
   float inv_cell;     // 1 / cell edge
   int nx, ny, nz;
-  uint32_t ncells;
+  int nbx, nby, nbz;  // bricks of 4x4x4 cells
+  uint32_t nbricks;
+  uint32_t ncells;    // nbricks * 64 (brick-major numbering)
 };
 
 struct PpfTableDesc {
@@ -66,7 +68,7 @@ struct stocs_b200_ctx {
   int M = 0, Mpad = 0;
   float cm[3] = {0, 0, 0};
   std::vector<float> h_mpos, h_mnrm;  // centred positions, normals (M*3)
-  DevBuf d_model;                      // SoA 6*Mpad floats: px,py,pz,nx,ny,nz
+  DevBuf d_model;                      // 7*Mpad floats: float4 positions, then nx[], ny[], nz[]
   DevBuf d_mpos4;                      // float4 (x,y,z,0) centred
   DevBuf d_mnrm4;                      // float4 (nx,ny,nz,0)
 
@@ -78,7 +80,8 @@ struct stocs_b200_ctx {
   DevBuf d_sattr;                      // float4 (nx,ny,nz,class probability)
   DevBuf d_spix;                       // int2 (row, col)
   GridDesc grid{};
-  DevBuf d_cell_start;                 // uint32[ncells+1]
+  DevBuf d_bricks;                     // uint4 {mask lo, mask hi, first occupied-cell rank, 0} per brick
+  DevBuf d_cell_start;                 // uint32[occupied cells + 1]: candidate offsets
   DevBuf d_cand;                       // float4 (x,y,z,bits(idx)) replicated per dilated cell
   int64_t ncand = 0;
   DevBuf d_kd_nodes, d_kd_pts;         // reference kd-tree for exact-tie resolution
