@@ -135,7 +135,7 @@ int stocs_b200_backproject(stocs_b200_ctx* ctx, const uint16_t* depth, const uin
 int stocs_b200_upload_model(stocs_b200_ctx* ctx, const float* pos3, const float* nrm3, int M) {
   if (!ctx) return STOCS_E_ARG;
   if (!pos3 || !nrm3 || M <= 0) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_model: bad argument");
-  if (M > 6144) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_model: at most 6144 model points are supported");
+  if (M > 5120) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_model: at most 5120 model points are supported");
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   STOCS_CUDA(ctx, ctx->d_tmp.ensure((size_t)M * 12));
@@ -150,13 +150,13 @@ int stocs_b200_upload_model(stocs_b200_ctx* ctx, const float* pos3, const float*
   STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_mpos.data(), ctx->d_tmp2.p, (size_t)M * 12, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   const int Mpad = ((M + 63) / 64) * 64;  // the scoring kernel consumes 64 points per iteration
-  // scoring-kernel layout: float4 centred positions (4*Mpad floats), then normals as SoA
-  std::vector<float> soa((size_t)7 * Mpad, 0.f);
+  // scoring-kernel layout: float4 centred positions (4*Mpad floats), then float4 normals
+  std::vector<float> soa((size_t)8 * Mpad, 0.f);
   std::vector<float> n4((size_t)4 * M, 0.f);
   for (int i = 0; i < M; ++i)
     for (int k = 0; k < 3; ++k) {
       soa[4 * (size_t)i + k] = ctx->h_mpos[3 * (size_t)i + k];
-      soa[(size_t)(4 + k) * Mpad + i] = nrm3[3 * (size_t)i + k];
+      soa[4 * (size_t)(Mpad + i) + k] = nrm3[3 * (size_t)i + k];
       n4[4 * (size_t)i + k] = nrm3[3 * (size_t)i + k];
     }
   STOCS_CUDA(ctx, ctx->d_model.ensure(soa.size() * 4));

@@ -103,15 +103,27 @@ __device__ __forceinline__ CellRange dilated_range(const GridDesc& g, float4 p, 
   return c;
 }
 
+// squared distance from p to the box of cell (x,y,z): a point joins the cell's list only when it
+// is within r of the box (Euclidean dilation; the per-axis ranges above are its bounding box)
+__device__ __forceinline__ bool near_cell(const GridDesc& g, float4 p, float r2, int x, int y, int z) {
+  const float cell = 1.0f / g.inv_cell;
+  const float lx = g.ox + (float)x * cell, ly = g.oy + (float)y * cell, lz = g.oz + (float)z * cell;
+  const float dx = fmaxf(fmaxf(lx - p.x, p.x - (lx + cell)), 0.f);
+  const float dy = fmaxf(fmaxf(ly - p.y, p.y - (ly + cell)), 0.f);
+  const float dz = fmaxf(fmaxf(lz - p.z, p.z - (lz + cell)), 0.f);
+  return dx * dx + dy * dy + dz * dz <= r2;
+}
+
 __global__ void grid_count_kernel(const float4* __restrict__ pts, int n, GridDesc g, float r,
                                   uint32_t* __restrict__ counts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  CellRange c = dilated_range(g, pts[i], r);
+  const float4 p = pts[i];
+  CellRange c = dilated_range(g, p, r);
   for (int z = c.z0; z <= c.z1; ++z)
     for (int y = c.y0; y <= c.y1; ++y)
       for (int x = c.x0; x <= c.x1; ++x)
-        atomicAdd(&counts[cell_number(g, x, y, z)], 1u);
+        if (near_cell(g, p, r * r, x, y, z)) atomicAdd(&counts[cell_number(g, x, y, z)], 1u);
 }
 
 __global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc g, float r,
@@ -124,6 +136,7 @@ __global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc
   for (int z = c.z0; z <= c.z1; ++z)
     for (int y = c.y0; y <= c.y1; ++y)
       for (int x = c.x0; x <= c.x1; ++x) {
+        if (!near_cell(g, p, r * r, x, y, z)) continue;
         size_t cell = cell_number(g, x, y, z);
         uint32_t slot = cell_start[cell] + atomicAdd(&cursor[cell], 1u);
         cand[slot] = p;

@@ -28,7 +28,7 @@ using namespace stocsm;
 namespace {
 
 #ifndef SCORE_GROUP
-#define SCORE_GROUP 8
+#define SCORE_GROUP 4
 #endif
 #ifndef SCORE_QUEUE
 #define SCORE_QUEUE 128
@@ -36,18 +36,20 @@ namespace {
 #ifndef SCORE_MIN_BLOCKS
 #define SCORE_MIN_BLOCKS 5
 #endif
-constexpr int kWarps = 8;           // warps per CTA
+#ifndef SCORE_WARPS
+#define SCORE_WARPS 8
+#endif
+constexpr int kWarps = SCORE_WARPS; // warps per CTA
 constexpr int kGroup = SCORE_GROUP; // lanes cooperating on one NN query
 constexpr int kGroupsPerWarp = 32 / kGroup;
 constexpr int kQueue = SCORE_QUEUE; // queued queries per warp
-constexpr int kQueueArrays = 6;     // qx qy qz a0 a1 pi
 
 struct ScoreArgs {
   const uint4* __restrict__ bricks;
   const uint32_t* __restrict__ starts;
   const float4* __restrict__ cand;
   const float4* __restrict__ sattr;
-  const float* __restrict__ model;   // 7*Mpad floats: float4 positions, then nx[], ny[], nz[]
+  const float* __restrict__ model;   // 8*Mpad floats: float4 positions, then float4 normals
   const KdNodeDev* __restrict__ kd_nodes;
   const float4* __restrict__ kd_pts;
   const float* __restrict__ T;
@@ -105,19 +107,18 @@ __device__ __noinline__ int kd_query_dev(const KdNodeDev* __restrict__ nodes, co
   return cl_id;
 }
 
-struct WarpQueue {
-  float* qx; float* qy; float* qz;
-  uint32_t* a0;   // occupied-cell rank -> candidate offset -> matched scene index (or -1)
-  uint32_t* a1;   // candidate count
-  uint32_t* pi;   // model point index
+struct WarpQueue {   // one per warp, static shared memory (single base register, constant offsets)
+  float qx[kQueue], qy[kQueue], qz[kQueue];
+  uint32_t a0[kQueue];   // occupied-cell rank -> candidate offset -> matched scene index (or -1)
+  uint32_t a1[kQueue];   // candidate count
+  uint32_t pi[kQueue];   // model point index
 };
 
 struct Acc { float acc; int inl; unsigned long long ties; };
 
-__device__ __forceinline__ void drain_queue(const ScoreArgs& a, const WarpQueue& q, int qn, int lane, int sub, int grp,
+__device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, int qn, int lane, int sub, int grp,
                                             const float4& c0, const float4& c1, const float4& c2,
-                                            const float* __restrict__ mnx, const float* __restrict__ mny,
-                                            const float* __restrict__ mnz, Acc& r) {
+                                            const float4* __restrict__ mn4, Acc& r) {
   __syncwarp();
   // 1. candidate-list offsets, 32 queries at a time
   for (int e = lane; e < qn; e += 32) {
@@ -191,7 +192,8 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, const WarpQueue&
       if (res >= 0) {
         const float4 sa = __ldg(a.sattr + res);
         const int i = (int)q.pi[e];
-        const float nx = mnx[i], ny = mny[i], nz = mnz[i];
+        const float4 mn = mn4[i];
+        const float nx = mn.x, ny = mn.y, nz = mn.z;
         // mat.block<3,3>(0,0) * n  -- see stocs_math.h xform_dir
         const float rx = c0.x * nx + (c1.x * ny + c2.x * nz);
         const float ry = c0.y * nx + (c1.y * ny + c2.y * nz);
@@ -219,20 +221,12 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   const int Mpad = a.Mpad;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_model + 7 * Mpad) + warp * (kQueue * kQueueArrays);
-  WarpQueue q;
-  q.qx = reinterpret_cast<float*>(s_queue);
-  q.qy = q.qx + kQueue;
-  q.qz = q.qy + kQueue;
-  q.a0 = s_queue + 3 * kQueue;
-  q.a1 = q.a0 + kQueue;
-  q.pi = q.a1 + kQueue;
-  for (int i = threadIdx.x; i < 7 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
+  __shared__ WarpQueue s_queues[kWarps];
+  WarpQueue& q = s_queues[warp];
+  for (int i = threadIdx.x; i < 8 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
   __syncthreads();
   const float4* mp4 = reinterpret_cast<const float4*>(s_model);  // positions as float4 (one LDS.128 per point)
-  const float* mnx = s_model + 4 * Mpad;
-  const float* mny = mnx + Mpad;
-  const float* mnz = mny + Mpad;
+  const float4* mn4 = mp4 + Mpad;                                 // normals as float4
 
   const int sub = lane % kGroup;
   const int grp = lane / kGroup;
@@ -284,7 +278,7 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
         qn += __popc(hm);
       }
       if (qn > kQueue - 32 || (base + 32 >= M && qn > 0)) {
-        drain_queue(a, q, qn, lane, sub, grp, c0, c1, c2, mnx, mny, mnz, r);
+        drain_queue(a, q, qn, lane, sub, grp, c0, c1, c2, mn4, r);
         qn = 0;
       }
     }
@@ -336,7 +330,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.Mpad = ctx->Mpad;
   a.sq_eps = ctx->eps * ctx->eps;
   a.dot_thr = ctx->dot_thr;
-  size_t smem = (size_t)7 * ctx->Mpad * 4 + (size_t)kWarps * kQueue * kQueueArrays * 4;
+  size_t smem = (size_t)8 * ctx->Mpad * 4;  // + static: kWarps queues
   static bool attr_set = false;
   if (!attr_set) {
     STOCS_CUDA(ctx, cudaFuncSetAttribute(score_lcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -68,7 +68,7 @@ struct stocs_b200_ctx {
   int M = 0, Mpad = 0;
   float cm[3] = {0, 0, 0};
   std::vector<float> h_mpos, h_mnrm;  // centred positions, normals (M*3)
-  DevBuf d_model;                      // 7*Mpad floats: float4 positions, then nx[], ny[], nz[]
+  DevBuf d_model;                      // 8*Mpad floats: float4 positions, then float4 normals
   DevBuf d_mpos4;                      // float4 (x,y,z,0) centred
   DevBuf d_mnrm4;                      // float4 (nx,ny,nz,0)
 
