@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libstocs_b200.so (include/stocs_b200.h): context, uploads, host-buffer
 // wrappers around the kernels.  No CPU fallback anywhere: every compute entry point launches
 // sm_100a kernels, and stocs_b200_create refuses to run without a compute-capability-10 device.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -77,7 +78,7 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->d_model, &ctx->d_mpos4, &ctx->d_mnrm4, &ctx->d_spos4, &ctx->d_sattr, &ctx->d_spix,
-                    &ctx->d_bricks, &ctx->d_cell_start, &ctx->d_cand, &ctx->d_kd_nodes, &ctx->d_kd_pts, &ctx->d_ppf_bin_start,
+                    &ctx->d_coarse, &ctx->d_bricks, &ctx->d_cell_start, &ctx->d_cand, &ctx->d_kd_nodes, &ctx->d_kd_pts, &ctx->d_ppf_bin_start,
                     &ctx->d_ppf_pairs, &ctx->d_ppf_keybits, &ctx->d_T, &ctx->d_lcp, &ctx->d_inl, &ctx->d_work,
                     &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_small};
   for (DevBuf* b : bufs) b->release();
@@ -152,6 +153,8 @@ int stocs_b200_upload_model(stocs_b200_ctx* ctx, const float* pos3, const float*
   const int Mpad = ((M + 63) / 64) * 64;  // the scoring kernel consumes 64 points per iteration
   // scoring-kernel layout: float4 centred positions (4*Mpad floats), then float4 normals
   std::vector<float> soa((size_t)8 * Mpad, 0.f);
+  for (int i = M; i < Mpad; ++i)   // padding points are NaN: they fall outside every grid
+    for (int k = 0; k < 3; ++k) soa[4 * (size_t)i + k] = std::nanf("");
   std::vector<float> n4((size_t)4 * M, 0.f);
   for (int i = 0; i < M; ++i)
     for (int k = 0; k < 3; ++k) {

@@ -163,10 +163,14 @@ __global__ void brick_mask_kernel(const uint32_t* __restrict__ cell_start, uint3
 // brick table {mask lo, mask hi, index of the brick's first occupied cell, 0} + compact starts
 __global__ void brick_table_kernel(const uint32_t* __restrict__ cell_start, const unsigned long long* __restrict__ masks,
                                    const uint32_t* __restrict__ occ_scan, uint32_t nbricks, uint32_t total_cand,
-                                   uint4* __restrict__ bricks, uint32_t* __restrict__ starts) {
+                                   uint4* __restrict__ bricks, uint32_t* __restrict__ starts,
+                                   uint32_t* __restrict__ coarse) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long mb = (b < nbricks) ? masks[b] : 0ull;
+  const unsigned cw = __ballot_sync(0xffffffffu, mb != 0ull);   // blockDim is a multiple of 32
+  if ((threadIdx.x & 31) == 0 && (b >> 5) < (nbricks + 31) / 32) coarse[b >> 5] = cw;
   if (b >= nbricks) return;
-  const unsigned long long m = masks[b];
+  const unsigned long long m = mb;
   const uint32_t base = occ_scan[b];
   bricks[b] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), base, 0u);
   unsigned long long r = m;
@@ -309,7 +313,9 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   g.ncells = g.nbricks * 64u;
   ctx->grid = g;
   // dilation radius: eps plus a margin that absorbs the rounding of both cell-index computations
-  const float r = (float)(eps * (1.0 + 1.0 / 1024.0) + cell / 1024.0);
+  // (the scoring kernel locates cells through an FMA-evaluated affine map whose error is a few
+  // 1e-5 cells at these grid sizes; the margin is cell/256 + eps/256)
+  const float r = (float)(eps * (1.0 + 1.0 / 256.0) + cell / 256.0);
 
   size_t nc1 = (size_t)g.ncells + 1;
   DevBuf d_dense;  // dense per-cell starts (temporary)
@@ -345,9 +351,11 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, cudaMemcpyAsync(&n_occ, d_occ_scan.as<uint32_t>() + g.nbricks, 4, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   STOCS_CUDA(ctx, ctx->d_bricks.ensure((size_t)g.nbricks * 16));
+  STOCS_CUDA(ctx, ctx->d_coarse.ensure((size_t)((g.nbricks + 31) / 32) * 4));
   STOCS_CUDA(ctx, ctx->d_cell_start.ensure((size_t)(n_occ + 1) * 4));
   brick_table_kernel<<<bb, 128, 0, st>>>(dense_start, d_masks.as<unsigned long long>(), d_occ_scan.as<uint32_t>(), g.nbricks,
-                                         total, ctx->d_bricks.as<uint4>(), ctx->d_cell_start.as<uint32_t>());
+                                         total, ctx->d_bricks.as<uint4>(), ctx->d_cell_start.as<uint32_t>(),
+                                         ctx->d_coarse.as<uint32_t>());
   STOCS_CUDA(ctx, cudaGetLastError());
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   d_dense.release(); d_masks.release(); d_occ.release(); d_occ_scan.release();

@@ -31,13 +31,13 @@ namespace {
 #define SCORE_GROUP 4
 #endif
 #ifndef SCORE_QUEUE
-#define SCORE_QUEUE 128
+#define SCORE_QUEUE 96
 #endif
 #ifndef SCORE_MIN_BLOCKS
-#define SCORE_MIN_BLOCKS 5
+#define SCORE_MIN_BLOCKS 2
 #endif
 #ifndef SCORE_WARPS
-#define SCORE_WARPS 8
+#define SCORE_WARPS 32
 #endif
 constexpr int kWarps = SCORE_WARPS; // warps per CTA
 constexpr int kGroup = SCORE_GROUP; // lanes cooperating on one NN query
@@ -46,6 +46,8 @@ constexpr int kQueue = SCORE_QUEUE; // queued queries per warp
 
 struct ScoreArgs {
   const uint4* __restrict__ bricks;
+  const uint32_t* __restrict__ coarse;   // 1 bit per brick: any occupied cell inside
+  int coarse_words;                      // words of `coarse` staged in shared memory (0: read from global)
   const uint32_t* __restrict__ starts;
   const float4* __restrict__ cand;
   const float4* __restrict__ sattr;
@@ -107,24 +109,48 @@ __device__ __noinline__ int kd_query_dev(const KdNodeDev* __restrict__ nodes, co
   return cl_id;
 }
 
+// Streaming 16-byte load that does not allocate in L1 (candidate and attribute records are read
+// once per query; keeping them out of L1 leaves it to the brick table and the spill slots).
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+#ifdef SCORE_STREAM_CAND
+#define LD_CAND ld_stream
+#else
+#define LD_CAND __ldg
+#endif
+
 struct WarpQueue {   // one per warp, static shared memory (single base register, constant offsets)
-  float qx[kQueue], qy[kQueue], qz[kQueue];
+  float T[12];           // exact transform: columns 0..2 (rotation) and 3 (translation), 3 rows each
+  float G[12];           // the same map into grid-cell coordinates (FMA-evaluated, phase A only)
+  float qx[kQueue], qy[kQueue], qz[kQueue];   // exact transformed points (filled by drain step 1)
   uint32_t a0[kQueue];   // occupied-cell rank -> candidate offset -> matched scene index (or -1)
   uint32_t a1[kQueue];   // candidate count
   uint32_t pi[kQueue];   // model point index
 };
 
-struct Acc { float acc; int inl; unsigned long long ties; };
+struct Acc { float acc; int inl; unsigned ties; };
 
-__device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, int qn, int lane, int sub, int grp,
-                                            const float4& c0, const float4& c1, const float4& c2,
-                                            const float4* __restrict__ mn4, Acc& r) {
+__device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, int qn, int lane,
+                                            const float4* __restrict__ mp4, const float4* __restrict__ mn4, Acc& r) {
+  const int sub = lane % kGroup;
+  const int grp = lane / kGroup;
   __syncwarp();
-  // 1. candidate-list offsets, 32 queries at a time
+  // 1. 32 queries at a time: candidate-list offsets, and the EXACT transformed point
+  //    (mat * p.homogeneous()).head<3>() in the reference's evaluation order (stocs_math.h
+  //    xform_point) -- phase A only located the cell.
   for (int e = lane; e < qn; e += 32) {
     const uint32_t k = q.a0[e];
     const uint32_t s = __ldg(a.starts + k);
     const uint32_t t = __ldg(a.starts + k + 1);
+    const float4 mp = mp4[q.pi[e]];
+    q.qx[e] = ((q.T[0] * mp.x + q.T[3] * mp.y) + q.T[6] * mp.z) + q.T[9];
+    q.qy[e] = ((q.T[1] * mp.x + q.T[4] * mp.y) + q.T[7] * mp.z) + q.T[10];
+    q.qz[e] = ((q.T[2] * mp.x + q.T[5] * mp.y) + q.T[8] * mp.z) + q.T[11];
     q.a0[e] = s;
     q.a1[e] = t - s;
   }
@@ -135,30 +161,21 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
   //    is fetched before the current one is reduced.
   const float sq_eps = a.sq_eps;
   const int gshift = grp * kGroup;
-  float nx_x = 0.f, nx_y = 0.f, nx_z = 0.f;
-  uint32_t nx_s = 0, nx_c = 0;
   float4 nx_cand = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (grp < qn) {
-    nx_x = q.qx[grp]; nx_y = q.qy[grp]; nx_z = q.qz[grp];
-    nx_s = q.a0[grp]; nx_c = q.a1[grp];
-    if ((uint32_t)sub < nx_c) nx_cand = __ldg(a.cand + nx_s + sub);
-  }
+  if (grp < qn && (uint32_t)sub < q.a1[grp]) nx_cand = LD_CAND(a.cand + q.a0[grp] + sub);
   for (int e0 = 0; e0 < qn; e0 += kGroupsPerWarp) {
     const int e = e0 + grp;
-    const float ex = nx_x, ey = nx_y, ez = nx_z;
-    const uint32_t es = nx_s, ec = (e < qn) ? nx_c : 0u;
     float4 c = nx_cand;
     const int en = e + kGroupsPerWarp;
-    if (en < qn) {
-      nx_x = q.qx[en]; nx_y = q.qy[en]; nx_z = q.qz[en];
-      nx_s = q.a0[en]; nx_c = q.a1[en];
-      if ((uint32_t)sub < nx_c) nx_cand = __ldg(a.cand + nx_s + sub);
-    }
+    if (en < qn && (uint32_t)sub < q.a1[en]) nx_cand = LD_CAND(a.cand + q.a0[en] + sub);
+    float ex = 0.f, ey = 0.f, ez = 0.f;
+    uint32_t es = 0, ec = 0;
+    if (e < qn) { ex = q.qx[e]; ey = q.qy[e]; ez = q.qz[e]; es = q.a0[e]; ec = q.a1[e]; }
     uint32_t best = 0x7f800000u;  // +inf
     int best_idx = -1;
     bool ltie = false;
     for (uint32_t j = sub; j < ec; j += kGroup) {
-      if (j != (uint32_t)sub) c = __ldg(a.cand + es + j);
+      if (j != (uint32_t)sub) c = LD_CAND(a.cand + es + j);
       const float dx = ex - c.x, dy = ey - c.y, dz = ez - c.z;
       const float d = dx * dx + (dy * dy + dz * dz);
       if (d <= sq_eps) {
@@ -190,14 +207,12 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
     if (e < qn) {
       const int res = (int)q.a0[e];
       if (res >= 0) {
-        const float4 sa = __ldg(a.sattr + res);
-        const int i = (int)q.pi[e];
-        const float4 mn = mn4[i];
-        const float nx = mn.x, ny = mn.y, nz = mn.z;
+        const float4 sa = ld_stream(a.sattr + res);
+        const float4 mn = __ldg(mn4 + q.pi[e]);
         // mat.block<3,3>(0,0) * n  -- see stocs_math.h xform_dir
-        const float rx = c0.x * nx + (c1.x * ny + c2.x * nz);
-        const float ry = c0.y * nx + (c1.y * ny + c2.y * nz);
-        const float rz = c0.z * nx + (c1.z * ny + c2.z * nz);
+        const float rx = q.T[0] * mn.x + (q.T[3] * mn.y + q.T[6] * mn.z);
+        const float ry = q.T[1] * mn.x + (q.T[4] * mn.y + q.T[7] * mn.z);
+        const float rz = q.T[2] * mn.x + (q.T[5] * mn.y + q.T[8] * mn.z);
         const float dt = sa.x * rx + (sa.y * ry + sa.z * rz);
         // acos(dt)*180/pi < 30  <=>  dot_thr <= dt <= 1   (threshold found by bisection on the host)
         match = (dt >= a.dot_thr) && (dt <= 1.0f);
@@ -221,65 +236,80 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   const int Mpad = a.Mpad;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  __shared__ WarpQueue s_queues[kWarps];
-  WarpQueue& q = s_queues[warp];
-  for (int i = threadIdx.x; i < 8 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
+  // dynamic shared memory: [model positions float4 x Mpad][coarse bitmap][one WarpQueue per warp]
+  for (int i = threadIdx.x; i < 4 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
+  uint32_t* s_coarse = reinterpret_cast<uint32_t*>(s_model + 4 * Mpad);
+  for (int i = threadIdx.x; i < a.coarse_words; i += blockDim.x) s_coarse[i] = a.coarse[i];
+  const bool coarse_smem = a.coarse_words > 0;
+  WarpQueue& q = reinterpret_cast<WarpQueue*>(s_coarse + ((a.coarse_words + 3) & ~3))[warp];
   __syncthreads();
-  const float4* mp4 = reinterpret_cast<const float4*>(s_model);  // positions as float4 (one LDS.128 per point)
-  const float4* mn4 = mp4 + Mpad;                                 // normals as float4
+  const float4* mp4 = reinterpret_cast<const float4*>(s_model);  // positions as float4 (NaN beyond M)
+  const float4* mn4 = reinterpret_cast<const float4*>(a.model) + Mpad;  // normals stay in global (hits only)
 
-  const int sub = lane % kGroup;
-  const int grp = lane / kGroup;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const float ox = a.g.ox, oy = a.g.oy, oz = a.g.oz, inv = a.g.inv_cell;
-  const unsigned gnx = (unsigned)a.g.nx, gny = (unsigned)a.g.ny, gnz = (unsigned)a.g.nz;
-  const int nbx = a.g.nbx, nby = a.g.nby;
   const int M = a.M;
   Acc r;
   r.ties = 0;
 
-  long long h = 0;
-  if (lane == 0) h = (long long)atomicAdd(a.work_counter, 1ull);
+  int h = 0;
+  if (lane == 0) h = (int)atomicAdd(a.work_counter, 1ull);
   h = __shfl_sync(0xffffffffu, h, 0);
   while (h < a.H) {
-    long long h_next = 0;
-    if (lane == 0) h_next = (long long)atomicAdd(a.work_counter, 1ull);
-    const float4* Tp = reinterpret_cast<const float4*>(a.T + 16 * h);
-    const float4 c0 = __ldg(Tp), c1 = __ldg(Tp + 1), c2 = __ldg(Tp + 2), c3 = __ldg(Tp + 3);
+    int h_next = 0;
+    if (lane == 0) h_next = (int)atomicAdd(a.work_counter, 1ull);
+    // lanes 0..11 fetch the 3x4 transform (column-major 4x4: element (r,c) at c*4+r) and publish
+    // it, with its grid-coordinate version G = inv_cell * (T - origin), to the warp's shared slot
+    if (lane < 12) {
+      const int c = lane / 3, rr = lane - 3 * c;
+      const float t = __ldg(a.T + 16 * (size_t)h + c * 4 + rr);
+      const float o = (rr == 0) ? a.g.ox : (rr == 1 ? a.g.oy : a.g.oz);
+      q.T[lane] = t;
+      q.G[lane] = (c == 3) ? (t - o) * a.g.inv_cell : t * a.g.inv_cell;
+    }
+    __syncwarp();
+    float g0 = q.G[0], g1 = q.G[1], g2 = q.G[2], g3 = q.G[3], g4 = q.G[4], g5 = q.G[5];
+    float g6 = q.G[6], g7 = q.G[7], g8 = q.G[8], g9 = q.G[9], g10 = q.G[10], g11 = q.G[11];
     r.acc = 0.f;
     r.inl = 0;
     int qn = 0;
-    // one loop, one drain call site: u-th half-round of 32 points per trip
     for (int base = 0; base < M; base += 32) {
       const int i = base + lane;
       const float4 mp = mp4[i];
-      const float px = mp.x, py = mp.y, pz = mp.z;
-      // (mat * p.homogeneous()).head<3>()  -- see stocs_math.h xform_point
-      const float qx = ((c0.x * px + c1.x * py) + c2.x * pz) + c3.x;
-      const float qy = ((c0.y * px + c1.y * py) + c2.y * pz) + c3.y;
-      const float qz = ((c0.z * px + c1.z * py) + c2.z * pz) + c3.z;
-      // floor to int saturates (NaN -> 0 lands in a border cell; the d^2 tests reject NaN anyway)
-      const int ix = __float2int_rd((qx - ox) * inv), iy = __float2int_rd((qy - oy) * inv),
-                iz = __float2int_rd((qz - oz) * inv);
-      const bool inb = (i < M) && ((unsigned)ix < gnx) && ((unsigned)iy < gny) && ((unsigned)iz < gnz);
+      // Cell coordinates through the fused affine map (explicit FMAs: this value only selects a
+      // cell, the eps-dilation margin of the index absorbs its rounding; the exact point is
+      // recomputed for queued queries).  Float->int floor saturates; NaN (padding) -> 0.
+      const float fx = __fmaf_rn(g0, mp.x, __fmaf_rn(g3, mp.y, __fmaf_rn(g6, mp.z, g9)));
+      const float fy = __fmaf_rn(g1, mp.x, __fmaf_rn(g4, mp.y, __fmaf_rn(g7, mp.z, g10)));
+      const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
+      const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
+      const bool inb = (fx == fx) && ((unsigned)ix < (unsigned)a.g.nx) && ((unsigned)iy < (unsigned)a.g.ny) &&
+                       ((unsigned)iz < (unsigned)a.g.nz);
       const int bit = ((iz & 3) << 4) | ((iy & 3) << 2) | (ix & 3);
       uint4 br = make_uint4(0u, 0u, 0u, 0u);
-      if (inb) br = __ldg(a.bricks + ((iz >> 2) * nby + (iy >> 2)) * nbx + (ix >> 2));
+      if (inb) {
+        // level 0: one bit per 4x4x4 brick (shared memory when it fits) rejects empty space
+        // without touching the brick table
+        const uint32_t bidx = (uint32_t)(((iz >> 2) * a.g.nby + (iy >> 2)) * a.g.nbx + (ix >> 2));
+        const uint32_t cw = coarse_smem ? s_coarse[bidx >> 5] : __ldg(a.coarse + (bidx >> 5));
+        if ((cw >> (bidx & 31)) & 1u) br = __ldg(a.bricks + bidx);
+      }
       const unsigned long long mask = ((unsigned long long)br.y << 32) | br.x;
       const bool has = (mask >> bit) & 1ull;
       const unsigned hm = __ballot_sync(0xffffffffu, has);
       if (hm) {
         if (has) {
           const int slot = qn + __popc(hm & lt_mask);
-          q.qx[slot] = qx; q.qy[slot] = qy; q.qz[slot] = qz;
           q.a0[slot] = br.z + (uint32_t)__popcll(mask & ((1ull << bit) - 1ull));
           q.pi[slot] = (uint32_t)i;
         }
         qn += __popc(hm);
       }
       if (qn > kQueue - 32 || (base + 32 >= M && qn > 0)) {
-        drain_queue(a, q, qn, lane, sub, grp, c0, c1, c2, mn4, r);
+        drain_queue(a, q, qn, lane, mp4, mn4, r);
         qn = 0;
+        // the map is re-read after a drain so that it is not live (in registers) across it
+        g0 = q.G[0]; g1 = q.G[1]; g2 = q.G[2]; g3 = q.G[3]; g4 = q.G[4]; g5 = q.G[5];
+        g6 = q.G[6]; g7 = q.G[7]; g8 = q.G[8]; g9 = q.G[9]; g10 = q.G[10]; g11 = q.G[11];
       }
     }
     if (lane == 0) {
@@ -287,8 +317,9 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
       if (a.inl) a.inl[h] = r.inl;
     }
     h = __shfl_sync(0xffffffffu, h_next, 0);
+    __syncwarp();
   }
-  if (r.ties) atomicAdd(a.tie_counter, r.ties);
+  if (r.ties) atomicAdd(a.tie_counter, (unsigned long long)r.ties);
 }
 
 __global__ void fmad_selftest_kernel(float a, float b, float c, float* out) { out[0] = a * b + c; }
@@ -310,8 +341,12 @@ bool stocs_fmad_selftest(stocs_b200_ctx* ctx) {
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp, int32_t* d_inl,
                        cudaStream_t st, bool time_it) {
   if (H <= 0) return STOCS_OK;
+  if (H >= (1ll << 31)) STOCS_FAIL(ctx, STOCS_E_ARG, "score: at most 2^31-1 hypotheses per call");
   ScoreArgs a;
   a.bricks = ctx->d_bricks.as<uint4>();
+  a.coarse = ctx->d_coarse.as<uint32_t>();
+  const int coarse_words = (int)((ctx->grid.nbricks + 31) / 32);
+  a.coarse_words = (coarse_words * 4 <= 16 * 1024) ? coarse_words : 0;
   a.starts = ctx->d_cell_start.as<uint32_t>();
   a.cand = ctx->d_cand.as<float4>();
   a.sattr = ctx->d_sattr.as<float4>();
@@ -330,12 +365,9 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.Mpad = ctx->Mpad;
   a.sq_eps = ctx->eps * ctx->eps;
   a.dot_thr = ctx->dot_thr;
-  size_t smem = (size_t)8 * ctx->Mpad * 4;  // + static: kWarps queues
-  static bool attr_set = false;
-  if (!attr_set) {
-    STOCS_CUDA(ctx, cudaFuncSetAttribute(score_lcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  size_t smem = (size_t)4 * ctx->Mpad * 4 + (size_t)((a.coarse_words + 3) & ~3) * 4 + (size_t)kWarps * sizeof(WarpQueue);
+  // static (per-warp queues) + dynamic (model, coarse bitmap) may exceed the 48 KB default
+  STOCS_CUDA(ctx, cudaFuncSetAttribute(score_lcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   STOCS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_lcp_kernel, kWarps * 32, smem));
   if (per_sm < 1) STOCS_FAIL(ctx, STOCS_E_ARG, "score: model too large for shared memory");

@@ -80,6 +80,7 @@ struct stocs_b200_ctx {
   DevBuf d_sattr;                      // float4 (nx,ny,nz,class probability)
   DevBuf d_spix;                       // int2 (row, col)
   GridDesc grid{};
+  DevBuf d_coarse;                     // 1 bit per brick: brick has an occupied cell
   DevBuf d_bricks;                     // uint4 {mask lo, mask hi, first occupied-cell rank, 0} per brick
   DevBuf d_cell_start;                 // uint32[occupied cells + 1]: candidate offsets
   DevBuf d_cand;                       // float4 (x,y,z,bits(idx)) replicated per dilated cell
