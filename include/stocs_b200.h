@@ -74,6 +74,12 @@ int stocs_b200_get_centred(stocs_b200_ctx* ctx, float* scene_pos3, float* model_
  * ppf_lookup: number of pairs stored under key4 in the reference's expanded map, -1 if the key is
  * absent; copies up to cap pairs (id1,id2) in the reference's list order. */
 int stocs_b200_ppf_num_pairs(stocs_b200_ctx* ctx, int64_t* own_bin_pairs, int64_t* own_bin_keys);
+/* number of keys of the reference's expanded map (what `ppf_map.size()` prints, src/stocs.cpp:96) */
+int stocs_b200_ppf_num_expanded_keys(stocs_b200_ctx* ctx, int64_t* expanded_keys);
+/* the compact table itself, for the `ppf_map` file written by model_preprocess
+ * (src/model_preprocess.cpp:28-36): per stored pair its own-bin key (4 ints) and (id1,id2),
+ * sorted by (key, id1, id2).  cap = capacity in pairs; *n = number of pairs. */
+int stocs_b200_ppf_export(stocs_b200_ctx* ctx, int32_t* keys4, int32_t* pairs2, int64_t cap, int64_t* n);
 int stocs_b200_ppf_lookup(stocs_b200_ctx* ctx, const int32_t* key4, int32_t* pairs2, int64_t cap,
                           int64_t* count);
 

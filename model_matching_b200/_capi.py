@@ -18,7 +18,8 @@ SYMBOLS = [
     "stocs_b200_abi_version", "stocs_b200_create", "stocs_b200_destroy", "stocs_b200_last_error",
     "stocs_b200_set_params", "stocs_b200_backproject", "stocs_b200_upload_model",
     "stocs_b200_upload_scene", "stocs_b200_get_centroids", "stocs_b200_get_centred",
-    "stocs_b200_ppf_num_pairs", "stocs_b200_ppf_lookup", "stocs_b200_sample_bases",
+    "stocs_b200_ppf_num_pairs", "stocs_b200_ppf_num_expanded_keys", "stocs_b200_ppf_export",
+    "stocs_b200_ppf_lookup", "stocs_b200_sample_bases",
     "stocs_b200_find_congruent", "stocs_b200_fit_transforms", "stocs_b200_score_lcp",
     "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device",
     "stocs_b200_run_pipeline", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
@@ -61,6 +62,8 @@ def lib():
     L.stocs_b200_get_centred.argtypes = [vp, vp, vp]
     L.stocs_b200_ppf_num_pairs.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.stocs_b200_ppf_lookup.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
+    L.stocs_b200_ppf_num_expanded_keys.argtypes = [vp, C.POINTER(i64)]
+    L.stocs_b200_ppf_export.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     L.stocs_b200_sample_bases.argtypes = [vp, u64, u32, i32, vp, vp, vp]
     L.stocs_b200_find_congruent.argtypes = [vp, i32, vp, vp, vp, i64, vp]
     L.stocs_b200_fit_transforms.argtypes = [vp, i64, vp, vp, vp, vp, vp]
@@ -161,6 +164,18 @@ class Context:
         a, b = C.c_int64(0), C.c_int64(0)
         self._check(self._L.stocs_b200_ppf_num_pairs(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def ppf_num_expanded_keys(self):
+        a = C.c_int64(0)
+        self._check(self._L.stocs_b200_ppf_num_expanded_keys(self.h, C.byref(a)))
+        return a.value
+
+    def ppf_export(self):
+        n = C.c_int64(0)
+        self._check(self._L.stocs_b200_ppf_export(self.h, None, None, 0, C.byref(n)))
+        keys, pairs = np.empty((n.value, 4), np.int32), np.empty((n.value, 2), np.int32)
+        self._check(self._L.stocs_b200_ppf_export(self.h, _ptr(keys), _ptr(pairs), n.value, C.byref(n)))
+        return keys, pairs
 
     def ppf_lookup(self, key):
         key = np.ascontiguousarray(key, np.int32).reshape(4)

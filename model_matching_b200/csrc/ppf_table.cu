@@ -75,6 +75,31 @@ __global__ void ppf_keybits_kernel(const uint32_t* __restrict__ bin_start, int n
   }
 }
 
+__global__ void ppf_count_bits_kernel(const uint32_t* __restrict__ bits, long long nwords, unsigned long long* __restrict__ out) {
+  unsigned long long c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x)
+    c += __popc(bits[i]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void ppf_export_kernel(const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ pairs, int n1, int na,
+                                  int tr, int rot, int* __restrict__ keys4, int* __restrict__ pairs2) {
+  const long long nb = (long long)n1 * na * na * na;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
+  const uint32_t s = bin_start[t], e = bin_start[t + 1];
+  if (s == e) return;
+  int r = (int)t;
+  const int b4 = r % na; r /= na;
+  const int b3 = r % na; r /= na;
+  const int b2 = r % na; r /= na;
+  for (uint32_t k = s; k < e; ++k) {
+    keys4[4 * (size_t)k] = r * tr; keys4[4 * (size_t)k + 1] = b2 * rot; keys4[4 * (size_t)k + 2] = b3 * rot; keys4[4 * (size_t)k + 3] = b4 * rot;
+    pairs2[2 * (size_t)k] = (int)(pairs[k] >> 16); pairs2[2 * (size_t)k + 1] = (int)(pairs[k] & 0xffffu);
+  }
+}
+
 // map lookup for the C ABI: gather the source bins of one key into out[], count in *n
 __global__ void ppf_gather_kernel(PpfView v, Ppf4 key, uint32_t* __restrict__ out, long long cap,
                                   long long* __restrict__ n_out) {
@@ -166,6 +191,11 @@ int stocs_build_ppf_table(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, cudaGetLastError());
   ctx->ppf.npairs = npairs;
   ctx->ppf.nkeys = (int64_t)nk;
+  STOCS_CUDA(ctx, cudaMemsetAsync(d_nkeys, 0, 8, st));
+  ppf_count_bits_kernel<<<64, 256, 0, st>>>(ctx->d_ppf_keybits.as<uint32_t>(), (nkeybits + 31) / 32, d_nkeys);
+  STOCS_CUDA(ctx, cudaMemcpyAsync(&nk, d_nkeys, 8, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->ppf.nexpanded = (int64_t)nk;
   keys_a.release(); keys_b.release(); cub_tmp.release();
   return STOCS_OK;
 }
@@ -177,6 +207,35 @@ int stocs_b200_ppf_num_pairs(stocs_b200_ctx* ctx, int64_t* own_bin_pairs, int64_
   if (ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "ppf: upload_model first");
   if (own_bin_pairs) *own_bin_pairs = ctx->ppf.npairs;
   if (own_bin_keys) *own_bin_keys = ctx->ppf.nkeys;
+  return STOCS_OK;
+}
+
+int stocs_b200_ppf_num_expanded_keys(stocs_b200_ctx* ctx, int64_t* expanded_keys) {
+  if (!ctx || !expanded_keys) return STOCS_E_ARG;
+  if (ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "ppf: upload_model first");
+  *expanded_keys = ctx->ppf.nexpanded;
+  return STOCS_OK;
+}
+
+int stocs_b200_ppf_export(stocs_b200_ctx* ctx, int32_t* keys4, int32_t* pairs2, int64_t cap, int64_t* n) {
+  if (!ctx || !n) return STOCS_E_ARG;
+  if (ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "ppf: upload_model first");
+  *n = ctx->ppf.npairs;
+  if (!keys4 || !pairs2) return STOCS_OK;
+  if (cap < ctx->ppf.npairs) STOCS_FAIL(ctx, STOCS_E_CAPACITY, "ppf_export: capacity too small");
+  if (ctx->ppf.npairs == 0) return STOCS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  DevBuf dk, dp;
+  STOCS_CUDA(ctx, dk.ensure((size_t)ctx->ppf.npairs * 16));
+  STOCS_CUDA(ctx, dp.ensure((size_t)ctx->ppf.npairs * 8));
+  const long long nb = (long long)ctx->ppf.n1 * ctx->ppf.na * ctx->ppf.na * ctx->ppf.na;
+  ppf_export_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(ctx->d_ppf_bin_start.as<uint32_t>(), ctx->d_ppf_pairs.as<uint32_t>(),
+                                                                  ctx->ppf.n1, ctx->ppf.na, ctx->ppf.tr, ctx->ppf.rot, dk.as<int>(), dp.as<int>());
+  STOCS_CUDA(ctx, cudaMemcpyAsync(keys4, dk.p, (size_t)ctx->ppf.npairs * 16, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(pairs2, dp.p, (size_t)ctx->ppf.npairs * 8, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  dk.release(); dp.release();
   return STOCS_OK;
 }
 

@@ -48,6 +48,7 @@ struct PpfTableDesc {
   int tr, rot;
   int64_t npairs;      // ordered pairs stored (own bin)
   int64_t nkeys;       // occupied own bins
+  int64_t nexpanded;   // keys of the reference's expanded map
 };
 
 struct stocs_b200_ctx {

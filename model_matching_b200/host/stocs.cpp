@@ -1,0 +1,288 @@
+// stocs.cpp -- stocs::stocs_estimator on libstocs_b200 (see stocs.hpp).  Host code only marshals:
+// every online computation of the reference's src/stocs.cpp runs in a CUDA kernel behind the C ABI.
+#include "stocs.hpp"
+
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "../../include/stocs_b200.h"
+
+namespace stocs {
+
+void stocs_estimator::fail(const char* where) {
+  std::cerr << "libstocs_b200: " << where << ": " << stocs_b200_last_error(ctx_) << std::endl;
+  std::exit(2);  // no CPU fallback: a GPU failure is fatal, loudly
+}
+
+stocs_estimator::stocs_estimator(std::string model_location, PPFMapType& ppf_map_preloaded, std::string rgb_location,
+                                 std::string depth_location, std::string class_probability_map_location,
+                                 std::string edge_probability_map_location, std::string debug_location,
+                                 std::vector<float> camera_intrinsics, int image_width, int image_height,
+                                 float read_depth_scale, float write_depth_scale, float voxel_size,
+                                 float distance_threshold, int ppf_tr_discretization, int ppf_rot_discretization,
+                                 float edge_threshold, float class_threshold) {
+  this->debug_location = debug_location;
+  this->distance_threshold = distance_threshold;
+  this->ppf_tr_discretization = ppf_tr_discretization;
+  this->ppf_rot_discretization = ppf_rot_discretization;
+  this->edge_threshold = edge_threshold;
+  this->class_threshold = class_threshold;
+  this->image_width = image_width;
+  this->image_height = image_height;
+  all_transforms.clear();
+  all_pose.clear();
+  best_lcp = 0;
+  best_index = -1;
+
+  const char* dev = std::getenv("STOCS_DEVICE");
+  int rc = stocs_b200_create(&ctx_, dev ? std::atoi(dev) : 0);
+  if (rc != 0) {
+    std::cerr << "libstocs_b200: cannot create a GPU context (" << rc << "): " << stocs_b200_last_error(nullptr)
+              << "\nThis build has no CPU path." << std::endl;
+    std::exit(2);
+  }
+  if (stocs_b200_set_params(ctx_, distance_threshold, ppf_tr_discretization, ppf_rot_discretization) != 0) fail("set_params");
+  const char* seed = std::getenv("STOCS_SEED");
+  seed_ = seed ? std::strtoull(seed, nullptr, 10)
+               : (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();  // src/stocs.cpp:135
+
+  load_object_info(model_location, ppf_map_preloaded);
+  load_scene_info(rgb_location, depth_location, class_probability_map_location, edge_probability_map_location,
+                  camera_intrinsics, read_depth_scale, write_depth_scale, voxel_size, debug_location + "/sampled_scene.ply");
+  // Move the centroid of the point sets to 0 and index the scene (src/stocs.cpp:943-980): both
+  // happen on the GPU when the point sets are uploaded.
+  centroid_shift();
+  kdtree_initialize();
+}
+
+stocs_estimator::~stocs_estimator() {
+  if (ctx_) stocs_b200_destroy(ctx_);  // PoseCandidate* are left to the caller, as in the reference
+}
+
+void stocs_estimator::load_object_info(std::string model_location, PPFMapType& ppf_map_preloaded) {
+  point3d_model.clear();
+  PCLPointCloud::Ptr cloud(new PCLPointCloud);
+  if (!rgbd::load_ply_file(model_location, *cloud)) std::cerr << "cannot read " << model_location << std::endl;
+  rgbd::load_ply_model(cloud, point3d_model, 1.0f);
+  ppf_map = ppf_map_preloaded;
+  std::cout << "|M| = " << point3d_model.size() << ",  |map(M)| = " << ppf_map.size() << std::endl;
+}
+
+void stocs_estimator::load_scene_info(std::string rgb_location, std::string depth_location,
+                                      std::string class_probability_map_location,
+                                      std::string edge_probability_map_location, std::vector<float> camera_intrinsics,
+                                      float read_depth_scale, float write_depth_scale, float voxel_size,
+                                      std::string dst_scene_location) {
+  point3d_scene.clear();
+  struct stat buffer;
+  edge_probability_map.clear();
+  if (stat(edge_probability_map_location.c_str(), &buffer) == 0)
+    imgio::load_gray8(edge_probability_map_location, edge_probability_map, edge_w, edge_h);
+  if (edge_probability_map.empty()) {
+    edge_w = image_width; edge_h = image_height;
+    edge_probability_map.assign((size_t)image_width * image_height, 0);
+  }
+  rgbd::load_rgbd_data_sampled(rgb_location, depth_location, class_probability_map_location, edge_probability_map, edge_w,
+                               edge_h, camera_intrinsics, read_depth_scale, voxel_size, class_threshold, point3d_scene, ctx_);
+  rgbd::save_as_ply(dst_scene_location, point3d_scene, write_depth_scale);
+}
+
+// src/stocs.cpp:943-964.  The sequential fp32 centroids are computed by the upload kernels; the
+// host copies are shifted with the values read back so that accessors see centred clouds.
+void stocs_estimator::centroid_shift() {
+  const size_t S = point3d_scene.size(), M = point3d_model.size();
+  if (S == 0 || M == 0) { std::cerr << "empty scene or model" << std::endl; return; }
+  std::vector<float> mp(M * 3), mn(M * 3), sp(S * 3), sn(S * 3), sc(S);
+  std::vector<int32_t> pix(S * 2);
+  for (size_t i = 0; i < M; ++i)
+    for (int k = 0; k < 3; ++k) { mp[3 * i + k] = point3d_model[i].pos()[k]; mn[3 * i + k] = point3d_model[i].normal()[k]; }
+  for (size_t i = 0; i < S; ++i) {
+    for (int k = 0; k < 3; ++k) { sp[3 * i + k] = point3d_scene[i].pos()[k]; sn[3 * i + k] = point3d_scene[i].normal()[k]; }
+    sc[i] = point3d_scene[i].class_probability();
+    pix[2 * i] = point3d_scene[i].pixel().first; pix[2 * i + 1] = point3d_scene[i].pixel().second;
+  }
+  if (stocs_b200_upload_model(ctx_, mp.data(), mn.data(), (int)M) != 0) fail("upload_model");
+  if (stocs_b200_upload_scene(ctx_, sp.data(), sn.data(), sc.data(), pix.data(), (int)S) != 0) fail("upload_scene");
+  float cs[3], cm[3];
+  if (stocs_b200_get_centroids(ctx_, cs, cm) != 0) fail("get_centroids");
+  if (stocs_b200_get_centred(ctx_, sp.data(), mp.data()) != 0) fail("get_centred");
+  centroid_scene_ = VectorType(cs[0], cs[1], cs[2]);
+  centroid_model_ = VectorType(cm[0], cm[1], cm[2]);
+  for (size_t i = 0; i < S; ++i) point3d_scene[i].pos() = VectorType(sp[3 * i], sp[3 * i + 1], sp[3 * i + 2]);
+  for (size_t i = 0; i < M; ++i) point3d_model[i].pos() = VectorType(mp[3 * i], mp[3 * i + 1], mp[3 * i + 2]);
+  int64_t pairs = 0, bins = 0;
+  stocs_b200_ppf_num_pairs(ctx_, &pairs, &bins);
+  if (!ppf_map.empty() && (int64_t)(ppf_map.pairs2.size() / 2) != pairs)
+    std::cerr << "warning: ppf_map file holds " << ppf_map.pairs2.size() / 2 << " pairs, the model yields " << pairs
+              << " (stale ppf_map? re-run model_preprocess)" << std::endl;
+}
+
+void stocs_estimator::kdtree_initialize() {
+  std::cout << "|S|: " << point3d_scene.size() << std::endl;  // the index was built by upload_scene
+}
+
+bool stocs_estimator::sample_class_base(std::vector<int>& base_indices, float& invariant1, float& invariant2) {
+  int32_t ids[4];
+  float inv[2];
+  uint8_t valid = 0;
+  if (stocs_b200_sample_bases(ctx_, seed_, next_base_no_++, 1, ids, inv, &valid) != 0) fail("sample_bases");
+  if (!valid) {
+    std::cout << "FAILED SAMPLING:: Zero probability returned!!!" << std::endl;
+    return false;
+  }
+  for (int k = 0; k < 4; ++k) base_indices[k] = ids[k];
+  invariant1 = inv[0];
+  invariant2 = inv[1];
+  return true;
+}
+
+bool stocs_estimator::sample_instance_base(std::vector<int>&, float&, float&, std::vector<Point3D>&, float, int) {
+  static bool warned = false;
+  if (!warned) {
+    std::cerr << "sample_instance_base: instance (edge-aware) sampling is not implemented on the GPU yet "
+                 "(SURVEY.md section 8f-4); returning false" << std::endl;
+    warned = true;
+  }
+  return false;
+}
+
+bool stocs_estimator::find_congruent_sets_on_model(std::vector<int>& base_indices, float invariant1, float invariant2,
+                                                   std::vector<Quadrilateral>* quadrilaterals) {
+  quadrilaterals->clear();
+  int32_t ids[4] = {base_indices[0], base_indices[1], base_indices[2], base_indices[3]};
+  float inv[2] = {invariant1, invariant2};
+  int64_t off[2] = {0, 0};
+  std::vector<int32_t> quads(4 * 4096);
+  int rc = stocs_b200_find_congruent(ctx_, 1, ids, inv, quads.data(), (int64_t)quads.size() / 4, off);
+  if (rc == STOCS_E_CAPACITY) {
+    quads.resize((size_t)off[1] * 4);
+    rc = stocs_b200_find_congruent(ctx_, 1, ids, inv, quads.data(), off[1], off);
+  }
+  if (rc != 0) fail("find_congruent");
+  for (int64_t i = 0; i < off[1]; ++i)
+    quadrilaterals->emplace_back(quads[4 * i], quads[4 * i + 1], quads[4 * i + 2], quads[4 * i + 3]);
+  return quadrilaterals->size() != 0;
+}
+
+bool stocs_estimator::get_rigid_transform_from_congruent_pair(std::vector<int>& base_indices, Quadrilateral& q,
+                                                              int base_index) {
+  for (int k = 0; k < 4; ++k) { pending_bases_.push_back(base_indices[k]); pending_quads_.push_back(q[k]); }
+  pending_base_index_.push_back(base_index);
+  return true;  // src/stocs.cpp:940 always returns true
+}
+
+void stocs_estimator::flush_pending() {
+  const int64_t n = (int64_t)pending_base_index_.size();
+  if (n == 0) return;
+  std::vector<float> Tc((size_t)n * 16), Tw((size_t)n * 16);
+  std::vector<uint8_t> ok((size_t)n);
+  if (stocs_b200_fit_transforms(ctx_, n, pending_bases_.data(), pending_quads_.data(), Tc.data(), Tw.data(), ok.data()) != 0)
+    fail("fit_transforms");
+  for (int64_t i = 0; i < n; ++i) {
+    if (!ok[i]) continue;  // "if(ok && rms >= 0)" (src/stocs.cpp:922)
+    MatrixType t, w;
+    std::memcpy(t.data(), &Tc[16 * i], 64);
+    std::memcpy(w.data(), &Tw[16 * i], 64);
+    all_transforms.push_back(t);
+    all_pose.push_back(new PoseCandidate(w, 0, (float)pending_base_index_[i]));
+  }
+  pending_bases_.clear(); pending_quads_.clear(); pending_base_index_.clear();
+}
+
+Scalar stocs_estimator::compute_alignment_score_for_rigid_transform(const Eigen::Ref<const MatrixType>& mat) {
+  float lcp = 0;
+  if (stocs_b200_score_lcp(ctx_, mat.data(), 1, &lcp, nullptr) != 0) fail("score_lcp");
+  return lcp;
+}
+
+// src/stocs.cpp:982-1004
+void stocs_estimator::compute_best_transform() {
+  flush_pending();
+  std::cout << "Transforms to verify: " << all_transforms.size() << std::endl;
+  const int64_t H = (int64_t)all_transforms.size();
+  best_lcp = 0;
+  best_index = -1;
+  if (H > 0) {
+    std::vector<float> T((size_t)H * 16), lcp((size_t)H);
+    for (int64_t i = 0; i < H; ++i) std::memcpy(&T[16 * i], all_transforms[i].data(), 64);
+    if (stocs_b200_score_lcp(ctx_, T.data(), H, lcp.data(), nullptr) != 0) fail("score_lcp");
+    for (int64_t i = 0; i < H; ++i) all_pose[i]->lcp = lcp[i];
+    int64_t bi = -1;
+    float bl = 0;
+    int64_t ti[1]; float tl[1];
+    if (stocs_b200_reduce_best(ctx_, nullptr, H, 1, &bi, &bl, ti, tl) != 0) fail("reduce_best");
+    best_lcp = bl;
+    best_index = (int)bi;
+  }
+  std::cout << "best index: " << best_index << ", maximum score: " << best_lcp << std::endl;
+}
+
+// include/stocs.hpp:136-149
+void stocs_estimator::visualize_best_pose() {
+  if (best_index == -1) return;
+  std::vector<Point3D> point3d_model_pose;
+  rgbd::transform_pointset(point3d_model, point3d_model_pose, all_transforms[best_index]);
+  rgbd::save_as_ply(debug_location + "/best_pose.ply", point3d_model_pose, 1);
+  rgbd::save_as_ply(debug_location + "/scene.ply", point3d_scene, 1);
+}
+
+// src/stocs.cpp:28-84.  Normal estimation and voxel-grid down-sampling are host restatements of
+// the PCL operators; the O(|M|^2) pair loop runs on the GPU (ppf_table.cu).
+void pre_process_model(std::string src_model_location, float normal_radius, float read_depth_scale,
+                       float write_depth_scale, float voxel_size, float ppf_tr_discretization,
+                       float ppf_rot_discretization, std::string dst_model_location, std::string dst_ppf_map_location) {
+  std::vector<Point3D> point3d_sampled;
+  PCLPointCloud::Ptr cloud(new PCLPointCloud);
+  if (!rgbd::load_ply_file(src_model_location, *cloud)) { std::cerr << "cannot read " << src_model_location << std::endl; return; }
+  rgbd::compute_normal_pcl(cloud, normal_radius);
+  for (auto& p : cloud->points) { p.nx = -p.nx; p.ny = -p.ny; p.nz = -p.nz; }  // normals face outside
+  rgbd::voxel_grid_filter(*cloud, voxel_size);
+  rgbd::load_ply_model(cloud, point3d_sampled, read_depth_scale);
+  std::cout << "After sampling |M|= " << point3d_sampled.size() << std::endl;
+
+  stocs_b200_ctx* ctx = nullptr;
+  const char* dev = std::getenv("STOCS_DEVICE");
+  if (stocs_b200_create(&ctx, dev ? std::atoi(dev) : 0) != 0) {
+    std::cerr << "libstocs_b200: cannot create a GPU context: " << stocs_b200_last_error(nullptr) << std::endl;
+    std::exit(2);
+  }
+  stocs_b200_set_params(ctx, 0.005f, (int)ppf_tr_discretization, (int)ppf_rot_discretization);
+  const size_t M = point3d_sampled.size();
+  std::vector<float> mp(M * 3), mn(M * 3);
+  float max_distance = 0;
+  for (size_t i = 0; i < M; ++i)
+    for (int k = 0; k < 3; ++k) { mp[3 * i + k] = point3d_sampled[i].pos()[k]; mn[3 * i + k] = point3d_sampled[i].normal()[k]; }
+  if (stocs_b200_upload_model(ctx, mp.data(), mn.data(), (int)M) != 0) {
+    std::cerr << "libstocs_b200: upload_model: " << stocs_b200_last_error(ctx) << std::endl;
+    std::exit(2);
+  }
+  for (size_t i = 0; i < M; ++i)
+    for (size_t j = 0; j < M; ++j) {
+      if (i == j) continue;
+      float d = (point3d_sampled[i].pos() - point3d_sampled[j].pos()).norm();
+      if (d > max_distance) max_distance = d;
+    }
+  std::cout << "max distance is: " << max_distance << std::endl;
+  PPFMapType map;
+  map.tr_discretization = (int)ppf_tr_discretization;
+  map.rot_discretization = (int)ppf_rot_discretization;
+  map.num_model_points = (int)M;
+  int64_t n = 0;
+  stocs_b200_ppf_export(ctx, nullptr, nullptr, 0, &n);
+  map.keys4.resize((size_t)n * 4);
+  map.pairs2.resize((size_t)n * 2);
+  if (stocs_b200_ppf_export(ctx, map.keys4.data(), map.pairs2.data(), n, &n) != 0) {
+    std::cerr << "libstocs_b200: ppf_export: " << stocs_b200_last_error(ctx) << std::endl;
+    std::exit(2);
+  }
+  stocs_b200_ppf_num_expanded_keys(ctx, &map.expanded_keys);
+  stocs_b200_destroy(ctx);
+  rgbd::save_ppf_map(dst_ppf_map_location, map);
+  rgbd::save_as_ply(dst_model_location, point3d_sampled, write_depth_scale);
+}
+
+}  // namespace stocs
