@@ -90,6 +90,24 @@ int stocs_b200_ppf_lookup(stocs_b200_ctx* ctx, const int32_t* key4, int32_t* pai
 int stocs_b200_sample_bases(stocs_b200_ctx* ctx, uint64_t seed, uint32_t first_base_no, int n_bases,
                             int32_t* base_idx4, float* inv2, uint8_t* valid);
 
+/* ---- a7: edge-aware instance sampling (src/stocs.cpp:521-535, 559-751; src/rgbd.cpp:314-367) ----
+ * upload_edge_map: the 8-bit edge probability image (H*W, 255 = no edge, as cv::imread(.., CV_8UC1)
+ * returns it); resets previous_segment / segmentation_buffer.  W*H must be a multiple of 4.
+ * sample_instance_base: ONE base (bases are sequentially coupled in this mode): decays the class
+ * prior inside the previous segment by `dispersion` (permanently), prunes edge pixels, draws the
+ * base restricted to the flood-filled segment around the first point.  base_num is 1..255 as in
+ * the reference driver (i+1) and also keys the random stream.  upload_scene must have been given
+ * pixel coordinates.  mask_out (may be NULL): the H*W segmentation mask (255 inside).
+ * segment_bits (may be NULL): ceil(S/32) words, bit i set = scene point i is in the reference's
+ * `segment` output (survived the first update and lies inside the mask). */
+int stocs_b200_upload_edge_map(stocs_b200_ctx* ctx, const uint8_t* edge, int W, int H);
+int stocs_b200_sample_instance_base(stocs_b200_ctx* ctx, uint64_t seed, int base_num, float dispersion,
+                                    int32_t* base_idx4, float* inv2, uint8_t* valid, uint8_t* mask_out,
+                                    uint32_t* segment_bits);
+/* current per-point class probability (instance sampling decays it; LCP uses the decayed value,
+ * src/stocs.cpp:577,1033) */
+int stocs_b200_get_class_probability(stocs_b200_ctx* ctx, float* out);
+
 /* ---- a9: congruent-set lookup (src/stocs.cpp:753-869) --------------------------------------
  * For each of n_bases bases returns its quadrilaterals (4 model indices each) in the reference's
  * std::set order; quad_offsets has n_bases+1 entries (CSR).  quads4 holds up to cap quads;

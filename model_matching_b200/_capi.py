@@ -20,6 +20,7 @@ SYMBOLS = [
     "stocs_b200_upload_scene", "stocs_b200_get_centroids", "stocs_b200_get_centred",
     "stocs_b200_ppf_num_pairs", "stocs_b200_ppf_num_expanded_keys", "stocs_b200_ppf_export",
     "stocs_b200_ppf_lookup", "stocs_b200_sample_bases",
+    "stocs_b200_upload_edge_map", "stocs_b200_sample_instance_base", "stocs_b200_get_class_probability",
     "stocs_b200_find_congruent", "stocs_b200_fit_transforms", "stocs_b200_score_lcp",
     "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device",
     "stocs_b200_run_pipeline", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
@@ -65,6 +66,9 @@ def lib():
     L.stocs_b200_ppf_num_expanded_keys.argtypes = [vp, C.POINTER(i64)]
     L.stocs_b200_ppf_export.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     L.stocs_b200_sample_bases.argtypes = [vp, u64, u32, i32, vp, vp, vp]
+    L.stocs_b200_upload_edge_map.argtypes = [vp, vp, i32, i32]
+    L.stocs_b200_sample_instance_base.argtypes = [vp, u64, i32, f32, vp, vp, vp, vp, vp]
+    L.stocs_b200_get_class_probability.argtypes = [vp, vp]
     L.stocs_b200_find_congruent.argtypes = [vp, i32, vp, vp, vp, i64, vp]
     L.stocs_b200_fit_transforms.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.stocs_b200_score_lcp.argtypes = [vp, vp, i64, vp, vp]
@@ -195,6 +199,23 @@ class Context:
         self._check(self._L.stocs_b200_sample_bases(self.h, int(seed), int(first_base_no), n_bases,
                                                      _ptr(ids), _ptr(inv), _ptr(valid)))
         return ids, inv, valid.astype(bool)
+
+    def upload_edge_map(self, edge):
+        edge = np.ascontiguousarray(edge, np.uint8)
+        self._edge_shape = edge.shape
+        self._check(self._L.stocs_b200_upload_edge_map(self.h, _ptr(edge), edge.shape[1], edge.shape[0]))
+
+    def sample_instance_base(self, seed, base_num, dispersion=0.9, want_mask=True):
+        ids, inv, valid = np.empty(4, np.int32), np.empty(2, np.float32), np.zeros(1, np.uint8)
+        mask = np.zeros(self._edge_shape, np.uint8) if want_mask else None
+        self._check(self._L.stocs_b200_sample_instance_base(self.h, int(seed), int(base_num), dispersion, _ptr(ids),
+                                                             _ptr(inv), _ptr(valid), _ptr(mask), None))
+        return bool(valid[0]), ids, inv, mask
+
+    def class_probability(self):
+        out = np.empty(self.S, np.float32)
+        self._check(self._L.stocs_b200_get_class_probability(self.h, _ptr(out)))
+        return out
 
     def find_congruent(self, base_idx, inv, cap=1 << 20):
         base_idx = np.ascontiguousarray(base_idx, np.int32).reshape(-1, 4)

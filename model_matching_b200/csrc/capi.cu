@@ -80,7 +80,8 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_model, &ctx->d_mpos4, &ctx->d_mnrm4, &ctx->d_spos4, &ctx->d_sattr, &ctx->d_spix,
                     &ctx->d_coarse, &ctx->d_bricks, &ctx->d_cell_start, &ctx->d_cand, &ctx->d_kd_nodes, &ctx->d_kd_pts, &ctx->d_ppf_bin_start,
                     &ctx->d_ppf_pairs, &ctx->d_ppf_keybits, &ctx->d_T, &ctx->d_lcp, &ctx->d_inl, &ctx->d_work,
-                    &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_small};
+                    &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_small, &ctx->d_edge, &ctx->d_inst_state, &ctx->d_mask_store,
+                    &ctx->d_frontier};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -192,6 +193,9 @@ int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float*
   STOCS_CUDA(ctx, ctx->d_spix.ensure((size_t)S * 8));
   if (pixel_rc) STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_spix.p, pixel_rc, (size_t)S * 8, cudaMemcpyHostToDevice, st));
   else STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_spix.p, 0, (size_t)S * 8, st));
+  ctx->has_pixels = pixel_rc != nullptr;
+  if (ctx->d_inst_state.p)  // a new scene starts with empty previous_segment / segmentation_buffer
+    STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_inst_state.p, 0, (size_t)ctx->img_w * ctx->img_h * 3, st));
   // positions -> centre -> index
   STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp.p, pos3, (size_t)S * 12, cudaMemcpyHostToDevice, st));
   rc = stocs_build_scene_index(ctx);

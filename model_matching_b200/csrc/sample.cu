@@ -10,10 +10,11 @@
 // Between draws one pass over the scene zeroes candidates by the reference's predicates
 // (PPF key present in the model map, internal angle >= 30 deg, coplanarity <= 0.015,
 // >= 0.01 m from the chosen points); survivors are kept as one bit per point.
-#include "ppf_device.cuh"
+#include "sample_common.cuh"
 #include "stocs_ctx.h"
 
 using namespace stocsm;
+using namespace stocs_sample;
 
 namespace {
 
@@ -30,43 +31,6 @@ struct SampleArgs {
   float* out_inv;
   uint8_t* out_valid;
 };
-
-__device__ double seg_dist_inv(V3 p1, V3 p2, V3 q1, V3 q2, double& inv1, double& inv2) {
-  const double kSmall = 0.0001;
-  const V3 u = sub(p2, p1), v = sub(q2, q1), w = sub(p1, q1);
-  const double a = dot(u, u), b = dot(u, v), c = dot(v, v), d = dot(u, w), e = dot(v, w);
-  const double f = a * c - b * b;
-  double s1 = 0.0, s2 = f, t1 = 0.0, t2 = f;
-  if (f < kSmall) {
-    s1 = 0.0; s2 = 1.0; t1 = e; t2 = c;
-  } else {
-    s1 = (b * e - c * d);
-    t1 = (a * e - b * d);
-    if (s1 < 0.0) { s1 = 0.0; t1 = e; t2 = c; }
-    else if (s1 > s2) { s1 = s2; t1 = e + b; t2 = c; }
-  }
-  if (t1 < 0.0) {
-    t1 = 0.0;
-    if (-d < 0.0) s1 = 0.0;
-    else if (-d > a) s1 = s2;
-    else { s1 = -d; s2 = a; }
-  } else if (t1 > t2) {
-    t1 = t2;
-    if ((-d + b) < 0.0) s1 = 0;
-    else if ((-d + b) > a) s1 = s2;
-    else { s1 = (-d + b); s2 = a; }
-  }
-  inv1 = (fabs(s1) < kSmall ? 0.0 : s1 / s2);
-  inv2 = (fabs(t1) < kSmall ? 0.0 : t1 / t2);
-  const V3 r = sub(add(w, scale(u, (float)inv1)), scale(v, (float)inv2));
-  return (double)norm(r);
-}
-
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 __global__ void __launch_bounds__(1024) sample_bases_kernel(SampleArgs a) {
   const int base = blockIdx.x;

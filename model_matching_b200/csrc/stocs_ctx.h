@@ -80,6 +80,10 @@ struct stocs_b200_ctx {
   DevBuf d_spos4;                      // float4 (x,y,z,bits(idx))
   DevBuf d_sattr;                      // float4 (nx,ny,nz,class probability)
   DevBuf d_spix;                       // int2 (row, col)
+  bool has_pixels = false;
+  // instance-mode state (edge map, previous_segment | segmentation_buffer | current mask, cached masks)
+  DevBuf d_edge, d_inst_state, d_mask_store, d_frontier;
+  int img_w = 0, img_h = 0;
   GridDesc grid{};
   DevBuf d_coarse;                     // 1 bit per brick: brick has an occupied cell
   DevBuf d_bricks;                     // uint4 {mask lo, mask hi, first occupied-cell rank, 0} per brick

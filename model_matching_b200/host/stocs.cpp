@@ -153,14 +153,27 @@ bool stocs_estimator::sample_class_base(std::vector<int>& base_indices, float& i
   return true;
 }
 
-bool stocs_estimator::sample_instance_base(std::vector<int>&, float&, float&, std::vector<Point3D>&, float, int) {
-  static bool warned = false;
-  if (!warned) {
-    std::cerr << "sample_instance_base: instance (edge-aware) sampling is not implemented on the GPU yet "
-                 "(SURVEY.md section 8f-4); returning false" << std::endl;
-    warned = true;
+// src/stocs.cpp:559-751.  One kernel launch per base (bases are sequentially coupled here).
+bool stocs_estimator::sample_instance_base(std::vector<int>& base_indices, float& invariant1, float& invariant2,
+                                           std::vector<Point3D>& segment, float dispersion, int base_num) {
+  if (!edge_uploaded_) {
+    if (stocs_b200_upload_edge_map(ctx_, edge_probability_map.data(), edge_w, edge_h) != 0) fail("upload_edge_map");
+    edge_uploaded_ = true;
   }
-  return false;
+  int32_t ids[4];
+  float inv[2];
+  uint8_t valid = 0;
+  std::vector<uint32_t> seg_bits((point3d_scene.size() + 31) / 32, 0u);
+  if (stocs_b200_sample_instance_base(ctx_, seed_, base_num, dispersion, ids, inv, &valid, nullptr, seg_bits.data()) != 0)
+    fail("sample_instance_base");
+  for (size_t i = 0; i < point3d_scene.size(); ++i)
+    if ((seg_bits[i >> 5] >> (i & 31)) & 1u) segment.push_back(point3d_scene[i]);
+  class_prob_dirty_ = true;  // the prior was decayed on the device (point3d.hpp:54-56 semantics)
+  if (!valid) return false;
+  for (int k = 0; k < 4; ++k) base_indices[k] = ids[k];
+  invariant1 = inv[0];
+  invariant2 = inv[1];
+  return true;
 }
 
 bool stocs_estimator::find_congruent_sets_on_model(std::vector<int>& base_indices, float invariant1, float invariant2,

@@ -11,8 +11,8 @@
 //  * get_rigid_transform_from_congruent_pair queues the (base, quad) pair; transforms are fitted,
 //    scored and reduced in one batched GPU pass at compute_best_transform() (or at the first
 //    accessor that needs them).  The lists all_transforms / all_pose end up identical.
-//  * sample_instance_base (edge-aware instance mode) is not on the GPU yet and
-//    returns false.
+//  * sample_instance_base keeps its cached segmentation masks in device memory instead of writing
+//    and re-reading dbg/seg_mask_<n>.png (src/stocs.cpp:625, src/rgbd.cpp:330); lossless either way.
 #ifndef STOCS_B200_STOCS_HPP_
 #define STOCS_B200_STOCS_HPP_
 #include <cstdint>
@@ -100,6 +100,8 @@ class stocs_estimator {
   struct stocs_b200_ctx* ctx_ = nullptr;
   uint64_t seed_ = 0;
   uint32_t next_base_no_ = 0;
+  bool edge_uploaded_ = false;
+  bool class_prob_dirty_ = false;
   std::vector<int32_t> pending_bases_, pending_quads_;
   std::vector<int> pending_base_index_;
 };

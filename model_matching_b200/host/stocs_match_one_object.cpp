@@ -85,7 +85,8 @@ void run_stocs_estimation(std::string scene_path, std::string object_name, PPFMa
 
   // Step 1: Sample n bases on scene
   auto start = std::chrono::high_resolution_clock::now();
-  const bool instance_mode = false;  // edge-aware instance sampling: SURVEY.md 8f-4, not on the GPU yet
+  struct stat buffer;
+  const bool instance_mode = stat(edge_probability_path.c_str(), &buffer) == 0;  // src/stocs_match_one_object.cpp:91
   for (int i = 0; i < number_of_bases; i++) {
     bool valid_base_found = false;
     std::vector<int> base_indices(4, -1);

@@ -64,6 +64,10 @@ def lib():
     L.orc_est_sample_class_base.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, i32p, f32p,
                                             C.POINTER(C.c_int)]
     L.orc_est_current_prob.argtypes = [C.c_void_p, f32p]
+    L.orc_est_class_prob.argtypes = [C.c_void_p, f32p]
+    L.orc_est_set_edge_map.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int]
+    L.orc_est_sample_instance_base.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_float, i32p, f32p,
+                                               C.c_void_p, C.POINTER(C.c_int)]
     L.orc_est_find_congruent.restype = C.c_longlong
     L.orc_est_find_congruent.argtypes = [C.c_void_p, i32p, C.c_float, C.c_float, i32p,
                                          C.c_longlong, i32p]
@@ -195,6 +199,22 @@ class Estimator:
         ids, inv, st = np.empty(4, np.int32), np.empty(2, np.float32), C.c_int(0)
         ok = lib().orc_est_sample_class_base(self.h, seed, base_no, ids, inv, C.byref(st))
         return bool(ok), ids, inv, st.value
+
+    def set_edge_map(self, edge):
+        edge = np.ascontiguousarray(edge, np.uint8)
+        self._edge_shape = edge.shape
+        lib().orc_est_set_edge_map(self.h, edge, edge.shape[1], edge.shape[0])
+
+    def sample_instance_base(self, seed, base_num, dispersion=0.9):
+        ids, inv, st = np.empty(4, np.int32), np.empty(2, np.float32), C.c_int(0)
+        mask = np.zeros(self._edge_shape, np.uint8)
+        ok = lib().orc_est_sample_instance_base(self.h, seed, base_num, dispersion, ids, inv, mask.ctypes.data, C.byref(st))
+        return bool(ok), ids, inv, st.value, mask
+
+    def class_prob(self):
+        out = np.empty(self.S, np.float32)
+        lib().orc_est_class_prob(self.h, out)
+        return out
 
     def current_prob(self):
         out = np.empty(self.S, np.float32)

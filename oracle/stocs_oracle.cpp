@@ -37,6 +37,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <queue>
 #include <memory>
 #include <set>
 #include <utility>
@@ -466,6 +467,123 @@ struct Estimator {
     return try_sampled_base(ids, inv1, inv2);
   }
 
+  // ---- instance mode (src/stocs.cpp:521-535, 559-751; src/rgbd.cpp:314-367) ----------------
+  int img_w = 0, img_h = 0;
+  std::vector<uint8_t> edge_map, previous_segment, segmentation_buffer;
+  std::map<int, std::vector<uint8_t>> mask_store;  // stands in for dbg/seg_mask_<n>.png (lossless)
+
+  void set_edge_map(const uint8_t* e, int w, int h) {
+    img_w = w; img_h = h;
+    edge_map.assign(e, e + (size_t)w * h);
+    previous_segment.assign((size_t)w * h, 0);
+    segmentation_buffer.assign((size_t)w * h, 0);
+    mask_store.clear();
+  }
+
+  // rgbd.cpp:314-367
+  void generate_segmentation_mask(int prow, int pcol, float max_distance, std::vector<uint8_t>& closed, int base_num) {
+    int segment_index = segmentation_buffer[(size_t)prow * img_w + pcol];
+    if (segment_index != 0) { closed = mask_store[segment_index]; return; }
+    std::queue<std::pair<int, int>> open_list;
+    open_list.push({prow, pcol});
+    while (!open_list.empty()) {
+      auto curr = open_list.front();
+      closed[(size_t)curr.first * img_w + curr.second] = 255;
+      segmentation_buffer[(size_t)curr.first * img_w + curr.second] = (uint8_t)base_num;
+      open_list.pop();
+      for (int i = curr.first - 1; i <= curr.first + 1; i += 1)
+        for (int j = curr.second - 1; j <= curr.second + 1; j += 1) {
+          if (i < 0 || j < 0 || i >= img_h || j >= img_w) continue;
+          float edge_probability = (float)(255.0 - edge_map[(size_t)i * img_w + j]) / 255.0;
+          int expanded = closed[(size_t)i * img_w + j];
+          float dist = std::sqrt(std::pow((prow - i), 2) + std::pow((pcol - j), 2));
+          if (expanded == 0 && edge_probability == 0 && dist < max_distance) {
+            open_list.push({i, j});
+            closed[(size_t)i * img_w + j] = 255;
+            segmentation_buffer[(size_t)i * img_w + j] = (uint8_t)base_num;
+          }
+        }
+    }
+  }
+
+  bool sample_instance_base(uint64_t seed, int ids[4], float& inv1, float& inv2, float dispersion, int base_num,
+                            std::vector<uint8_t>* mask_out, int* stage_out) {
+    const float plane_threshold = 0.015f, min_distance_base = 0.01f;
+    const float internal_angle_threshold = 30;
+    const int S = (int)spos.size();
+    const uint32_t base_no = (uint32_t)base_num;
+    if (stage_out) *stage_out = 0;
+    for (int i = 0; i < S; ++i) {
+      int isPresent = previous_segment[(size_t)srow[i] * img_w + scol[i]];
+      if (isPresent) scls[i] = dispersion * scls[i];   // permanent (point3d.hpp:54-56)
+      scur[i] = scls[i];
+    }
+    for (int i = 0; i < S; ++i) {                       // prune_edge_pixels
+      float edge_probability = (float)(255.0 - edge_map[(size_t)srow[i] * img_w + scol[i]]) / 255.0;
+      if (edge_probability == 1) scur[i] = 0;
+    }
+    int b1 = sample_point(seed, base_no, 0);
+    if (b1 < 0 || scur[b1] == 0.0f) return false;
+    if (stage_out) *stage_out = 1;
+    float max_pixel_distance = 0;
+    for (int i = 0; i < S; ++i) {
+      stocsm::Ppf4 f = scene_ppf(b1, i);
+      if (!has_key(f) || i == b1) scur[i] = 0;
+      if (scur[i] != 0) {
+        float dist = std::sqrt(std::pow((srow[b1] - srow[i]), 2) + std::pow((scol[b1] - scol[i]), 2));
+        if (dist > max_pixel_distance) max_pixel_distance = dist;
+      }
+    }
+    std::vector<uint8_t> mask((size_t)img_w * img_h, 0);
+    generate_segmentation_mask(srow[b1], scol[b1], max_pixel_distance, mask, base_num);
+    mask_store[base_num] = mask;                          // cv::imwrite(seg_mask_<base_num>.png)
+    previous_segment = mask;
+    if (mask_out) *mask_out = mask;
+    for (int i = 0; i < S; ++i)
+      if (scur[i] != 0 && !mask[(size_t)srow[i] * img_w + scol[i]]) scur[i] = 0;
+    int b2 = sample_point(seed, base_no, 1);
+    if (b2 < 0 || scur[b2] == 0.0f) return false;
+    if (stage_out) *stage_out = 2;
+    V3 v_1 = stocsm::normalized(stocsm::sub(spos[b2], spos[b1]));
+    for (int i = 0; i < S; ++i) {
+      V3 v_2 = stocsm::normalized(stocsm::sub(spos[i], spos[b1]));
+      float int_angle = (float)stocsm::rad_to_deg_ref(stocsm::acos_f(stocsm::dot(v_1, v_2)));
+      float other = 180 - int_angle;
+      int_angle = (other < int_angle) ? other : int_angle;
+      stocsm::Ppf4 f = scene_ppf(b2, i);
+      if (!has_key(f) || i == b2 || int_angle < internal_angle_threshold) scur[i] = 0;
+    }
+    int b3 = sample_point(seed, base_no, 2);
+    if (b3 < 0 || scur[b3] == 0.0f) return false;
+    if (stage_out) *stage_out = 3;
+    {
+      double x1 = spos[b1].x, y1 = spos[b1].y, z1 = spos[b1].z;
+      double x2 = spos[b2].x, y2 = spos[b2].y, z2 = spos[b2].z;
+      double x3 = spos[b3].x, y3 = spos[b3].y, z3 = spos[b3].z;
+      float denom = (-x3 * y2 * z1 + x2 * y3 * z1 + x3 * y1 * z2 - x1 * y3 * z2 - x2 * y1 * z3 + x1 * y2 * z3);
+      float A = 0, B = 0, C = 0;
+      if (denom != 0) {
+        A = (-y2 * z1 + y3 * z1 + y1 * z2 - y3 * z2 - y1 * z3 + y2 * z3) / denom;
+        B = (x2 * z1 - x3 * z1 - x1 * z2 + x3 * z2 + x1 * z3 - x2 * z3) / denom;
+        C = (-x2 * y1 + x3 * y1 + x1 * y2 - x3 * y2 - x1 * y3 + x2 * y3) / denom;
+      }
+      for (int i = 0; i < S; ++i) {
+        float planar_distance = 10000;
+        if (denom != 0) planar_distance = std::abs(A * spos[i].x + B * spos[i].y + C * spos[i].z - 1.0);
+        stocsm::Ppf4 f = scene_ppf(b3, i);
+        if (planar_distance > plane_threshold || stocsm::norm(stocsm::sub(spos[i], spos[b1])) < min_distance_base ||
+            stocsm::norm(stocsm::sub(spos[i], spos[b2])) < min_distance_base ||
+            stocsm::norm(stocsm::sub(spos[i], spos[b3])) < min_distance_base || !has_key(f) || i == b3)
+          scur[i] = 0;
+      }
+    }
+    int b4 = sample_point(seed, base_no, 3);
+    if (b4 < 0 || scur[b4] == 0.0f) return false;
+    if (stage_out) *stage_out = 4;
+    ids[0] = b1; ids[1] = b2; ids[2] = b3; ids[3] = b4;
+    return try_sampled_base(ids, inv1, inv2);
+  }
+
   // src/stocs.cpp:753-869 + pairCreationFunctor.h:96-143.
   int find_congruent(const int base[4], float invariant1, float invariant2,
                      std::vector<std::array<int, 4>>& quads, int* nP, int* nQ) const {
@@ -791,6 +909,22 @@ int orc_est_sample_class_base(void* h, unsigned long long seed, unsigned base_no
 void orc_est_current_prob(void* h, float* out) {
   auto* e = (orc::Estimator*)h;
   memcpy(out, e->scur.data(), e->scur.size() * sizeof(float));
+}
+void orc_est_set_edge_map(void* h, const uint8_t* edge, int w, int hgt) { ((orc::Estimator*)h)->set_edge_map(edge, w, hgt); }
+int orc_est_sample_instance_base(void* h, unsigned long long seed, int base_num, float dispersion, int* ids4,
+                                 float* inv2, uint8_t* mask_out, int* stage) {
+  auto* e = (orc::Estimator*)h;
+  float i1 = 0, i2 = 0;
+  ids4[0] = ids4[1] = ids4[2] = ids4[3] = -1;
+  std::vector<uint8_t> mask;
+  bool ok = e->sample_instance_base(seed, ids4, i1, i2, dispersion, base_num, &mask, stage);
+  if (mask_out && !mask.empty()) memcpy(mask_out, mask.data(), mask.size());
+  inv2[0] = i1; inv2[1] = i2;
+  return ok ? 1 : 0;
+}
+void orc_est_class_prob(void* h, float* out) {
+  auto* e = (orc::Estimator*)h;
+  memcpy(out, e->scls.data(), e->scls.size() * sizeof(float));
 }
 long long orc_est_find_congruent(void* h, const int* base4, float inv1, float inv2, int* quads4,
                                  long long cap, int* nPQ) {

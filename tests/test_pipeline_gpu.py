@@ -121,3 +121,57 @@ def test_run_pipeline_matches_composition(world):
     assert np.array_equal(np.array(r.best_T_world[:], np.float32), Tws[bi])
     # the recovered pose is the planted one: the winning hypothesis explains most of the model
     assert inl[bi] > 0.5 * len(mpos)
+
+
+def _pixels_and_edges(pos):
+    """Synthetic pixel coordinates (orthographic binning of x,y) and an edge map with a grid of
+    edge lines, so that flood fills are bounded regions and later bases land in cached segments."""
+    W, H = 640, 480
+    u = ((pos[:, 0] - pos[:, 0].min()) / (np.ptp(pos[:, 0]) + 1e-6) * (W - 1)).astype(np.int32)
+    v = ((pos[:, 1] - pos[:, 1].min()) / (np.ptp(pos[:, 1]) + 1e-6) * (H - 1)).astype(np.int32)
+    edge = np.full((H, W), 255, np.uint8)
+    edge[::40, :] = 0
+    edge[:, ::50] = 0
+    edge[100:140, 200:260] = 128     # neither edge nor free: stops the fill, is not pruned
+    return np.stack([v, u], -1).astype(np.int32), edge
+
+
+def test_sample_instance_base_sequence_bit_exact(gpu_ctx):
+    """Instance mode is stateful across bases (prior decay, cached masks): run the same sequence of
+    bases on the oracle and on the GPU and compare every output and the evolving state."""
+    sc, mpos, mnrm = object_scene()
+    pix, edge = _pixels_and_edges(sc["pos"])
+    omap = oracle.PPFMap(mpos, mnrm)
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm, ppfmap=omap, spix=pix)
+    est.set_edge_map(edge)
+    ctx = gpu_ctx
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"], pix)
+    ctx.upload_edge_map(edge)
+    n_ok = n_cached = 0
+    seen_masks = []
+    for b in range(1, 41):
+        ook, oids, oinv, ostage, omask = est.sample_instance_base(SEED, b, 0.9)
+        gok, gids, ginv, gmask = ctx.sample_instance_base(SEED, b, 0.9)
+        assert gok == ook, (b, ostage)
+        if ostage >= 1:   # a first point was drawn: the mask of this base exists
+            assert np.array_equal(gmask, omask), b
+            if any(np.array_equal(omask, m) for m in seen_masks):
+                n_cached += 1
+            seen_masks.append(omask)
+        if ook:
+            n_ok += 1
+            assert np.array_equal(gids, oids) and np.array_equal(ginv.view(np.uint32), oinv.view(np.uint32)), b
+        assert np.array_equal(ctx.class_probability().view(np.uint32), est.class_prob().view(np.uint32)), b
+    assert n_ok >= 4 and n_cached >= 3
+    assert (est.class_prob() != sc["cls"]).sum() > 100      # the prior really decayed
+    # scoring uses the decayed prior (src/stocs.cpp:1033)
+    T, _ = synth_hyp(sc, mpos)
+    lcp, inl = ctx.score_lcp(T)
+    olcp, oinl = est.score(T)
+    assert np.array_equal(inl, oinl) and np.array_equal(lcp.view(np.uint32), olcp.view(np.uint32))
+
+
+def synth_hyp(sc, mpos):
+    from model_matching_b200 import synth
+    return synth.make_hypotheses(300, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=3, near_fraction=0.3)
