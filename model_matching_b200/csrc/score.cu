@@ -46,8 +46,9 @@ constexpr int kQueue = SCORE_QUEUE; // queued queries per warp
 
 struct ScoreArgs {
   const uint4* __restrict__ bricks;
-  const uint32_t* __restrict__ coarse;   // 1 bit per brick: any occupied cell inside
-  int coarse_words;                      // words of `coarse` staged in shared memory (0: read from global)
+  const uint32_t* __restrict__ coarse;   // 1 bit per block of 2^coarse_shift cells per axis: any occupied cell inside
+  int coarse_words;                      // words of `coarse` (always staged in shared memory, <= 16 KB)
+  int coarse_shift, coarse_nx, coarse_ny;
   const uint32_t* __restrict__ starts;
   const float4* __restrict__ cand;
   const float4* __restrict__ sattr;
@@ -240,7 +241,6 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   for (int i = threadIdx.x; i < 4 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
   uint32_t* s_coarse = reinterpret_cast<uint32_t*>(s_model + 4 * Mpad);
   for (int i = threadIdx.x; i < a.coarse_words; i += blockDim.x) s_coarse[i] = a.coarse[i];
-  const bool coarse_smem = a.coarse_words > 0;
   WarpQueue& q = reinterpret_cast<WarpQueue*>(s_coarse + ((a.coarse_words + 3) & ~3))[warp];
   __syncthreads();
   const float4* mp4 = reinterpret_cast<const float4*>(s_model);  // positions as float4 (NaN beyond M)
@@ -272,34 +272,36 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
     r.acc = 0.f;
     r.inl = 0;
     int qn = 0;
-    for (int base = 0; base < M; base += 32) {
-      const int i = base + lane;
+    int i = lane;                                  // running model-point index of this lane
+    for (int base = 0; base < M; base += 32, i += 32) {
       const float4 mp = mp4[i];
       // Cell coordinates through the fused affine map (explicit FMAs: this value only selects a
       // cell, the eps-dilation margin of the index absorbs its rounding; the exact point is
-      // recomputed for queued queries).  Float->int floor saturates; NaN (padding) -> 0.
+      // recomputed for queued queries).  Float->int floor saturates; NaN (padding points,
+      // rejected fits) -> cell 0, whose queries find no candidate within eps because every
+      // distance is NaN.
       const float fx = __fmaf_rn(g0, mp.x, __fmaf_rn(g3, mp.y, __fmaf_rn(g6, mp.z, g9)));
       const float fy = __fmaf_rn(g1, mp.x, __fmaf_rn(g4, mp.y, __fmaf_rn(g7, mp.z, g10)));
       const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
-      const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
-      const bool inb = (fx == fx) && ((unsigned)ix < (unsigned)a.g.nx) && ((unsigned)iy < (unsigned)a.g.ny) &&
-                       ((unsigned)iz < (unsigned)a.g.nz);
-      const int bit = ((iz & 3) << 4) | ((iy & 3) << 2) | (ix & 3);
+      const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy), iz = (unsigned)__float2int_rd(fz);
       uint4 br = make_uint4(0u, 0u, 0u, 0u);
-      if (inb) {
-        // level 0: one bit per 4x4x4 brick (shared memory when it fits) rejects empty space
-        // without touching the brick table
-        const uint32_t bidx = (uint32_t)(((iz >> 2) * a.g.nby + (iy >> 2)) * a.g.nbx + (ix >> 2));
-        const uint32_t cw = coarse_smem ? s_coarse[bidx >> 5] : __ldg(a.coarse + (bidx >> 5));
-        if ((cw >> (bidx & 31)) & 1u) br = __ldg(a.bricks + bidx);
+      if (ix < (unsigned)a.g.nx && iy < (unsigned)a.g.ny && iz < (unsigned)a.g.nz) {
+        // level 0: one bit per block of 2^k cells per axis, staged in shared memory, rejects
+        // empty space without touching the brick table
+        const unsigned k = (unsigned)a.coarse_shift;
+        const uint32_t cidx = ((iz >> k) * (unsigned)a.coarse_ny + (iy >> k)) * (unsigned)a.coarse_nx + (ix >> k);
+        if ((s_coarse[cidx >> 5] >> (cidx & 31)) & 1u)
+          br = __ldg(a.bricks + ((iz >> 2) * (unsigned)a.g.nby + (iy >> 2)) * (unsigned)a.g.nbx + (ix >> 2));
       }
-      const unsigned long long mask = ((unsigned long long)br.y << 32) | br.x;
-      const bool has = (mask >> bit) & 1ull;
+      const unsigned bit = ((iz & 3u) << 4) | ((iy & 3u) << 2) | (ix & 3u);
+      const unsigned half = (bit & 32u) ? br.y : br.x;      // 64-bit occupancy mask as two words
+      const bool has = (half >> (bit & 31u)) & 1u;
       const unsigned hm = __ballot_sync(0xffffffffu, has);
       if (hm) {
         if (has) {
           const int slot = qn + __popc(hm & lt_mask);
-          q.a0[slot] = br.z + (uint32_t)__popcll(mask & ((1ull << bit) - 1ull));
+          const unsigned below = __popc(half & ((1u << (bit & 31u)) - 1u)) + ((bit & 32u) ? __popc(br.x) : 0u);
+          q.a0[slot] = br.z + below;
           q.pi[slot] = (uint32_t)i;
         }
         qn += __popc(hm);
@@ -345,8 +347,8 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   ScoreArgs a;
   a.bricks = ctx->d_bricks.as<uint4>();
   a.coarse = ctx->d_coarse.as<uint32_t>();
-  const int coarse_words = (int)((ctx->grid.nbricks + 31) / 32);
-  a.coarse_words = (coarse_words * 4 <= 16 * 1024) ? coarse_words : 0;
+  a.coarse_words = ctx->coarse_words;
+  a.coarse_shift = ctx->coarse_shift; a.coarse_nx = ctx->coarse_nx; a.coarse_ny = ctx->coarse_ny;
   a.starts = ctx->d_cell_start.as<uint32_t>();
   a.cand = ctx->d_cand.as<float4>();
   a.sattr = ctx->d_sattr.as<float4>();
