@@ -242,13 +242,23 @@ int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float
   STOCS_CUDA(ctx, ctx->d_T.ensure((size_t)H * 64));
   STOCS_CUDA(ctx, ctx->d_lcp.ensure((size_t)H * 4));
   STOCS_CUDA(ctx, ctx->d_inl.ensure((size_t)H * 4));
-  // chunked: the H2D copy of chunk k+1 (copy stream) overlaps the scoring of chunk k
-  const int64_t chunk = 1 << 17;
-  int64_t nchunks = (H + chunk - 1) / chunk;
+  // chunked: the H2D copy of chunk k+1 (copy stream) overlaps the scoring of chunk k.  Chunks grow
+  // geometrically (H/8, H/8, H/4, H/2) so that scoring starts early and most of the work runs in
+  // large launches.
+  std::vector<int64_t> bounds;
+  if (H <= (1 << 16)) {
+    bounds = {0, H};
+  } else {
+    const int64_t e8 = (H + 7) / 8;
+    bounds = {0, e8, 2 * e8, 4 * e8, H};
+    for (auto& b : bounds) if (b > H) b = H;
+  }
+  const int64_t nchunks = (int64_t)bounds.size() - 1;
   std::vector<cudaEvent_t> evs((size_t)nchunks, nullptr);
   int rc = STOCS_OK;
   for (int64_t c = 0; c < nchunks && rc == STOCS_OK; ++c) {
-    const int64_t off = c * chunk, n = (H - off < chunk) ? (H - off) : chunk;
+    const int64_t off = bounds[c], n = bounds[c + 1] - bounds[c];
+    if (n <= 0) continue;
     cudaError_t e = cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_T.as<float>() + off * 16, T16 + off * 16, (size_t)n * 64,
                                               cudaMemcpyHostToDevice, ctx->copy_stream);
