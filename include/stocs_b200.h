@@ -54,6 +54,18 @@ int stocs_b200_backproject(stocs_b200_ctx* ctx, const uint16_t* depth, const uin
                            int H, float fx, float cx, float fy, float cy, float depth_scale,
                            float* xyz_out, uint32_t* rgb_out);
 
+/* ---- f1: scene-cloud construction (body of rgbd::load_rgbd_data_sampled, src/rgbd.cpp:190-279) ----
+ * back-projection -> voxel-grid centroids (leaf = voxel_size) -> radius outlier removal
+ * (r = 2*voxel_size + 0.005, more than 10 neighbours) -> per centroid: 0 < z <= 2, re-projection to
+ * (row, col), class probability (uint16 / 10000) >= class_threshold, valid depth normal.
+ * class_prob: H*W uint16; edge: H*W uint8 or NULL (treated as 0).  Outputs hold up to cap points
+ * (rgb3, edge_p may be NULL); *n_out = number of points (STOCS_E_CAPACITY if > cap). */
+int stocs_b200_build_scene_cloud(stocs_b200_ctx* ctx, const uint16_t* depth, const uint8_t* bgr,
+                                 const uint16_t* class_prob, const uint8_t* edge, int W, int H, float fx,
+                                 float cx, float fy, float cy, float depth_scale, float voxel_size,
+                                 float class_threshold, float* pos3, float* nrm3, float* rgb3,
+                                 int32_t* pixel_rc, float* class_p, float* edge_p, int64_t cap, int64_t* n_out);
+
 /* ---- a2/a11: model and scene upload --------------------------------------------------------
  * upload_model replaces load_object_info's point part (src/stocs.cpp:86-97) and the model half of
  * centroid_shift (src/stocs.cpp:951-962); it also builds the compact own-bin PPF table that

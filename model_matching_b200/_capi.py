@@ -16,7 +16,7 @@ _LIB = None
 # every symbol include/stocs_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "stocs_b200_abi_version", "stocs_b200_create", "stocs_b200_destroy", "stocs_b200_last_error",
-    "stocs_b200_set_params", "stocs_b200_backproject", "stocs_b200_upload_model",
+    "stocs_b200_set_params", "stocs_b200_backproject", "stocs_b200_build_scene_cloud", "stocs_b200_upload_model",
     "stocs_b200_upload_scene", "stocs_b200_get_centroids", "stocs_b200_get_centred",
     "stocs_b200_ppf_num_pairs", "stocs_b200_ppf_num_expanded_keys", "stocs_b200_ppf_export",
     "stocs_b200_ppf_lookup", "stocs_b200_sample_bases",
@@ -57,6 +57,8 @@ def lib():
     L.stocs_b200_last_error.restype = C.c_char_p
     L.stocs_b200_set_params.argtypes = [vp, f32, i32, i32]
     L.stocs_b200_backproject.argtypes = [vp, vp, vp, i32, i32, f32, f32, f32, f32, f32, vp, vp]
+    L.stocs_b200_build_scene_cloud.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, f32, f32, f32, f32, f32, f32,
+                                               vp, vp, vp, vp, vp, vp, i64, C.POINTER(i64)]
     L.stocs_b200_upload_model.argtypes = [vp, vp, vp, i32]
     L.stocs_b200_upload_scene.argtypes = [vp, vp, vp, vp, vp, i32]
     L.stocs_b200_get_centroids.argtypes = [vp, vp, vp]
@@ -135,6 +137,26 @@ class Context:
         self._check(self._L.stocs_b200_backproject(self.h, _ptr(depth), _ptr(bgr), W, H, fx, cx, fy, cy,
                                                     depth_scale, _ptr(xyz), _ptr(rgb)))
         return xyz, rgb
+
+    # ---- f1
+    def build_scene_cloud(self, depth, bgr, prob, edge, K, depth_scale, voxel_size, class_threshold):
+        depth = np.ascontiguousarray(depth, np.uint16)
+        H, W = depth.shape
+        bgr = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        prob = np.ascontiguousarray(prob, np.uint16)
+        edge = None if edge is None else np.ascontiguousarray(edge, np.uint8)
+        cap = H * W
+        pos, nrm, rgb = (np.empty((cap, 3), np.float32) for _ in range(3))
+        pix = np.empty((cap, 2), np.int32)
+        cls, ep = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        n = C.c_int64(0)
+        self._check(self._L.stocs_b200_build_scene_cloud(self.h, _ptr(depth), _ptr(bgr), _ptr(prob), _ptr(edge), W, H,
+                                                          K[0], K[1], K[2], K[3], depth_scale, voxel_size, class_threshold,
+                                                          _ptr(pos), _ptr(nrm), _ptr(rgb), _ptr(pix), _ptr(cls), _ptr(ep),
+                                                          cap, C.byref(n)))
+        k = n.value
+        return dict(pos=pos[:k].copy(), nrm=nrm[:k].copy(), rgb=rgb[:k].copy(), pix=pix[:k].copy(), cls=cls[:k].copy(),
+                    edge=ep[:k].copy())
 
     # ---- uploads
     def upload_model(self, pos, nrm):

@@ -139,7 +139,7 @@ void load_ppf_map(std::string location, PPFMapType& m) {
   f.read((char*)m.pairs2.data(), (std::streamsize)(n * 8));
 }
 
-// ---- PCL operator restatements (host; "next" row 8f-1) ------------------------------------------
+// ---- PCL operator restatements used by the OFFLINE model preprocessing (row 8f-2) ---------------
 // pcl::VoxelGrid: centroid of every occupied leaf, output in increasing leaf index
 // (x fastest), all fields averaged.
 void voxel_grid_filter(PCLPointCloud& cloud, float leaf) {
@@ -204,24 +204,6 @@ struct HashGrid {
   }
 };
 
-// pcl::RadiusOutlierRemoval: keep points with more than min_neighbors points (itself included)
-// within `radius`; input order is preserved.
-void radius_outlier_removal(std::vector<CloudPoint>& pts, float radius, int min_neighbors) {
-  HashGrid grid(pts, radius);
-  std::vector<CloudPoint> out;
-  const float r2 = radius * radius;
-  for (auto& p : pts) {
-    int k = 0;
-    grid.for_each_near(p, [&](uint32_t j) {
-      const auto& q = pts[j];
-      const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-      if (dx * dx + dy * dy + dz * dz <= r2) ++k;
-    });
-    if (k > min_neighbors) out.push_back(p);
-  }
-  pts.swap(out);
-}
-
 // smallest-eigenvalue eigenvector of a symmetric 3x3 matrix (cyclic Jacobi)
 void smallest_eigenvector(double a[3][3], double v[3]) {
   double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
@@ -275,43 +257,9 @@ void compute_normal_pcl(PCLPointCloud::Ptr cloud, float radius) {
   }
 }
 
-// Depth-image normal at one pixel: stand-in for cv::rgbd::RgbdNormals(..., 5,
-// RGBD_NORMALS_METHOD_LINEMOD) (reference src/rgbd.cpp:202-206; opencv_contrib is not available).
-// Least-squares plane through the back-projected points of a 9x9 window (stride 2) that lie on
-// the same surface as the centre pixel (depth within 2 % + 5 mm), oriented towards the camera.
-// Returns the zero vector when the pixel has no depth or too few supporting points, which the
-// caller treats as invalid exactly as the reference does (:266).
-static void depth_normal_at(const float* xyz, int W, int H, int row, int col, float n_out[3]) {
-  n_out[0] = n_out[1] = n_out[2] = 0.f;
-  const float* c = xyz + 3 * ((size_t)row * W + col);
-  if (!(c[2] > 0)) return;
-  const float tol = 0.02f * c[2] + 0.005f;
-  double m[3] = {0, 0, 0};
-  float pts[25][3];
-  int n = 0;
-  for (int di = -4; di <= 4; di += 2)
-    for (int dj = -4; dj <= 4; dj += 2) {
-      const int i = row + di, j = col + dj;
-      if (i < 0 || i >= H || j < 0 || j >= W) continue;
-      const float* p = xyz + 3 * ((size_t)i * W + j);
-      if (!(p[2] > 0) || std::fabs(p[2] - c[2]) > tol) continue;
-      pts[n][0] = p[0]; pts[n][1] = p[1]; pts[n][2] = p[2];
-      m[0] += p[0]; m[1] += p[1]; m[2] += p[2];
-      ++n;
-    }
-  if (n < 8) return;
-  for (int k = 0; k < 3; ++k) m[k] /= n;
-  double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  for (int t = 0; t < n; ++t) {
-    const double d[3] = {pts[t][0] - m[0], pts[t][1] - m[1], pts[t][2] - m[2]};
-    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) cov[a][b] += d[a] * d[b];
-  }
-  double v[3];
-  smallest_eigenvector(cov, v);
-  if (v[0] * c[0] + v[1] * c[1] + v[2] * c[2] > 0) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
-  n_out[0] = (float)v[0]; n_out[1] = (float)v[1]; n_out[2] = (float)v[2];
-}
-
+// reference src/rgbd.cpp:179-281.  The whole body -- back-projection, VoxelGrid,
+// RadiusOutlierRemoval, re-projection, class threshold, depth normals -- runs on the GPU
+// (stocs_b200_build_scene_cloud, csrc/scene_cloud.cu); the host only decodes the PNGs.
 void load_rgbd_data_sampled(std::string rgb_location, std::string depth_location, std::string class_probability_map_location,
                             const std::vector<uint8_t>& edge_map, int edge_w, int edge_h, std::vector<float> K,
                             float depth_scale, float voxel_size, float class_probability_threshold,
@@ -327,41 +275,22 @@ void load_rgbd_data_sampled(std::string rgb_location, std::string depth_location
     std::cerr << "load_rgbd_data_sampled: cannot read " << class_probability_map_location << std::endl;
     return;
   }
-  // back-projection of every pixel on the GPU (reference src/rgbd.cpp:208-225)
-  std::vector<float> xyz((size_t)W * H * 3);
-  std::vector<uint32_t> rgb((size_t)W * H);
-  int rc = stocs_b200_backproject(ctx, depth.data(), bgr.data(), W, H, K[0], K[1], K[2], K[3], depth_scale, xyz.data(), rgb.data());
-  if (rc != 0) { std::cerr << "stocs_b200_backproject: " << stocs_b200_last_error(ctx) << std::endl; return; }
-  PCLPointCloud cloud;
-  cloud.points.resize((size_t)W * H);
-  for (size_t k = 0; k < (size_t)W * H; ++k) {
-    CloudPoint& p = cloud.points[k];
-    p.x = xyz[3 * k]; p.y = xyz[3 * k + 1]; p.z = xyz[3 * k + 2];
-    p.nx = p.ny = p.nz = 0;
-    p.r = (float)((rgb[k] >> 16) & 255); p.g = (float)((rgb[k] >> 8) & 255); p.b = (float)(rgb[k] & 255);
-  }
-  voxel_grid_filter(cloud, voxel_size);                                       // src/rgbd.cpp:227-230
-  radius_outlier_removal(cloud.points, 2 * voxel_size + 0.005f, 10);          // :232-236
-  for (auto& pt : cloud.points) {                                             // :238-279
-    if (std::isnan(pt.z) || pt.z <= 0 || pt.z > 2.0) continue;
-    const float u = K[0] * pt.x + K[1] * pt.z, v = K[2] * pt.y + K[3] * pt.z;
-    const int col = (int)(u / pt.z), row = (int)(v / pt.z);
-    if (row < 0 || row >= H || col < 0 || col >= W) continue;  // the reference reads out of bounds here
-    const float class_probability = (float)((double)(float)prob[(size_t)row * W + col] * (1.0 / 10000));
-    uint8_t e = 0;
-    if (!edge_map.empty() && row < edge_h && col < edge_w) e = edge_map[(size_t)row * edge_w + col];
-    const float edge_probability = (float)((255.0 - e) / 255.0);
-    if (class_probability < class_probability_threshold) continue;
-    float n[3];
-    depth_normal_at(xyz.data(), W, H, row, col, n);
-    if (std::isnan(n[0]) || std::isnan(n[1]) || std::isnan(n[2])) continue;
-    if (n[0] == 0 && n[1] == 0 && n[2] == 0) continue;
-    point3d.emplace_back(pt.x, pt.y, pt.z);
-    point3d.back().set_normal(Point3D::VectorType(n[0], n[1], n[2]));
-    const uint8_t* c = &bgr[3 * ((size_t)row * W + col)];
-    point3d.back().set_rgb(Point3D::VectorType((float)c[2], (float)c[1], (float)c[0]));
-    point3d.back().set_pixel(std::make_pair(row, col));
-    point3d.back().set_probability(class_probability, edge_probability);
+  const bool have_edge = !edge_map.empty() && edge_w == W && edge_h == H;
+  const int64_t cap = (int64_t)W * H;
+  std::vector<float> pos((size_t)cap * 3), nrm((size_t)cap * 3), rgb((size_t)cap * 3), cls((size_t)cap), ep((size_t)cap);
+  std::vector<int32_t> pix((size_t)cap * 2);
+  int64_t n = 0;
+  int rc = stocs_b200_build_scene_cloud(ctx, depth.data(), bgr.data(), prob.data(), have_edge ? edge_map.data() : nullptr, W, H,
+                                        K[0], K[1], K[2], K[3], depth_scale, voxel_size, class_probability_threshold, pos.data(),
+                                        nrm.data(), rgb.data(), pix.data(), cls.data(), ep.data(), cap, &n);
+  if (rc != 0) { std::cerr << "stocs_b200_build_scene_cloud: " << stocs_b200_last_error(ctx) << std::endl; return; }
+  point3d.reserve(point3d.size() + (size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    point3d.emplace_back(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    point3d.back().set_normal(Point3D::VectorType(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+    point3d.back().set_rgb(Point3D::VectorType(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]));
+    point3d.back().set_pixel(std::make_pair((int)pix[2 * i], (int)pix[2 * i + 1]));
+    point3d.back().set_probability(cls[i], ep[i]);
   }
 }
 

@@ -38,9 +38,8 @@ struct PCLPointCloud {
 
 namespace rgbd {
 
-// a1 + scene-cloud construction (reference src/rgbd.cpp:179-281).  The back-projection runs on
-// the GPU through stocs_b200_backproject; the voxel-grid / outlier / normal stages are host
-// restatements of the PCL / OpenCV operators ("next").
+// a1 + scene-cloud construction (reference src/rgbd.cpp:179-281): runs on the GPU through
+// stocs_b200_build_scene_cloud; the host decodes the PNG files.
 void load_rgbd_data_sampled(std::string rgb_location, std::string depth_location,
                             std::string class_probability_map_location,
                             const std::vector<uint8_t>& edge_probability_map, int edge_w, int edge_h,

@@ -38,6 +38,9 @@ def lib():
     L = C.CDLL(build())
     L.orc_backproject.argtypes = [u16p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_float, f32p, C.c_void_p]
+    L.orc_build_scene_cloud.restype = C.c_longlong
+    L.orc_build_scene_cloud.argtypes = [u16p, C.c_void_p, u16p, C.c_void_p, C.c_int, C.c_int] + [C.c_float] * 7 + \
+        [f32p, f32p, f32p, i32p, f32p, f32p, C.c_longlong]
     L.orc_ppf_compute.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, i32p]
     L.orc_math_eval.argtypes = [C.c_int, f32p, f32p, C.c_int, f32p]
     L.orc_philox.argtypes = [C.c_uint32] * 6 + [u32p]
@@ -90,6 +93,24 @@ def backproject(depth, bgr, fx, cx, fy, cy, depth_scale):
     lib().orc_backproject(d, b.ctypes.data if b is not None else None, W, H, fx, cx, fy, cy,
                           depth_scale, xyz, rgb.ctypes.data)
     return xyz, rgb
+
+
+def build_scene_cloud(depth, bgr, prob, edge, K, depth_scale, voxel_size, class_threshold):
+    """CPU restatement of rgbd::load_rgbd_data_sampled's body (src/rgbd.cpp:190-279)."""
+    depth = np.ascontiguousarray(depth, np.uint16)
+    H, W = depth.shape
+    bgr = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+    prob = np.ascontiguousarray(prob, np.uint16)
+    edge = None if edge is None else np.ascontiguousarray(edge, np.uint8)
+    cap = H * W
+    pos, nrm, rgb = (np.empty((cap, 3), np.float32) for _ in range(3))
+    pix = np.empty((cap, 2), np.int32)
+    cls, ep = np.empty(cap, np.float32), np.empty(cap, np.float32)
+    k = lib().orc_build_scene_cloud(depth, bgr.ctypes.data if bgr is not None else None, prob,
+                                    edge.ctypes.data if edge is not None else None, W, H, K[0], K[1], K[2], K[3],
+                                    depth_scale, voxel_size, class_threshold, pos, nrm, rgb, pix, cls, ep, cap)
+    return dict(pos=pos[:k].copy(), nrm=nrm[:k].copy(), rgb=rgb[:k].copy(), pix=pix[:k].copy(), cls=cls[:k].copy(),
+                edge=ep[:k].copy())
 
 
 def ppf_compute(p1, n1, p2, n2, tr=5, rot=5):

@@ -44,6 +44,8 @@
 #include <vector>
 
 #include "../model_matching_b200/csrc/stocs_math.h"
+#include "../model_matching_b200/csrc/stocs_scene_math.h"
+#include <unordered_map>
 
 #include <atomic>
 #include <thread>
@@ -745,6 +747,101 @@ void orc_backproject(const uint16_t* depth, const uint8_t* bgr, int W, int H, fl
         rgb[k] = ((uint32_t)bgr[3 * k + 2] << 16 | (uint32_t)bgr[3 * k + 1] << 8 |
                   (uint32_t)bgr[3 * k + 0]);
     }
+}
+
+// Scene-cloud construction, src/rgbd.cpp:190-279, restated on the CPU: stable sort of (leaf index,
+// pixel index), sequential fp32 leaf sums, hash-grid radius counting, per-centroid filters.
+long long orc_build_scene_cloud(const uint16_t* depth, const uint8_t* bgr, const uint16_t* prob, const uint8_t* edge, int W,
+                                int H, float fx, float cx, float fy, float cy, float depth_scale, float voxel_size,
+                                float class_threshold, float* pos3, float* nrm3, float* rgb3, int* pix2, float* cls,
+                                float* edgep, long long cap) {
+  const size_t n = (size_t)W * H;
+  std::vector<float> xyz(n * 3);
+  orc_backproject(depth, nullptr, W, H, fx, cx, fy, cy, depth_scale, xyz.data(), nullptr);
+  const float inv = 1.0f / voxel_size;
+  struct Item { long long z, y, x; uint32_t i; };
+  std::vector<Item> items;
+  items.reserve(n);
+  for (uint32_t k = 0; k < n; ++k) {
+    const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+    if (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z)) continue;
+    long long ijk[3];
+    stocsm::voxel_coords(x, y, z, inv, ijk);
+    items.push_back({ijk[2], ijk[1], ijk[0], k});
+  }
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+    if (a.z != b.z) return a.z < b.z;
+    if (a.y != b.y) return a.y < b.y;
+    return a.x < b.x;
+  });
+  struct Cent { float x, y, z; long long ix, iy, iz; };
+  std::vector<Cent> cent;
+  for (size_t i = 0; i < items.size();) {
+    size_t j = i;
+    float sx = 0, sy = 0, sz = 0;
+    while (j < items.size() && items[j].z == items[i].z && items[j].y == items[i].y && items[j].x == items[i].x) {
+      const uint32_t k = items[j].i;
+      sx += xyz[3 * k]; sy += xyz[3 * k + 1]; sz += xyz[3 * k + 2];
+      ++j;
+    }
+    const float c = (float)(j - i);
+    cent.push_back({sx / c, sy / c, sz / c, items[i].x, items[i].y, items[i].z});
+    i = j;
+  }
+  // radius outlier removal through a hash grid with cell = radius
+  const double radius = (double)(2 * voxel_size) + 0.005;
+  const float r2 = (float)(radius * radius);
+  const float ginv = (float)(1.0 / radius);
+  auto gkey = [](long long x, long long y, long long z) {
+    return ((uint64_t)(x & 0x1fffff) << 42) | ((uint64_t)(y & 0x1fffff) << 21) | (uint64_t)(z & 0x1fffff);
+  };
+  std::unordered_map<uint64_t, std::vector<uint32_t>> grid;
+  for (uint32_t i = 0; i < cent.size(); ++i)
+    grid[gkey((long long)std::floor(cent[i].x * ginv), (long long)std::floor(cent[i].y * ginv),
+              (long long)std::floor(cent[i].z * ginv))].push_back(i);
+  long long nout = 0;
+  for (uint32_t i = 0; i < cent.size(); ++i) {
+    const Cent& p = cent[i];
+    const long long gx = (long long)std::floor(p.x * ginv), gy = (long long)std::floor(p.y * ginv), gz = (long long)std::floor(p.z * ginv);
+    int k = 0;
+    for (long long z = gz - 1; z <= gz + 1; ++z)
+      for (long long y = gy - 1; y <= gy + 1; ++y)
+        for (long long x = gx - 1; x <= gx + 1; ++x) {
+          auto it = grid.find(gkey(x, y, z));
+          if (it == grid.end()) continue;
+          for (uint32_t j : it->second) {
+            const float ex = p.x - cent[j].x, ey = p.y - cent[j].y, ez = p.z - cent[j].z;
+            if ((ex * ex + ey * ey) + ez * ez <= r2) ++k;
+          }
+        }
+    if (!(k > 10)) continue;
+    if (std::isnan(p.z) || p.z <= 0 || p.z > 2.0) continue;
+    int row, col;
+    stocsm::reproject(p.x, p.y, p.z, fx, cx, fy, cy, &row, &col);
+    if (row < 0 || row >= H || col < 0 || col >= W) continue;
+    const size_t px = (size_t)row * W + col;
+    const float class_probability = (float)prob[px] * (1.0 / 10000);
+    const float edge_probability = (float)(255.0 - (edge ? edge[px] : 0)) / 255.0;
+    if (class_probability < class_threshold) continue;
+    float nr[3];
+    stocsm::depth_normal_at(xyz.data(), W, H, row, col, nr);
+    if (std::isnan(nr[0]) || std::isnan(nr[1]) || std::isnan(nr[2])) continue;
+    if (nr[0] == 0 && nr[1] == 0 && nr[2] == 0) continue;
+    if (nout < cap) {
+      pos3[3 * nout] = p.x; pos3[3 * nout + 1] = p.y; pos3[3 * nout + 2] = p.z;
+      const V3 nn = stocsm::normalized(v3(nr[0], nr[1], nr[2]));
+      nrm3[3 * nout] = nn.x; nrm3[3 * nout + 1] = nn.y; nrm3[3 * nout + 2] = nn.z;
+      if (rgb3) {
+        rgb3[3 * nout] = bgr ? (float)bgr[3 * px + 2] : 0.f; rgb3[3 * nout + 1] = bgr ? (float)bgr[3 * px + 1] : 0.f;
+        rgb3[3 * nout + 2] = bgr ? (float)bgr[3 * px] : 0.f;
+      }
+      pix2[2 * nout] = row; pix2[2 * nout + 1] = col;
+      cls[nout] = class_probability;
+      if (edgep) edgep[nout] = edge_probability;
+    }
+    ++nout;
+  }
+  return nout;
 }
 
 void orc_ppf_compute(const float* p1, const float* n1, const float* p2, const float* n2, int n,
