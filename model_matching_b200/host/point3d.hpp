@@ -29,6 +29,8 @@ class Point3D {
 
   void set_rgb(const VectorType& rgb) { rgb_ = rgb; }
   void set_normal(const VectorType& n) { normal_ = n.normalized(); }
+  // addition: store a normal that is already the result of set_normal (GPU-built scene cloud)
+  void set_unit_normal(const VectorType& n) { normal_ = n; }
   void set_pixel(const std::pair<int, int>& p) { pixel_ = p; }
   void set_probability(float class_probability, float edge_probability) {
     class_probability_ = class_probability;

@@ -287,7 +287,7 @@ void load_rgbd_data_sampled(std::string rgb_location, std::string depth_location
   point3d.reserve(point3d.size() + (size_t)n);
   for (int64_t i = 0; i < n; ++i) {
     point3d.emplace_back(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
-    point3d.back().set_normal(Point3D::VectorType(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+    point3d.back().set_unit_normal(Point3D::VectorType(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));  // normalised on the device
     point3d.back().set_rgb(Point3D::VectorType(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]));
     point3d.back().set_pixel(std::make_pair((int)pix[2 * i], (int)pix[2 * i + 1]));
     point3d.back().set_probability(cls[i], ep[i]);
