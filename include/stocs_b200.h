@@ -156,6 +156,13 @@ int stocs_b200_reduce_best_device(stocs_b200_ctx* ctx, const float* d_lcp, int64
                                   int64_t index_offset, int64_t* d_topk_index, float* d_topk_lcp,
                                   void* stream);
 
+/* Every hypothesis with lcp > threshold (and > 0), ordered by (lcp descending, index ascending):
+ * the filter + sort that opens clustering::greedy_clustering (src/pose_clustering.cpp:93-101).
+ * lcp == NULL uses the resident array of the last score call.  STOCS_E_CAPACITY (with *n_out set)
+ * when more than cap qualify. */
+int stocs_b200_select_above(stocs_b200_ctx* ctx, const float* lcp, int64_t H, float threshold,
+                            int64_t* index_out, float* lcp_out, int64_t cap, int64_t* n_out);
+
 /* ---- fused online pipeline (run_stocs_estimation, src/stocs_match_one_object.cpp:79-165) ----
  * sample n_bases bases -> congruent sets -> at most max_sets transforms per base (the first
  * max_sets quads in set order when a base has more; see DESIGN.md on quirk 5) -> score -> best.

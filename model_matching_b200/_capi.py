@@ -22,7 +22,7 @@ SYMBOLS = [
     "stocs_b200_ppf_lookup", "stocs_b200_sample_bases",
     "stocs_b200_upload_edge_map", "stocs_b200_sample_instance_base", "stocs_b200_get_class_probability",
     "stocs_b200_find_congruent", "stocs_b200_fit_transforms", "stocs_b200_score_lcp",
-    "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device",
+    "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device", "stocs_b200_select_above",
     "stocs_b200_run_pipeline", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
 ]
 
@@ -77,6 +77,7 @@ def lib():
     L.stocs_b200_score_lcp_device.argtypes = [vp, vp, i64, vp, vp, vp]
     L.stocs_b200_reduce_best.argtypes = [vp, vp, i64, i32, C.POINTER(i64), C.POINTER(f32), vp, vp]
     L.stocs_b200_reduce_best_device.argtypes = [vp, vp, i64, i32, i64, vp, vp, vp]
+    L.stocs_b200_select_above.argtypes = [vp, vp, i64, f32, vp, vp, i64, C.POINTER(i64)]
     L.stocs_b200_run_pipeline.argtypes = [vp, u64, i32, i32, C.POINTER(PipelineResult)]
     L.stocs_b200_get_counters.argtypes = [vp, vp, i32]
     L.stocs_b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
@@ -291,6 +292,14 @@ class Context:
         self._check(self._L.stocs_b200_reduce_best(self.h, _ptr(lcp), H, K, C.byref(bi), C.byref(bl),
                                                     _ptr(ti), _ptr(tl)))
         return bi.value, bl.value, ti, tl
+
+    def select_above(self, lcp, threshold):
+        lcp = _f32(lcp, (-1,))
+        n = C.c_int64(0)
+        idx, val = np.empty(lcp.size, np.int64), np.empty(lcp.size, np.float32)
+        self._check(self._L.stocs_b200_select_above(self.h, _ptr(lcp), lcp.size, threshold, _ptr(idx), _ptr(val),
+                                                     lcp.size, C.byref(n)))
+        return idx[:n.value].copy(), val[:n.value].copy()
 
     def reduce_best_device(self, dlcp_ptr, H, K, index_offset, didx_ptr, dval_ptr, stream=None):
         self._check(self._L.stocs_b200_reduce_best_device(self.h, dlcp_ptr, H, K, index_offset, didx_ptr,

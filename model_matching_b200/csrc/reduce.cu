@@ -7,6 +7,9 @@
 // smaller index.  Each warp keeps a sorted top-32 across its lanes (lane j = j-th best) and
 // inserts with one ballot + shuffle per surviving key; a single-warp kernel merges the per-warp
 // lists.  Memory traffic: one read of the LCP array.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
 #include "stocs_ctx.h"
 
 namespace {
@@ -79,7 +82,70 @@ __global__ void __launch_bounds__(1024) topk_merge_kernel(const unsigned long lo
   }
 }
 
+__global__ void above_keys_kernel(const float* __restrict__ lcp, long long H, float thr, unsigned long long* __restrict__ keys) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H) return;
+  const float v = lcp[i];
+  keys[i] = (v > thr && v > 0.f) ? make_key(v, (unsigned long long)i) : 0ull;
+}
+struct NonZero { __device__ bool operator()(unsigned long long k) const { return k != 0ull; } };
+__global__ void unpack_keys_kernel(const unsigned long long* __restrict__ keys, long long n, long long* __restrict__ idx,
+                                   float* __restrict__ val) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  idx[i] = (long long)(0xffffffffull - (keys[i] & 0xffffffffull));
+  val[i] = __uint_as_float((unsigned)(keys[i] >> 32));
+}
+
 }  // namespace
+
+// All hypotheses with lcp > threshold, ordered by (lcp descending, index ascending): the filter +
+// sort that opens clustering::greedy_clustering (reference src/pose_clustering.cpp:93-101).
+extern "C" int stocs_b200_select_above(stocs_b200_ctx* ctx, const float* lcp, int64_t H, float threshold,
+                                       int64_t* index_out, float* lcp_out, int64_t cap, int64_t* n_out) {
+  if (!ctx) return STOCS_E_ARG;
+  if (H < 0 || H >= (1ll << 31) || !n_out || cap < 0) STOCS_FAIL(ctx, STOCS_E_ARG, "select_above: bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  *n_out = 0;
+  if (H == 0) return STOCS_OK;
+  const float* d_src = nullptr;
+  if (lcp) {
+    STOCS_CUDA(ctx, ctx->d_lcp.ensure((size_t)H * 4));
+    STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_lcp.p, lcp, (size_t)H * 4, cudaMemcpyHostToDevice, st));
+    ctx->last_H = H;
+  } else if (ctx->last_H != H || !ctx->d_lcp.p) {
+    STOCS_FAIL(ctx, STOCS_E_STATE, "select_above: no resident lcp array of that size");
+  }
+  d_src = ctx->d_lcp.as<float>();
+  DevBuf ka, kb, tmp, cnt, oi, ov;
+  auto cleanup = [&]() { ka.release(); kb.release(); tmp.release(); cnt.release(); oi.release(); ov.release(); };
+#define SA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
+  SA(ka.ensure((size_t)H * 8)); SA(kb.ensure((size_t)H * 8)); SA(cnt.ensure(16));
+  above_keys_kernel<<<(unsigned)((H + 255) / 256), 256, 0, st>>>(d_src, H, threshold, ka.as<unsigned long long>());
+  size_t tb = 0, tb2 = 0;
+  cub::DeviceSelect::If(nullptr, tb, ka.as<unsigned long long>(), kb.as<unsigned long long>(), cnt.as<int>(), (int)H, NonZero(), st);
+  cub::DeviceRadixSort::SortKeysDescending(nullptr, tb2, kb.as<unsigned long long>(), ka.as<unsigned long long>(), (int)H, 0, 64, st);
+  SA(tmp.ensure(tb > tb2 ? tb : tb2));
+  cub::DeviceSelect::If(tmp.p, tb, ka.as<unsigned long long>(), kb.as<unsigned long long>(), cnt.as<int>(), (int)H, NonZero(), st);
+  int n = 0;
+  SA(cudaMemcpyAsync(&n, cnt.p, 4, cudaMemcpyDeviceToHost, st));
+  SA(cudaStreamSynchronize(st));
+  *n_out = n;
+  if (n > cap) { cleanup(); STOCS_FAIL(ctx, STOCS_E_CAPACITY, "select_above: capacity too small"); }
+  if (n > 0) {
+    if (!index_out || !lcp_out) { cleanup(); STOCS_FAIL(ctx, STOCS_E_ARG, "select_above: output pointer is NULL"); }
+    cub::DeviceRadixSort::SortKeysDescending(tmp.p, tb2, kb.as<unsigned long long>(), ka.as<unsigned long long>(), n, 0, 64, st);
+    SA(oi.ensure((size_t)n * 8)); SA(ov.ensure((size_t)n * 4));
+    unpack_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(ka.as<unsigned long long>(), n, oi.as<long long>(), ov.as<float>());
+    SA(cudaMemcpyAsync(index_out, oi.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    SA(cudaMemcpyAsync(lcp_out, ov.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    SA(cudaStreamSynchronize(st));
+  }
+#undef SA
+  cleanup();
+  return STOCS_OK;
+}
 
 int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
                       int64_t* d_idx, float* d_val, cudaStream_t st) {

@@ -129,3 +129,17 @@ def test_backproject_bit_exact(gpu_ctx):
     assert none is None
     oxyz2, _ = oracle.backproject(depth[:7, :5].copy(), None, fx, cx, fy, cy, 1 / 8000.0)
     assert np.array_equal(xyz2.view(np.uint32), oxyz2.view(np.uint32))
+
+
+def test_select_above_is_the_clustering_prefilter(gpu_ctx):
+    rng = np.random.default_rng(4)
+    lcp = rng.uniform(0, 1, 50000).astype(np.float32)
+    lcp[rng.integers(0, lcp.size, 100)] = np.float32(0.75)    # equal scores: index ascending
+    best = float(lcp.max())
+    thr = np.float32(0.7) * np.float32(best)
+    idx, val = gpu_ctx.select_above(lcp, float(thr))
+    keep = np.flatnonzero(lcp > thr)
+    order = keep[np.lexsort((keep, -lcp[keep].astype(np.float64)))]
+    assert np.array_equal(idx, order) and np.array_equal(val, lcp[order])
+    idx0, _ = gpu_ctx.select_above(np.zeros(10, np.float32), 0.0)
+    assert idx0.size == 0
