@@ -132,6 +132,24 @@ def pose_latency(ctx_factory, with_cpu):
     out = {"workload": "YCB 024_bowl example scene (|S|=%d, |M|=%d), 100 bases, <=200 sets/base" % (len(g["spos"]), len(g["mpos"])),
            "gpu_ms_per_pose": 1e3 * float(np.median(times)), "gpu_upload_index_ms": 1e3 * t_upload,
            "transforms_scored": int(res.n_transforms), "congruent_sets": int(res.n_congruent_sets)}
+    try:  # frame -> scene cloud (src/rgbd.cpp:190-279) on the device, PNG decoding excluded
+        import cv2
+        d = os.path.join(ROOT, "tests", "golden", "examples", "ycb")
+        depth = cv2.imread(os.path.join(d, "depth.png"), cv2.IMREAD_UNCHANGED)
+        bgr = cv2.imread(os.path.join(d, "rgb.png"), cv2.IMREAD_COLOR)
+        prob = cv2.imread(os.path.join(d, "probability_maps", "024_bowl.png"), cv2.IMREAD_UNCHANGED)
+        K = [1066.778, 312.986, 1067.487, 241.310]
+        ctx.build_scene_cloud(depth, bgr, prob, None, K, 1 / 10000.0, 0.005, 0.10)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            sc = ctx.build_scene_cloud(depth, bgr, prob, None, K, 1 / 10000.0, 0.005, 0.10)
+            ts.append(time.perf_counter() - t0)
+        out["gpu_scene_cloud_ms"] = 1e3 * float(np.median(ts))
+        out["scene_cloud_points"] = int(len(sc["pos"]))
+    except Exception as e:  # cv2 missing or data absent: the headline numbers do not depend on it
+        out["gpu_scene_cloud_ms"] = None
+        out["scene_cloud_error"] = str(e)[:100]
     ctx.close()
     if with_cpu:
         import oracle
