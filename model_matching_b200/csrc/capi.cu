@@ -83,6 +83,7 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
                     &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_small, &ctx->d_edge, &ctx->d_inst_state, &ctx->d_mask_store,
                     &ctx->d_frontier};
   for (DevBuf* b : bufs) b->release();
+  for (DevBuf& b : ctx->pool) b.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

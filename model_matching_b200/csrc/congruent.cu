@@ -291,11 +291,10 @@ int stocs_congruent_device(stocs_b200_ctx* ctx, int n_bases, const int* d_base_i
   h_quad_off.assign((size_t)n_bases + 1, 0);
   if (n_bases == 0) return STOCS_OK;
   const PpfView v = stocs_ppf_view(ctx);
-  DevBuf d_info, d_seg, d_codes_a, d_codes_b, d_tmp, d_pe, d_qe, d_qcell, d_cnt, d_scan, d_qoff;
-  auto cleanup = [&]() {
-    DevBuf* all[] = {&d_info, &d_seg, &d_codes_a, &d_codes_b, &d_tmp, &d_pe, &d_qe, &d_qcell, &d_cnt, &d_scan, &d_qoff};
-    for (DevBuf* b : all) b->release();
-  };
+  DevBuf &d_info = ctx->pool[0], &d_seg = ctx->pool[1], &d_codes_a = ctx->pool[2], &d_codes_b = ctx->pool[3], &d_tmp = ctx->pool[4],
+         &d_pe = ctx->pool[5], &d_qe = ctx->pool[6], &d_qcell = ctx->pool[7], &d_cnt = ctx->pool[8], &d_scan = ctx->pool[9],
+         &d_qoff = ctx->pool[10];
+  auto cleanup = [&]() {};  // pool slots persist
 #define CG(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
   CG(d_info.ensure((size_t)n_bases * sizeof(BaseInfo)));
   cong_count_kernel<<<n_bases, 256, 0, st>>>(ctx->d_spos4.as<float4>(), ctx->d_sattr.as<float4>(), v, d_base_idx4, d_inv2,
@@ -381,18 +380,17 @@ extern "C" int stocs_b200_find_congruent(stocs_b200_ctx* ctx, int n_bases, const
     STOCS_CUDA(ctx, cudaMemcpyAsync(d_ids, base_idx4, (size_t)n_bases * 16, cudaMemcpyHostToDevice, st));
     STOCS_CUDA(ctx, cudaMemcpyAsync(d_inv, inv2, (size_t)n_bases * 8, cudaMemcpyHostToDevice, st));
   }
-  DevBuf quads;
+  DevBuf& quads = ctx->pool[11];
   std::vector<long long> off;
   int rc = stocs_congruent_device(ctx, n_bases, d_ids, d_inv, quads, off, st);
-  if (rc) { quads.release(); return rc; }
+  if (rc) return rc;
   for (int b = 0; b <= n_bases; ++b) quad_offsets[b] = off[b];
   const long long total = off[n_bases];
-  if (total > cap) { quads.release(); STOCS_FAIL(ctx, STOCS_E_CAPACITY, "find_congruent: quads4 capacity too small"); }
+  if (total > cap) STOCS_FAIL(ctx, STOCS_E_CAPACITY, "find_congruent: quads4 capacity too small");
   if (total > 0) {
-    if (!quads4) { quads.release(); STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: quads4 is NULL"); }
+    if (!quads4) STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: quads4 is NULL");
     STOCS_CUDA(ctx, cudaMemcpyAsync(quads4, quads.p, (size_t)total * 16, cudaMemcpyDeviceToHost, st));
     STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   }
-  quads.release();
   return STOCS_OK;
 }

@@ -174,13 +174,13 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   result->best_index = -1;
   result->best_base = -1;
   // 1. bases
-  DevBuf d_bases;
+  DevBuf& d_bases = ctx->pool[0 + 31 - 0];
   STOCS_CUDA(ctx, d_bases.ensure((size_t)n_bases * 25 + 64));
   int* d_ids = d_bases.as<int>();
   float* d_inv = (float*)(d_ids + 4 * (size_t)n_bases);
   uint8_t* d_valid = (uint8_t*)(d_inv + 2 * (size_t)n_bases);
   int rc = stocs_launch_sample(ctx, seed, 0, n_bases, d_ids, d_inv, d_valid, st);
-  if (rc) { d_bases.release(); return rc; }
+  if (rc) return rc;
   std::vector<int> h_ids((size_t)4 * n_bases);
   std::vector<float> h_inv((size_t)2 * n_bases);
   std::vector<uint8_t> h_valid((size_t)n_bases);
@@ -197,14 +197,14 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
     }
   const int nv = (int)(v_ids.size() / 4);
   result->n_valid_bases = nv;
-  if (nv == 0) { d_bases.release(); return STOCS_OK; }
+  if (nv == 0) return STOCS_OK;
   STOCS_CUDA(ctx, cudaMemcpyAsync(d_ids, v_ids.data(), (size_t)nv * 16, cudaMemcpyHostToDevice, st));
   STOCS_CUDA(ctx, cudaMemcpyAsync(d_inv, v_inv.data(), (size_t)nv * 8, cudaMemcpyHostToDevice, st));
   // 2. congruent sets
-  DevBuf d_quads;
+  DevBuf& d_quads = ctx->pool[11];
   std::vector<long long> quad_off;
   rc = stocs_congruent_device(ctx, nv, d_ids, d_inv, d_quads, quad_off, st);
-  if (rc) { d_bases.release(); d_quads.release(); return rc; }
+  if (rc) return rc;
   result->n_congruent_sets = quad_off[nv];
   // 3. at most max_sets transforms per base
   std::vector<long long> item_off((size_t)nv + 1, 0);
@@ -213,9 +213,9 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
     item_off[b + 1] = item_off[b] + (cnt < max_sets ? cnt : max_sets);
   }
   const long long n_items = item_off[nv];
-  if (n_items == 0) { d_bases.release(); d_quads.release(); return STOCS_OK; }
-  DevBuf d_off, d_items, d_fit;
-  auto cleanup = [&]() { d_bases.release(); d_quads.release(); d_off.release(); d_items.release(); d_fit.release(); };
+  if (n_items == 0) return STOCS_OK;
+  DevBuf &d_off = ctx->pool[28], &d_items = ctx->pool[29], &d_fit = ctx->pool[30];
+  auto cleanup = [&]() {};  // pool slots persist
 #define PL(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
   PL(d_off.ensure((size_t)(nv + 1) * 16));
   long long* d_qoff = d_off.as<long long>();

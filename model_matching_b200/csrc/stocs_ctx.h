@@ -101,6 +101,8 @@ struct stocs_b200_ctx {
   DevBuf d_ppf_keybits;                // bitmap of keys present in the reference's expanded map
   std::vector<uint32_t> h_ppf_bin_start, h_ppf_pairs;
 
+  // grow-only scratch slots reused by the multi-kernel stages (no cudaMalloc/cudaFree per call)
+  DevBuf pool[32];
   // scratch
   DevBuf d_T, d_lcp, d_inl, d_work, d_tmp, d_tmp2, d_small;
   void* h_pinned = nullptr;
