@@ -334,7 +334,7 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   const float r = (float)(eps * (1.0 + 1.0 / 256.0) + cell / 256.0);
 
   size_t nc1 = (size_t)g.ncells + 1;
-  DevBuf d_dense;  // dense per-cell starts (temporary)
+  DevBuf& d_dense = ctx->pool[12];  // dense per-cell starts (scratch)
   STOCS_CUDA(ctx, d_dense.ensure(nc1 * 4));
   STOCS_CUDA(ctx, ctx->d_work.ensure(nc1 * 4));
   uint32_t* counts = ctx->d_work.as<uint32_t>();
@@ -353,7 +353,7 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
   grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>());
   // brick table + compact starts
-  DevBuf d_masks, d_occ, d_occ_scan;
+  DevBuf &d_masks = ctx->pool[13], &d_occ = ctx->pool[14], &d_occ_scan = ctx->pool[15];
   STOCS_CUDA(ctx, d_masks.ensure((size_t)g.nbricks * 8));
   STOCS_CUDA(ctx, d_occ.ensure((size_t)(g.nbricks + 1) * 4));
   STOCS_CUDA(ctx, d_occ_scan.ensure((size_t)(g.nbricks + 1) * 4));
@@ -383,7 +383,6 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
                                          ctx->d_coarse.as<uint32_t>(), g, cshift, cnx, cny);
   STOCS_CUDA(ctx, cudaGetLastError());
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
-  d_dense.release(); d_masks.release(); d_occ.release(); d_occ_scan.release();
   ctx->counters[4] = n_occ;
 
   // reference kd-tree (tie resolution only)
