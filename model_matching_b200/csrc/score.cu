@@ -6,10 +6,14 @@
 //
 // One warp per hypothesis, persistent CTAs, dynamic work counter.  Model points live in shared
 // memory (SoA, conflict-free).
-//   Phase A (per 32 model points): every lane transforms one point and reads ONE 16-byte brick
-//     record of the eps-dilated voxel grid (64-bit occupancy mask + rank base).  Lanes whose
-//     cell is occupied are compacted (ballot + popc rank) into a per-warp shared-memory queue that
-//     runs ACROSS rounds, in model-point order.
+//   Phase A (per block of 256 model points), two loops:
+//     1. the test every point takes: fused affine map "transform o world->grid" (9 FMAs), floor,
+//        one bit of a multi-resolution occupancy bitmap held in shared memory; survivors (~35 %)
+//        are compacted, in model-point order, into a per-warp byte list;
+//     2. survivors only, 32 at a time: ONE 16-byte brick record of the eps-dilated voxel grid
+//        (64-bit occupancy mask + rank base); lanes whose cell is occupied are compacted (ballot +
+//        popc rank) into a per-warp shared-memory queue that runs ACROSS rounds, in model-point
+//        order.
 //   Phase B (queue nearly full, or end of the model):
 //     1. 32 lanes fetch the candidate-list offsets of 32 queued queries at once;
 //     2. 8-lane groups scan one queued query each: the float4 candidate records of a query are
@@ -31,7 +35,7 @@ namespace {
 #define SCORE_GROUP 4
 #endif
 #ifndef SCORE_QUEUE
-#define SCORE_QUEUE 96
+#define SCORE_QUEUE 64
 #endif
 #ifndef SCORE_MIN_BLOCKS
 #define SCORE_MIN_BLOCKS 2
@@ -132,6 +136,7 @@ struct WarpQueue {   // one per warp, static shared memory (single base register
   uint32_t a0[kQueue];   // occupied-cell rank -> candidate offset -> matched scene index (or -1)
   uint32_t a1[kQueue];   // candidate count
   uint32_t pi[kQueue];   // model point index
+  uint8_t plist[256];    // phase A: survivors of the coarse test within the current 256-point block
 };
 
 struct Acc { float acc; int inl; unsigned ties; };
@@ -272,48 +277,67 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
     r.acc = 0.f;
     r.inl = 0;
     int qn = 0;
-    int i = lane;                                  // running model-point index of this lane
-    for (int base = 0; base < M; base += 32, i += 32) {
-      const float4 mp = mp4[i];
-      // Cell coordinates through the fused affine map (explicit FMAs: this value only selects a
-      // cell, the eps-dilation margin of the index absorbs its rounding; the exact point is
-      // recomputed for queued queries).  Float->int floor saturates; NaN (padding points,
-      // rejected fits) -> cell 0, whose queries find no candidate within eps because every
-      // distance is NaN.
-      const float fx = __fmaf_rn(g0, mp.x, __fmaf_rn(g3, mp.y, __fmaf_rn(g6, mp.z, g9)));
-      const float fy = __fmaf_rn(g1, mp.x, __fmaf_rn(g4, mp.y, __fmaf_rn(g7, mp.z, g10)));
-      const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
-      const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy), iz = (unsigned)__float2int_rd(fz);
-      uint4 br = make_uint4(0u, 0u, 0u, 0u);
-      if (ix < (unsigned)a.g.nx && iy < (unsigned)a.g.ny && iz < (unsigned)a.g.nz) {
-        // level 0: one bit per block of 2^k cells per axis, staged in shared memory, rejects
-        // empty space without touching the brick table
-        const unsigned k = (unsigned)a.coarse_shift;
-        const uint32_t cidx = ((iz >> k) * (unsigned)a.coarse_ny + (iy >> k)) * (unsigned)a.coarse_nx + (ix >> k);
-        if ((s_coarse[cidx >> 5] >> (cidx & 31)) & 1u)
-          br = __ldg(a.bricks + ((iz >> 2) * (unsigned)a.g.nby + (iy >> 2)) * (unsigned)a.g.nbx + (ix >> 2));
-      }
-      const unsigned bit = ((iz & 3u) << 4) | ((iy & 3u) << 2) | (ix & 3u);
-      const unsigned half = (bit & 32u) ? br.y : br.x;      // 64-bit occupancy mask as two words
-      const bool has = (half >> (bit & 31u)) & 1u;
-      const unsigned hm = __ballot_sync(0xffffffffu, has);
-      if (hm) {
-        if (has) {
-          const int slot = qn + __popc(hm & lt_mask);
-          const unsigned below = __popc(half & ((1u << (bit & 31u)) - 1u)) + ((bit & 32u) ? __popc(br.x) : 0u);
-          q.a0[slot] = br.z + below;
-          q.pi[slot] = (uint32_t)i;
+    // Phase A runs over blocks of 256 model points in two loops.  Loop 1 is the cheap test every
+    // point takes: fused affine map -> cell -> one bit of the shared-memory coarse occupancy map;
+    // the survivors' indices are compacted, in model-point order, into a byte list.  Loop 2 visits
+    // only the survivors, 32 at a time: brick record, exact cell bit, enqueue.  (Explicit FMAs: the
+    // map only selects a cell, the eps-dilation margin of the index absorbs its rounding; the exact
+    // point is recomputed for queued queries.  Float->int floor saturates; NaN -- padding points,
+    // rejected fits -- gives cell 0, whose queries find no candidate because every distance is NaN.)
+    for (int blk = 0; blk < M; blk += 256) {
+      int nl = 0;
+      const int rounds = min(8, (M - blk + 31) >> 5);
+      for (int rr = 0; rr < rounds; ++rr) {
+        const float4 mp = mp4[blk + rr * 32 + lane];
+        const float fx = __fmaf_rn(g0, mp.x, __fmaf_rn(g3, mp.y, __fmaf_rn(g6, mp.z, g9)));
+        const float fy = __fmaf_rn(g1, mp.x, __fmaf_rn(g4, mp.y, __fmaf_rn(g7, mp.z, g10)));
+        const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
+        const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy), iz = (unsigned)__float2int_rd(fz);
+        bool pass = false;
+        if (ix < (unsigned)a.g.nx && iy < (unsigned)a.g.ny && iz < (unsigned)a.g.nz) {
+          const unsigned k = (unsigned)a.coarse_shift;
+          const uint32_t cidx = ((iz >> k) * (unsigned)a.coarse_ny + (iy >> k)) * (unsigned)a.coarse_nx + (ix >> k);
+          pass = (s_coarse[cidx >> 5] >> (cidx & 31)) & 1u;
         }
-        qn += __popc(hm);
+        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+        if (pass) q.plist[nl + __popc(pm & lt_mask)] = (uint8_t)(rr * 32 + lane);
+        nl += __popc(pm);
       }
-      if (qn > kQueue - 32 || (base + 32 >= M && qn > 0)) {
-        drain_queue(a, q, qn, lane, mp4, mn4, r);
-        qn = 0;
-        // the map is re-read after a drain so that it is not live (in registers) across it
-        g0 = q.G[0]; g1 = q.G[1]; g2 = q.G[2]; g3 = q.G[3]; g4 = q.G[4]; g5 = q.G[5];
-        g6 = q.G[6]; g7 = q.G[7]; g8 = q.G[8]; g9 = q.G[9]; g10 = q.G[10]; g11 = q.G[11];
+      __syncwarp();
+      for (int e0 = 0; e0 < nl; e0 += 32) {
+        const bool valid = e0 + lane < nl;
+        const int i = blk + (valid ? (int)q.plist[e0 + lane] : 0);
+        const float4 mp = mp4[i];
+        const float fx = __fmaf_rn(g0, mp.x, __fmaf_rn(g3, mp.y, __fmaf_rn(g6, mp.z, g9)));
+        const float fy = __fmaf_rn(g1, mp.x, __fmaf_rn(g4, mp.y, __fmaf_rn(g7, mp.z, g10)));
+        const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
+        const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy), iz = (unsigned)__float2int_rd(fz);
+        uint4 br = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) br = __ldg(a.bricks + ((iz >> 2) * (unsigned)a.g.nby + (iy >> 2)) * (unsigned)a.g.nbx + (ix >> 2));
+        const unsigned bit = ((iz & 3u) << 4) | ((iy & 3u) << 2) | (ix & 3u);
+        const unsigned half = (bit & 32u) ? br.y : br.x;      // 64-bit occupancy mask as two words
+        const bool has = (half >> (bit & 31u)) & 1u;
+        const unsigned hm = __ballot_sync(0xffffffffu, has);
+        if (hm) {
+          if (has) {
+            const int slot = qn + __popc(hm & lt_mask);
+            const unsigned below = __popc(half & ((1u << (bit & 31u)) - 1u)) + ((bit & 32u) ? __popc(br.x) : 0u);
+            q.a0[slot] = br.z + below;
+            q.pi[slot] = (uint32_t)i;
+          }
+          qn += __popc(hm);
+        }
+        if (qn > kQueue - 32) {
+          drain_queue(a, q, qn, lane, mp4, mn4, r);
+          qn = 0;
+          // the map is re-read after a drain so that it is not live (in registers) across it
+          g0 = q.G[0]; g1 = q.G[1]; g2 = q.G[2]; g3 = q.G[3]; g4 = q.G[4]; g5 = q.G[5];
+          g6 = q.G[6]; g7 = q.G[7]; g8 = q.G[8]; g9 = q.G[9]; g10 = q.G[10]; g11 = q.G[11];
+        }
       }
+      __syncwarp();
     }
+    if (qn > 0) drain_queue(a, q, qn, lane, mp4, mn4, r);
     if (lane == 0) {
       a.lcp[h] = r.acc / (float)M;
       if (a.inl) a.inl[h] = r.inl;
