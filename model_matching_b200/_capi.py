@@ -230,7 +230,8 @@ class Context:
 
     def sample_instance_base(self, seed, base_num, dispersion=0.9, want_mask=True):
         ids, inv, valid = np.empty(4, np.int32), np.empty(2, np.float32), np.zeros(1, np.uint8)
-        mask = np.zeros(self._edge_shape, np.uint8) if want_mask else None
+        shape = getattr(self, "_edge_shape", None)
+        mask = np.zeros(shape, np.uint8) if (want_mask and shape is not None) else None
         self._check(self._L.stocs_b200_sample_instance_base(self.h, int(seed), int(base_num), dispersion, _ptr(ids),
                                                              _ptr(inv), _ptr(valid), _ptr(mask), None))
         return bool(valid[0]), ids, inv, mask
