@@ -12,8 +12,8 @@
 //    PCL's accumulation) -> centroids in increasing leaf order.  All zero-depth pixels sit at
 //    (0,0,0): they add nothing to a sum, so one representative is sorted and the others only count.
 //  * RadiusOutlierRemoval: a centroid's neighbours within r = 2*leaf + 0.005 lie within
-//    ceil(r/leaf)+1 leaves per axis: binary searches in the sorted leaf keys; keep when more than
-//    10 centroids (itself included) are within r.
+//    ceil(r/leaf)+1 leaves per axis; the sorted leaf keys make every (dz,dy) row one binary search
+//    plus a linear walk; keep when more than 10 centroids (itself included) are within r.
 //  * normals: plane fit over a 9x9 window of the organised cloud (stocs_scene_math.h).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -91,15 +91,6 @@ __global__ void centroid_kernel(const float* __restrict__ xyz, const uint16_t* _
   cent[v] = make_float4(sx / c, sy / c, sz / c, 0.f);
 }
 
-__device__ __forceinline__ int find_key(const unsigned long long* __restrict__ ukeys, int n, unsigned long long key) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (ukeys[mid] < key) lo = mid + 1; else hi = mid;
-  }
-  return (lo < n && ukeys[lo] == key) ? lo : -1;
-}
-
 __global__ void outlier_kernel(const float4* __restrict__ cent, const unsigned long long* __restrict__ ukeys, int nvox,
                                float r2, int reach, int min_neighbors, int* __restrict__ keep) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,17 +99,26 @@ __global__ void outlier_kernel(const float4* __restrict__ cent, const unsigned l
   const unsigned long long key = ukeys[v];
   const long long ix = (long long)(key & 0x1fffff), iy = (long long)((key >> 21) & 0x1fffff), iz = (long long)(key >> 42);
   int k = 0;
+  // keys are sorted (z, y, x): the leaves of one (dz, dy) row are contiguous -> one binary search
+  // for the row's first key, then a linear walk
   for (long long dz = -reach; dz <= reach; ++dz)
-    for (long long dy = -reach; dy <= reach; ++dy)
-      for (long long dx = -reach; dx <= reach; ++dx) {
-        const long long jx = ix + dx, jy = iy + dy, jz = iz + dz;
-        if (jx < 0 || jy < 0 || jz < 0 || jx >= 2 * kOff || jy >= 2 * kOff || jz >= 2 * kOff) continue;
-        const int u = find_key(ukeys, nvox, ((unsigned long long)jz << 42) | ((unsigned long long)jy << 21) | (unsigned long long)jx);
-        if (u < 0) continue;
+    for (long long dy = -reach; dy <= reach; ++dy) {
+      const long long jy = iy + dy, jz = iz + dz;
+      if (jy < 0 || jz < 0 || jy >= 2 * kOff || jz >= 2 * kOff) continue;
+      const long long x0 = ix - reach < 0 ? 0 : ix - reach, x1 = ix + reach >= 2 * kOff ? 2 * kOff - 1 : ix + reach;
+      const unsigned long long k0 = ((unsigned long long)jz << 42) | ((unsigned long long)jy << 21) | (unsigned long long)x0;
+      const unsigned long long k1 = ((unsigned long long)jz << 42) | ((unsigned long long)jy << 21) | (unsigned long long)x1;
+      int lo = 0, hi = nvox;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ukeys[mid] < k0) lo = mid + 1; else hi = mid;
+      }
+      for (int u = lo; u < nvox && ukeys[u] <= k1; ++u) {
         const float4 q = cent[u];
         const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
         if ((ex * ex + ey * ey) + ez * ez <= r2) ++k;
       }
+    }
   keep[v] = (k > min_neighbors) ? 1 : 0;
 }
 
