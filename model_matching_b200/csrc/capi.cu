@@ -195,6 +195,16 @@ int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float*
   if (pixel_rc) STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_spix.p, pixel_rc, (size_t)S * 8, cudaMemcpyHostToDevice, st));
   else STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_spix.p, 0, (size_t)S * 8, st));
   ctx->has_pixels = pixel_rc != nullptr;
+  ctx->pix_min[0] = ctx->pix_min[1] = 0; ctx->pix_max[0] = ctx->pix_max[1] = 0;
+  if (pixel_rc) {  // range of the pixel coordinates: instance sampling indexes images with them
+    ctx->pix_min[0] = ctx->pix_max[0] = pixel_rc[0]; ctx->pix_min[1] = ctx->pix_max[1] = pixel_rc[1];
+    for (int i = 0; i < S; ++i)
+      for (int k = 0; k < 2; ++k) {
+        const int v = pixel_rc[2 * (size_t)i + k];
+        if (v < ctx->pix_min[k]) ctx->pix_min[k] = v;
+        if (v > ctx->pix_max[k]) ctx->pix_max[k] = v;
+      }
+  }
   if (ctx->d_inst_state.p)  // a new scene starts with empty previous_segment / segmentation_buffer
     STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_inst_state.p, 0, (size_t)ctx->img_w * ctx->img_h * 3, st));
   // positions -> centre -> index

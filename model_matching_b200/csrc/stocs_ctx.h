@@ -81,6 +81,7 @@ struct stocs_b200_ctx {
   DevBuf d_sattr;                      // float4 (nx,ny,nz,class probability)
   DevBuf d_spix;                       // int2 (row, col)
   bool has_pixels = false;
+  int pix_min[2] = {0, 0}, pix_max[2] = {0, 0};  // (row, col) range of the uploaded pixel coordinates
   // instance-mode state (edge map, previous_segment | segmentation_buffer | current mask, cached masks)
   DevBuf d_edge, d_inst_state, d_mask_store, d_frontier;
   int img_w = 0, img_h = 0;
