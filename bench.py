@@ -105,8 +105,13 @@ def cpu_baseline(sc, mpos, mnrm, T, seconds_target=15.0):
     t0 = time.perf_counter()
     lcp, inl = est.score(T[:n], threads=cores)
     dt = time.perf_counter() - t0
+    n1 = min(len(T), 20000)   # the reference itself is single-threaded: report that figure too
+    t0 = time.perf_counter()
+    est.score(T[:n1], threads=1)
+    dt1 = time.perf_counter() - t0
     return est, {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                 "sample": f"first {n} of the {len(T)} hypotheses of the same workload, {cores} threads, {dt:.1f} s"}, (lcp, inl, n)
+                 "sample": f"first {n} of the {len(T)} hypotheses of the same workload, {cores} threads, {dt:.1f} s",
+                 "single_thread": {"value": n1 / dt1, "unit": UNIT, "sample": f"first {n1} hypotheses, 1 thread, {dt1:.1f} s"}}, (lcp, inl, n)
 
 
 def pose_latency(ctx_factory, with_cpu):

@@ -145,3 +145,37 @@ def test_sampling_is_reproducible_and_seed_dependent():
     est.sample_class_base(1, 0)
     cur = est.current_prob()
     assert np.all((cur == 0) | (cur == sc["cls"]))
+
+
+def test_score_matches_an_independent_numpy_restatement(small_scene):
+    """compute_alignment_score_for_rigid_transform (src/stocs.cpp:1006-1041) written a second time,
+    in vectorised numpy float32 with brute-force NN instead of the kd-tree and numpy's arccos instead
+    of the shared math header: inlier counts must agree exactly, LCP to 1e-6 relative."""
+    sc, mpos, mnrm = small_scene
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+    T, near = synth.make_hypotheses(60, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=21, near_fraction=0.5)
+    lcp, inl = est.score(T)
+    s, m = est.centred()
+    f = np.float32
+    eps2 = f(0.005) * f(0.005)
+    for h in range(len(T)):
+        A = T[h].reshape(4, 4).T.astype(np.float32)
+        q = np.stack([((A[r, 0] * m[:, 0] + A[r, 1] * m[:, 1]) + A[r, 2] * m[:, 2]) + A[r, 3] for r in range(3)], -1)
+        nq = np.stack([A[r, 0] * mnrm[:, 0] + (A[r, 1] * mnrm[:, 1] + A[r, 2] * mnrm[:, 2]) for r in range(3)], -1)
+        count, acc = 0, f(0)
+        # brute force only near the scene (all model points whose box is close); chunked for memory
+        for i in range(len(m)):
+            d = q[i] - s
+            d2 = d[:, 0] * d[:, 0] + (d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+            j = int(np.argmin(d2))
+            if d2[j] <= eps2:
+                n = sc["nrm"][j]
+                dot = n[0] * nq[i, 0] + (n[1] * nq[i, 1] + n[2] * nq[i, 2])
+                if abs(dot) <= 1:
+                    ang = f(np.float64(f(f(np.arccos(np.float64(dot))) * f(180))) / np.pi)
+                    if ang < 30:
+                        count += 1
+                        acc = f(acc + sc["cls"][j])
+        assert count == inl[h], h
+        assert abs(float(acc / f(len(m))) - float(lcp[h])) <= 1e-6 * max(1e-6, float(lcp[h])), h
+    assert inl[near].min() > 50
