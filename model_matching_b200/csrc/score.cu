@@ -14,15 +14,16 @@
 //        (64-bit occupancy mask + rank base); lanes whose cell is occupied are compacted (ballot +
 //        popc rank) into a per-warp shared-memory queue that runs ACROSS rounds, in model-point
 //        order.
-//   Phase B (queue nearly full, or end of the model):
-//     1. 32 lanes fetch the candidate-list offsets of 32 queued queries at once;
-//     2. 8-lane groups scan one queued query each: the float4 candidate records of a query are
-//        read by adjacent lanes (coalesced), the nearest is found with redux.sync min on the bit
-//        pattern of d^2, and an exact d^2 tie falls through to a walk of the reference kd-tree so
-//        that it is broken the way kdtree.h:416-428 breaks it;
-//     3. 32 lanes fetch the matched scene points' normal + class probability, apply the
-//        30-degree test and accumulate the class probabilities in queue order == model-point
-//        order, which makes the LCP bit-identical to the reference's sequential fp32 sum.
+//   Phase B (queue more than half full, or end of the model), 32 queued queries at a time, one
+//     per "owner" lane: (1) owners fetch their candidate-list offsets and compute the exact
+//     transformed point; (2) the 32 candidate lists are swept as ONE flat list, 32 consecutive
+//     float4 records per trip (coalesced, no padding to the longest list); owners are found with a
+//     redux.or + popc, their points arrive by shuffle, hits race with shared-memory atomicMin on the
+//     bit pattern of d^2 and then on the scene index; an exact d^2 tie falls through to a walk of
+//     the reference kd-tree so that it is broken the way kdtree.h:416-428 breaks it; (3) owners
+//     fetch the matched scene point's normal + class probability, apply the 30-degree test, and
+//     the class probabilities are accumulated in lane order == model-point order, which makes the
+//     LCP bit-identical to the reference's sequential fp32 sum.
 // All memory-dependent steps are batched 32 wide, so the latency chain
 // brick -> offsets -> candidates -> attributes is paid once per drain, not once per model point.
 #include "stocs_ctx.h"
@@ -31,9 +32,6 @@ using namespace stocsm;
 
 namespace {
 
-#ifndef SCORE_GROUP
-#define SCORE_GROUP 4
-#endif
 #ifndef SCORE_QUEUE
 #define SCORE_QUEUE 64
 #endif
@@ -44,8 +42,6 @@ namespace {
 #define SCORE_WARPS 32
 #endif
 constexpr int kWarps = SCORE_WARPS; // warps per CTA
-constexpr int kGroup = SCORE_GROUP; // lanes cooperating on one NN query
-constexpr int kGroupsPerWarp = 32 / kGroup;
 constexpr int kQueue = SCORE_QUEUE; // queued queries per warp
 
 struct ScoreArgs {
@@ -129,92 +125,103 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
 #define LD_CAND __ldg
 #endif
 
-struct WarpQueue {   // one per warp, static shared memory (single base register, constant offsets)
+struct WarpQueue {   // one per warp, shared memory (single base register, constant offsets)
   float T[12];           // exact transform: columns 0..2 (rotation) and 3 (translation), 3 rows each
   float G[12];           // the same map into grid-cell coordinates (FMA-evaluated, phase A only)
-  float qx[kQueue], qy[kQueue], qz[kQueue];   // exact transformed points (filled by drain step 1)
-  uint32_t a0[kQueue];   // occupied-cell rank -> candidate offset -> matched scene index (or -1)
-  uint32_t a1[kQueue];   // candidate count
-  uint32_t pi[kQueue];   // model point index
+  uint32_t a0[kQueue];   // occupied-cell rank of the queued query
+  uint32_t pi[kQueue];   // model point index of the queued query
+  unsigned long long best[32];  // drain: min over hits of (d^2 bit pattern << 32 | scene index), atomicMin
   uint8_t plist[256];    // phase A: survivors of the coarse test within the current 256-point block
 };
 
 struct Acc { float acc; int inl; unsigned ties; };
 
+// Phase B.  The queued queries are processed 32 at a time, one per lane ("owner" lane e holds
+// query e: exact transformed point, candidate offset, candidate count).
+//   1. owners fetch their candidate-list offsets and compute the EXACT transformed point
+//      (mat * p.homogeneous()).head<3>() in the reference's evaluation order (stocs_math.h
+//      xform_point) -- phase A only located the cell;
+//   2. the candidate lists of the 32 queries are swept as ONE flat list, 32 consecutive records
+//      per trip (coalesced, no padding to the longest list).  The owner of flat position f is found
+//      without any table: a redux.or of "my list starts at window offset j" bits + popc gives the
+//      rank, the owner's point arrives by shuffle.  Candidates within eps race with a 64-bit
+//      shared-memory atomicMin on (d^2 bit pattern, scene index); a hit that meets the SAME d^2
+//      under a different index flags the query, and a flagged query is answered by a walk of the
+//      reference kd-tree, which reproduces the reference's tie rule (kdtree.h:416-428);
+//   3. owners fetch the matched scene point's normal + class probability, apply the 30-degree test
+//      and the class probabilities are accumulated in lane order == model-point order, which makes
+//      the LCP bit-identical to the reference's sequential fp32 sum.
 __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, int qn, int lane,
                                             const float4* __restrict__ mp4, const float4* __restrict__ mn4, Acc& r) {
-  const int sub = lane % kGroup;
-  const int grp = lane / kGroup;
   __syncwarp();
-  // 1. 32 queries at a time: candidate-list offsets, and the EXACT transformed point
-  //    (mat * p.homogeneous()).head<3>() in the reference's evaluation order (stocs_math.h
-  //    xform_point) -- phase A only located the cell.
-  for (int e = lane; e < qn; e += 32) {
-    const uint32_t k = q.a0[e];
-    const uint32_t s = __ldg(a.starts + k);
-    const uint32_t t = __ldg(a.starts + k + 1);
-    const float4 mp = mp4[q.pi[e]];
-    q.qx[e] = ((q.T[0] * mp.x + q.T[3] * mp.y) + q.T[6] * mp.z) + q.T[9];
-    q.qy[e] = ((q.T[1] * mp.x + q.T[4] * mp.y) + q.T[7] * mp.z) + q.T[10];
-    q.qz[e] = ((q.T[2] * mp.x + q.T[5] * mp.y) + q.T[8] * mp.z) + q.T[11];
-    q.a0[e] = s;
-    q.a1[e] = t - s;
-  }
-  __syncwarp();
-  // 2. nearest neighbour within eps: kGroupsPerWarp queries per trip, one per kGroup-lane group.
-  //    Warp-synchronous (the trip count is warp-uniform, every collective uses the full mask:
-  //    sub-warp masks would serialise the groups); the first candidate of the NEXT trip's query
-  //    is fetched before the current one is reduced.
   const float sq_eps = a.sq_eps;
-  const int gshift = grp * kGroup;
-  float4 nx_cand = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (grp < qn && (uint32_t)sub < q.a1[grp]) nx_cand = LD_CAND(a.cand + q.a0[grp] + sub);
-  for (int e0 = 0; e0 < qn; e0 += kGroupsPerWarp) {
-    const int e = e0 + grp;
-    float4 c = nx_cand;
-    const int en = e + kGroupsPerWarp;
-    if (en < qn && (uint32_t)sub < q.a1[en]) nx_cand = LD_CAND(a.cand + q.a0[en] + sub);
-    float ex = 0.f, ey = 0.f, ez = 0.f;
-    uint32_t es = 0, ec = 0;
-    if (e < qn) { ex = q.qx[e]; ey = q.qy[e]; ez = q.qz[e]; es = q.a0[e]; ec = q.a1[e]; }
-    uint32_t best = 0x7f800000u;  // +inf
-    int best_idx = -1;
-    bool ltie = false;
-    for (uint32_t j = sub; j < ec; j += kGroup) {
-      if (j != (uint32_t)sub) c = LD_CAND(a.cand + es + j);
-      const float dx = ex - c.x, dy = ey - c.y, dz = ez - c.z;
-      const float d = dx * dx + (dy * dy + dz * dz);
-      if (d <= sq_eps) {
-        const uint32_t b = __float_as_uint(d);
-        if (b < best) { best = b; best_idx = __float_as_int(c.w); ltie = false; }
-        else if (b == best) { ltie = true; }
+  const unsigned le_mask = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+  for (int half = 0; half < qn; half += 32) {
+    const int e = half + lane;
+    const bool has = e < qn;
+    // 1.
+    uint32_t s = 0, cnt = 0, mi = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (has) {
+      const uint32_t k = q.a0[e];
+      s = __ldg(a.starts + k);
+      cnt = __ldg(a.starts + k + 1) - s;
+      mi = q.pi[e];
+      const float4 mp = mp4[mi];
+      qx = ((q.T[0] * mp.x + q.T[3] * mp.y) + q.T[6] * mp.z) + q.T[9];
+      qy = ((q.T[1] * mp.x + q.T[4] * mp.y) + q.T[7] * mp.z) + q.T[10];
+      qz = ((q.T[2] * mp.x + q.T[5] * mp.y) + q.T[8] * mp.z) + q.T[11];
+    }
+    q.best[lane] = ~0ull;
+    uint32_t pre = cnt;         // inclusive scan of the counts -> exclusive prefix
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += up;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+    pre -= cnt;
+    __syncwarp();
+    // 2.
+    unsigned flag = 0;          // queries this lane wants answered by the kd-tree (exact d^2 ties)
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t f = t0 + lane;
+      const int rel = (int)pre - (int)t0;
+      const unsigned starts_here = __reduce_or_sync(0xffffffffu, (cnt > 0 && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+      const int before = __popc(__ballot_sync(0xffffffffu, cnt > 0 && rel < 0));
+      // owner = the last query whose list starts at or before f.  Lists are non-empty (every queued
+      // cell is occupied), so ranks among non-empty lists == lane numbers among `has` lanes.
+      const int own = before - 1 + __popc(starts_here & le_mask);
+      const int src = own < 0 ? 0 : own;
+      const float ox = __shfl_sync(0xffffffffu, qx, src), oy = __shfl_sync(0xffffffffu, qy, src),
+                  oz = __shfl_sync(0xffffffffu, qz, src);
+      const uint32_t os = __shfl_sync(0xffffffffu, s, src), op = __shfl_sync(0xffffffffu, pre, src);
+      if (f < total) {
+        const float4 c = LD_CAND(a.cand + os + (f - op));
+        const float dx = ox - c.x, dy = oy - c.y, dz = oz - c.z;
+        const float d = dx * dx + (dy * dy + dz * dz);
+        if (d <= sq_eps) {
+          const uint32_t b = __float_as_uint(d), ci = __float_as_uint(c.w);
+          const unsigned long long old = atomicMin(&q.best[src], ((unsigned long long)b << 32) | ci);
+          if ((uint32_t)(old >> 32) == b && (uint32_t)old != ci) flag |= 1u << src;   // same d^2, another point
+        }
       }
     }
-    uint32_t dmin = best;
-#pragma unroll
-    for (int o = 1; o < kGroup; o <<= 1) dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-    const bool iswin = (best == dmin) && (best != 0x7f800000u);
-    const unsigned winners = (__ballot_sync(0xffffffffu, iswin) >> gshift) & ((1u << kGroup) - 1u);
-    const unsigned lties = (__ballot_sync(0xffffffffu, ltie && iswin) >> gshift) & ((1u << kGroup) - 1u);
-    int widx = __shfl_sync(0xffffffffu, best_idx, gshift + (winners ? __ffs(winners) - 1 : 0));
-    if (!winners) widx = -1;
-    if ((__popc(winners) > 1 || lties) && sub == 0) {
-      widx = kd_query_dev(a.kd_nodes, a.kd_pts, ex, ey, ez, sq_eps);
-      r.ties++;
-    }
-    if (sub == 0 && e < qn) q.a0[e] = (uint32_t)widx;
-  }
-  __syncwarp();
-  // 3. normal test + ordered accumulation, 32 queries at a time
-  for (int e0 = 0; e0 < qn; e0 += 32) {
-    const int e = e0 + lane;
+    __syncwarp();
+    flag = __reduce_or_sync(0xffffffffu, flag);
+    // 3.
     bool match = false;
     float w = 0.f;
-    if (e < qn) {
-      const int res = (int)q.a0[e];
+    const unsigned long long mine = q.best[lane];
+    if (has && mine != ~0ull) {
+      int res = (int)(uint32_t)mine;
+      if ((flag >> lane) & 1u) {
+        res = kd_query_dev(a.kd_nodes, a.kd_pts, qx, qy, qz, sq_eps);
+        r.ties++;
+      }
       if (res >= 0) {
         const float4 sa = ld_stream(a.sattr + res);
-        const float4 mn = __ldg(mn4 + q.pi[e]);
+        const float4 mn = __ldg(mn4 + mi);
         // mat.block<3,3>(0,0) * n  -- see stocs_math.h xform_dir
         const float rx = q.T[0] * mn.x + (q.T[3] * mn.y + q.T[6] * mn.z);
         const float ry = q.T[1] * mn.x + (q.T[4] * mn.y + q.T[7] * mn.z);
@@ -232,8 +239,8 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
       r.acc += __shfl_sync(0xffffffffu, w, b);
       mm &= mm - 1;
     }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kernel(ScoreArgs a) {
