@@ -125,6 +125,12 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
 #define LD_CAND __ldg
 #endif
 
+// %laneid / %lanemask_* as plain (non-volatile) asm: one instruction when the compiler has to
+// rematerialise them inside the loops (registers are capped at 32 for 64 warps/SM)
+__device__ __forceinline__ unsigned lane_id() { unsigned r; asm("mov.u32 %0, %%laneid;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned lanemask_le() { unsigned r; asm("mov.u32 %0, %%lanemask_le;" : "=r"(r)); return r; }
+
 struct WarpQueue {   // one per warp, shared memory (single base register, constant offsets)
   float T[12];           // exact transform: columns 0..2 (rotation) and 3 (translation), 3 rows each
   float G[12];           // the same map into grid-cell coordinates (FMA-evaluated, phase A only)
@@ -155,7 +161,7 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
                                             const float4* __restrict__ mp4, const float4* __restrict__ mn4, Acc& r) {
   __syncwarp();
   const float sq_eps = a.sq_eps;
-  const unsigned le_mask = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+  const unsigned le_mask = lanemask_le();
   for (int half = 0; half < qn; half += 32) {
     const int e = half + lane;
     const bool has = e < qn;
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_model = reinterpret_cast<float*>(smem_raw);
   const int Mpad = a.Mpad;
-  const int lane = threadIdx.x & 31;
+  const int lane = (int)lane_id();
   const int warp = threadIdx.x >> 5;
   // dynamic shared memory: [model positions float4 x Mpad][coarse bitmap][one WarpQueue per warp]
   for (int i = threadIdx.x; i < 4 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   const float4* mp4 = reinterpret_cast<const float4*>(s_model);  // positions as float4 (NaN beyond M)
   const float4* mn4 = reinterpret_cast<const float4*>(a.model) + Mpad;  // normals stay in global (hits only)
 
-  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned lt_mask = lanemask_lt();
   const int M = a.M;
   Acc r;
   r.ties = 0;
