@@ -4,6 +4,7 @@
 
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -138,18 +139,29 @@ void stocs_estimator::kdtree_initialize() {
   std::cout << "|S|: " << point3d_scene.size() << std::endl;  // the index was built by upload_scene
 }
 
+// src/stocs.cpp:363-519.  Class-mode bases are independent and keyed by (seed, base number), so
+// the shim samples them kPrefetch at a time in ONE launch and hands them out call by call; the
+// values are identical to sampling them one by one.
 bool stocs_estimator::sample_class_base(std::vector<int>& base_indices, float& invariant1, float& invariant2) {
-  int32_t ids[4];
-  float inv[2];
-  uint8_t valid = 0;
-  if (stocs_b200_sample_bases(ctx_, seed_, next_base_no_++, 1, ids, inv, &valid) != 0) fail("sample_bases");
-  if (!valid) {
+  const uint32_t no = next_base_no_++;
+  if (no < cache_first_ || no >= cache_first_ + (uint32_t)cache_valid_.size()) {
+    cache_first_ = no;
+    cache_ids_.assign((size_t)kPrefetch * 4, -1);
+    cache_inv_.assign((size_t)kPrefetch * 2, 0.f);
+    cache_valid_.assign((size_t)kPrefetch, 0);
+    if (stocs_b200_sample_bases(ctx_, seed_, no, kPrefetch, cache_ids_.data(), cache_inv_.data(), cache_valid_.data()) != 0)
+      fail("sample_bases");
+    cong_ready_ = false;
+  }
+  const size_t k = no - cache_first_;
+  if (!cache_valid_[k]) {
     std::cout << "FAILED SAMPLING:: Zero probability returned!!!" << std::endl;
     return false;
   }
-  for (int k = 0; k < 4; ++k) base_indices[k] = ids[k];
-  invariant1 = inv[0];
-  invariant2 = inv[1];
+  for (int j = 0; j < 4; ++j) base_indices[j] = cache_ids_[4 * k + j];
+  invariant1 = cache_inv_[2 * k];
+  invariant2 = cache_inv_[2 * k + 1];
+  handed_out_ = std::max(handed_out_, k + 1);
   return true;
 }
 
@@ -176,11 +188,45 @@ bool stocs_estimator::sample_instance_base(std::vector<int>& base_indices, float
   return true;
 }
 
+// src/stocs.cpp:753-869.  When the queried base is one of the bases this estimator handed out, the
+// congruent sets of ALL of them are computed in one batched call (the reference driver asks for
+// every base in turn, src/stocs_match_one_object.cpp:111-118) and served from the cache.
 bool stocs_estimator::find_congruent_sets_on_model(std::vector<int>& base_indices, float invariant1, float invariant2,
                                                    std::vector<Quadrilateral>* quadrilaterals) {
   quadrilaterals->clear();
   int32_t ids[4] = {base_indices[0], base_indices[1], base_indices[2], base_indices[3]};
   float inv[2] = {invariant1, invariant2};
+  // cached?
+  for (size_t k = 0; k < handed_out_ && k < cache_valid_.size(); ++k) {
+    if (!cache_valid_[k]) continue;
+    if (std::memcmp(&cache_ids_[4 * k], ids, 16) != 0 || cache_inv_[2 * k] != inv[0] || cache_inv_[2 * k + 1] != inv[1]) continue;
+    if (!cong_ready_) {
+      std::vector<int32_t> bids;
+      std::vector<float> binv;
+      cong_slot_.assign(cache_valid_.size(), -1);
+      for (size_t j = 0; j < handed_out_; ++j)
+        if (cache_valid_[j]) {
+          cong_slot_[j] = (int)(bids.size() / 4);
+          bids.insert(bids.end(), &cache_ids_[4 * j], &cache_ids_[4 * j] + 4);
+          binv.push_back(cache_inv_[2 * j]); binv.push_back(cache_inv_[2 * j + 1]);
+        }
+      const int nb = (int)(bids.size() / 4);
+      cong_off_.assign((size_t)nb + 1, 0);
+      cong_quads_.assign(4 * 65536, 0);
+      int rc = stocs_b200_find_congruent(ctx_, nb, bids.data(), binv.data(), cong_quads_.data(), (int64_t)cong_quads_.size() / 4, cong_off_.data());
+      if (rc == STOCS_E_CAPACITY) {
+        cong_quads_.assign((size_t)cong_off_[nb] * 4, 0);
+        rc = stocs_b200_find_congruent(ctx_, nb, bids.data(), binv.data(), cong_quads_.data(), cong_off_[nb], cong_off_.data());
+      }
+      if (rc != 0) fail("find_congruent");
+      cong_ready_ = true;
+    }
+    const int slot = cong_slot_[k];
+    for (int64_t i = cong_off_[slot]; i < cong_off_[slot + 1]; ++i)
+      quadrilaterals->emplace_back(cong_quads_[4 * i], cong_quads_[4 * i + 1], cong_quads_[4 * i + 2], cong_quads_[4 * i + 3]);
+    return quadrilaterals->size() != 0;
+  }
+  // a base the estimator did not sample (e.g. instance mode, or supplied by the caller): single call
   int64_t off[2] = {0, 0};
   std::vector<int32_t> quads(4 * 4096);
   int rc = stocs_b200_find_congruent(ctx_, 1, ids, inv, quads.data(), (int64_t)quads.size() / 4, off);

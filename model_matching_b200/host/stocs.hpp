@@ -8,6 +8,8 @@
 //  * PPFMapType is the compact own-bin table, not a std::map (rgbd.hpp).
 //  * Sampling is keyed by (seed, base number) instead of the wall clock; the seed comes from the
 //    environment variable STOCS_SEED when set, else from the clock as in the reference.
+//  * sample_class_base draws bases 128 at a time in one launch and find_congruent_sets_on_model
+//    batches over the bases handed out so far; the values returned per call are unchanged.
 //  * get_rigid_transform_from_congruent_pair queues the (base, quad) pair; transforms are fitted,
 //    scored and reduced in one batched GPU pass at compute_best_transform() (or at the first
 //    accessor that needs them).  The lists all_transforms / all_pose end up identical.
@@ -100,6 +102,17 @@ class stocs_estimator {
   struct stocs_b200_ctx* ctx_ = nullptr;
   uint64_t seed_ = 0;
   uint32_t next_base_no_ = 0;
+  // class-mode prefetch: bases sampled kPrefetch at a time, congruent sets batched over them
+  static constexpr int kPrefetch = 128;
+  uint32_t cache_first_ = 0;
+  std::vector<int32_t> cache_ids_;
+  std::vector<float> cache_inv_;
+  std::vector<uint8_t> cache_valid_;
+  size_t handed_out_ = 0;
+  bool cong_ready_ = false;
+  std::vector<int> cong_slot_;
+  std::vector<int64_t> cong_off_;
+  std::vector<int32_t> cong_quads_;
   bool edge_uploaded_ = false;
   bool class_prob_dirty_ = false;
   std::vector<int32_t> pending_bases_, pending_quads_;
