@@ -143,3 +143,21 @@ def test_select_above_is_the_clustering_prefilter(gpu_ctx):
     assert np.array_equal(idx, order) and np.array_equal(val, lcp[order])
     idx0, _ = gpu_ctx.select_above(np.zeros(10, np.float32), 0.0)
     assert idx0.size == 0
+
+
+def test_multi_object_sweep_shares_one_scene_index(gpu_ctx, small_scene):
+    """BASELINE.json configs[4] at test size: eight models (|M| in 384..1024) scored against the same
+    scene; the scene index is built once, only the model tables are swapped."""
+    sc, _, _ = small_scene
+    gpu_ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    cells_before = gpu_ctx.counters()[2]
+    for k, M in enumerate([384, 448, 512, 600, 640, 768, 900, 1024]):
+        mpos, mnrm = synth.make_model(M, radius=0.05 + 0.005 * k)
+        gpu_ctx.upload_model(mpos, mnrm)
+        T, _ = synth.make_hypotheses(1500, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=1000 + k, near_fraction=0.05)
+        est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+        lcp, inl = gpu_ctx.score_lcp(T)
+        olcp, oinl = est.score(T, threads=8)
+        assert np.array_equal(inl, oinl), M
+        assert np.array_equal(lcp.view(np.uint32), olcp.view(np.uint32)), M
+    assert gpu_ctx.counters()[2] == cells_before
