@@ -3,6 +3,7 @@
 // sm_100a kernels, and stocs_b200_create refuses to run without a compute-capability-10 device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -55,8 +56,11 @@ int stocs_b200_create(stocs_b200_ctx** out, int device) {
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ctx->chunk_ev[0], cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ctx->chunk_ev[1], cudaEventDisableTiming) == cudaSuccess;
+            cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->join_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->join_ev[1], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < stocs_b200_ctx::kMaxChunks; ++i)
+    ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { g_create_err = "stream/event creation failed"; delete ctx; return STOCS_E_CUDA; }
   ctx->dot_thr = stocs_angle_threshold_dot();
   if (ctx->d_small.ensure(4096) != cudaSuccess || cudaMemset(ctx->d_small.p, 0, 4096) != cudaSuccess) {
@@ -87,7 +91,9 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  for (int i = 0; i < 2; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+  for (int i = 0; i < stocs_b200_ctx::kMaxChunks; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+  for (int i = 0; i < 2; ++i) if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -255,40 +261,55 @@ int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float
   STOCS_CUDA(ctx, ctx->d_inl.ensure((size_t)H * 4));
   // chunked: the H2D copy of chunk k+1 (copy stream) overlaps the scoring of chunk k.  Chunks grow
   // geometrically (H/8, H/8, H/4, H/2) so that scoring starts early and most of the work runs in
-  // large launches.
+  // large launches.  Consecutive chunks alternate between two compute streams, each launch with
+  // its own work counter, so the CTAs of chunk k+1 move in as the straggler warps of chunk k
+  // retire (a launch's tail is ~0.2 ms on the S1 workload); each chunk's results go back on its
+  // own stream right behind its kernel.
   std::vector<int64_t> bounds;
-  if (H <= (1 << 16)) {
+  int nequal = 0;
+  if (const char* e = getenv("STOCS_SCORE_CHUNKS")) nequal = atoi(e);
+  if (nequal > stocs_b200_ctx::kMaxChunks) nequal = stocs_b200_ctx::kMaxChunks;
+  if (H <= (1 << 16) || nequal == 1) {
     bounds = {0, H};
+  } else if (nequal > 1) {
+    for (int c = 0; c <= nequal; ++c) bounds.push_back(H * c / nequal);
   } else {
     const int64_t e8 = (H + 7) / 8;
     bounds = {0, e8, 2 * e8, 4 * e8, H};
     for (auto& b : bounds) if (b > H) b = H;
   }
   const int64_t nchunks = (int64_t)bounds.size() - 1;
-  std::vector<cudaEvent_t> evs((size_t)nchunks, nullptr);
+  cudaStream_t cs[2] = {ctx->stream, ctx->aux_stream};
   int rc = STOCS_OK;
-  for (int64_t c = 0; c < nchunks && rc == STOCS_OK; ++c) {
+  cudaError_t e = cudaSuccess;
+  if (nchunks > 1) {  // aux stream starts behind whatever is queued on the context stream
+    e = cudaEventRecord(ctx->join_ev[0], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, ctx->join_ev[0], 0);
+  }
+  for (int64_t c = 0; c < nchunks && rc == STOCS_OK && e == cudaSuccess; ++c) {
     const int64_t off = bounds[c], n = bounds[c + 1] - bounds[c];
     if (n <= 0) continue;
-    cudaError_t e = cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_T.as<float>() + off * 16, T16 + off * 16, (size_t)n * 64,
-                                              cudaMemcpyHostToDevice, ctx->copy_stream);
-    if (e == cudaSuccess) e = cudaEventRecord(evs[c], ctx->copy_stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, evs[c], 0);
-    if (e != cudaSuccess) { ctx->err = std::string("score_lcp copy: ") + cudaGetErrorString(e); rc = STOCS_E_CUDA; break; }
+    cudaStream_t st = cs[c & 1];
+    e = cudaMemcpyAsync(ctx->d_T.as<float>() + off * 16, T16 + off * 16, (size_t)n * 64, cudaMemcpyHostToDevice,
+                        ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0);
+    if (e != cudaSuccess) break;
     rc = stocs_launch_score(ctx, ctx->d_T.as<float>() + off * 16, n, ctx->d_lcp.as<float>() + off,
-                            ctx->d_inl.as<int32_t>() + off, ctx->stream, false);
-  }
-  if (rc == STOCS_OK) {
-    cudaError_t e = cudaMemcpyAsync(lcp, ctx->d_lcp.p, (size_t)H * 4, cudaMemcpyDeviceToHost, ctx->stream);
+                            ctx->d_inl.as<int32_t>() + off, st, false, (int)c);
+    if (rc != STOCS_OK) break;
+    e = cudaMemcpyAsync(lcp + off, ctx->d_lcp.as<float>() + off, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && inliers)
-      e = cudaMemcpyAsync(inliers, ctx->d_inl.p, (size_t)H * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { ctx->err = std::string("score_lcp: ") + cudaGetErrorString(e); rc = STOCS_E_CUDA; }
-  } else {
-    cudaStreamSynchronize(ctx->stream);
+      e = cudaMemcpyAsync(inliers + off, ctx->d_inl.as<int32_t>() + off, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
   }
-  for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+  if (nchunks > 1) {  // join: the context stream is the one callers order against
+    cudaError_t e2 = cudaEventRecord(ctx->join_ev[1], ctx->aux_stream);
+    if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(ctx->stream, ctx->join_ev[1], 0);
+    if (e == cudaSuccess) e = e2;
+  }
+  cudaError_t es = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = es;
+  if (rc == STOCS_OK && e != cudaSuccess) { ctx->err = std::string("score_lcp: ") + cudaGetErrorString(e); rc = STOCS_E_CUDA; }
   ctx->last_H = H;
   return rc;
 }

@@ -378,7 +378,7 @@ bool stocs_fmad_selftest(stocs_b200_ctx* ctx) {
 }
 
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp, int32_t* d_inl,
-                       cudaStream_t st, bool time_it) {
+                       cudaStream_t st, bool time_it, int slot) {
   if (H <= 0) return STOCS_OK;
   if (H >= (1ll << 31)) STOCS_FAIL(ctx, STOCS_E_ARG, "score: at most 2^31-1 hypotheses per call");
   ScoreArgs a;
@@ -395,8 +395,11 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.T = d_T;
   a.lcp = d_lcp;
   a.inl = d_inl;
+  // slot 0 is the default work counter; launches that may run concurrently (score_lcp's chunks
+  // on two streams) take distinct slots.  One tie counter accumulates over all launches.
   unsigned long long* ctr = (unsigned long long*)(ctx->d_small.as<char>() + 192);
-  a.work_counter = ctr;
+  unsigned long long* wctr = slot == 0 ? ctr : (unsigned long long*)(ctx->d_small.as<char>() + 2048) + slot;
+  a.work_counter = wctr;
   a.tie_counter = ctr + 1;
   a.H = H;
   a.g = ctx->grid;
@@ -413,7 +416,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   long long want = (H + kWarps - 1) / kWarps;
   long long grid = (long long)ctx->num_sms * per_sm;
   if (grid > want) grid = want;
-  STOCS_CUDA(ctx, cudaMemsetAsync(ctr, 0, 8, st));  // work counter only; tie counter accumulates
+  STOCS_CUDA(ctx, cudaMemsetAsync(wctr, 0, 8, st));  // work counter only; tie counter accumulates
   if (time_it) STOCS_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
   score_lcp_kernel<<<(unsigned)grid, kWarps * 32, smem, st>>>(a);
   if (time_it) STOCS_CUDA(ctx, cudaEventRecord(ctx->ev1, st));

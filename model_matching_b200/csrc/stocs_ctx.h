@@ -56,8 +56,11 @@ struct stocs_b200_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;   // second compute stream: consecutive score chunks overlap their tails
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
+  static constexpr int kMaxChunks = 16;
+  cudaEvent_t chunk_ev[kMaxChunks] = {};  // H2D-complete events of score_lcp's chunks
+  cudaEvent_t join_ev[2] = {nullptr, nullptr};
   std::string err;
 
   // parameters
@@ -133,7 +136,7 @@ int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4*
                         float* d_out3, float* h_centroid3, float* h_aabb6);
 int stocs_pack_scene_attr(stocs_b200_ctx* ctx, const float* d_nrm3, const float* d_cls, int S);
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp,
-                       int32_t* d_inl, cudaStream_t st, bool time_it);     // score.cu
+                       int32_t* d_inl, cudaStream_t st, bool time_it, int slot = 0);  // score.cu
 int stocs_launch_backproject(stocs_b200_ctx* ctx, const uint16_t* d_depth, const uint8_t* d_bgr,
                              int W, int H, float fx, float cx, float fy, float cy, float scale,
                              float* d_xyz, uint32_t* d_rgb, cudaStream_t st);  // backproject.cu
