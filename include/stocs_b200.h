@@ -163,6 +163,20 @@ int stocs_b200_reduce_best_device(stocs_b200_ctx* ctx, const float* d_lcp, int64
 int stocs_b200_select_above(stocs_b200_ctx* ctx, const float* lcp, int64_t H, float threshold,
                             int64_t* index_out, float* lcp_out, int64_t cap, int64_t* n_out);
 
+/* Point-to-plane ICP refinement: clustering::point_to_plane_icp (src/pose_clustering.cpp:123-141;
+ * pcl::IterativeClosestPointWithNormals with setMaximumIterations(5),
+ * setMaxCorrespondenceDistance(0.035), source = segment, target = model cloud with normals).
+ * Host arrays in, xyz triples.  T16_out: accumulated transform (column-major), identity when the
+ * first iteration already fails; aligned_pos3 (optional): the moved source, as the reference leaves
+ * it in segment_cloud; pairs_per_iteration (optional): max_iterations entries; *converged = 0 when
+ * an iteration found fewer than 3 correspondences or a singular system (PCL's "not converged",
+ * the reference then leaves offset_transform untouched).  Needs no uploaded model or scene. */
+int stocs_b200_icp_point_to_plane(stocs_b200_ctx* ctx, const float* src_pos3, int n_src,
+                                  const float* tgt_pos3, const float* tgt_nrm3, int n_tgt,
+                                  int max_iterations, float max_correspondence_distance,
+                                  float* T16_out, float* aligned_pos3, int32_t* pairs_per_iteration,
+                                  int32_t* iterations_done, int32_t* converged);
+
 /* ---- fused online pipeline (run_stocs_estimation, src/stocs_match_one_object.cpp:79-165) ----
  * sample n_bases bases -> congruent sets -> at most max_sets transforms per base (the first
  * max_sets quads in set order when a base has more; see DESIGN.md on quirk 5) -> score -> best.

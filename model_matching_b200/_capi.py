@@ -23,6 +23,7 @@ SYMBOLS = [
     "stocs_b200_upload_edge_map", "stocs_b200_sample_instance_base", "stocs_b200_get_class_probability",
     "stocs_b200_find_congruent", "stocs_b200_fit_transforms", "stocs_b200_score_lcp",
     "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device", "stocs_b200_select_above",
+    "stocs_b200_icp_point_to_plane",
     "stocs_b200_run_pipeline", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
 ]
 
@@ -78,6 +79,7 @@ def lib():
     L.stocs_b200_reduce_best.argtypes = [vp, vp, i64, i32, C.POINTER(i64), C.POINTER(f32), vp, vp]
     L.stocs_b200_reduce_best_device.argtypes = [vp, vp, i64, i32, i64, vp, vp, vp]
     L.stocs_b200_select_above.argtypes = [vp, vp, i64, f32, vp, vp, i64, C.POINTER(i64)]
+    L.stocs_b200_icp_point_to_plane.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.stocs_b200_run_pipeline.argtypes = [vp, u64, i32, i32, C.POINTER(PipelineResult)]
     L.stocs_b200_get_counters.argtypes = [vp, vp, i32]
     L.stocs_b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
@@ -301,6 +303,19 @@ class Context:
         self._check(self._L.stocs_b200_select_above(self.h, _ptr(lcp), lcp.size, threshold, _ptr(idx), _ptr(val),
                                                      lcp.size, C.byref(n)))
         return idx[:n.value].copy(), val[:n.value].copy()
+
+    def icp_point_to_plane(self, src, tgt, tgt_nrm, max_iterations=5, max_dist=0.035):
+        """-> (T 4x4, aligned source, pairs per iteration, iterations done, converged)"""
+        src, tgt, tgt_nrm = _f32(src, (-1, 3)), _f32(tgt, (-1, 3)), _f32(tgt_nrm, (-1, 3))
+        assert tgt.shape == tgt_nrm.shape
+        T = np.zeros(16, np.float32)
+        out = np.empty_like(src)
+        pairs = np.zeros(max(max_iterations, 1), np.int32)
+        done, conv = C.c_int32(0), C.c_int32(0)
+        self._check(self._L.stocs_b200_icp_point_to_plane(self.h, _ptr(src), src.shape[0], _ptr(tgt), _ptr(tgt_nrm),
+                                                           tgt.shape[0], max_iterations, max_dist, _ptr(T), _ptr(out),
+                                                           _ptr(pairs), C.byref(done), C.byref(conv)))
+        return T.reshape(4, 4).T.copy(), out, pairs, done.value, bool(conv.value)
 
     def reduce_best_device(self, dlcp_ptr, H, K, index_offset, didx_ptr, dval_ptr, stream=None):
         self._check(self._L.stocs_b200_reduce_best_device(self.h, dlcp_ptr, H, K, index_offset, didx_ptr,

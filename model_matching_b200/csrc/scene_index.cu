@@ -15,6 +15,9 @@
 // reproduce the reference's traversal-order tie rule (kdtree.h:416-428).
 #include <cub/device/device_scan.cuh>
 
+#include <chrono>
+#include <thread>
+#include <cstdio>
 #include <algorithm>
 #include <cfloat>
 #include <climits>
@@ -279,10 +282,26 @@ int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4*
   return STOCS_OK;
 }
 
+namespace {
+// STOCS_TRACE=1: wall-clock of each stage of the index build on stderr (adds a synchronize per stage)
+struct StageTrace {
+  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+  StageTrace(cudaStream_t s) : on(getenv("STOCS_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[stocs trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   // expects ctx->d_tmp = raw pos3 (S*3 floats)
   const int S = ctx->S;
   cudaStream_t st = ctx->stream;
+  StageTrace tr(st);
   STOCS_CUDA(ctx, ctx->d_spos4.ensure((size_t)S * 16));
   STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)S * 12));
   int nb = (S + 255) / 256;
@@ -293,10 +312,26 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   ctx->h_spos.resize((size_t)S * 3);
   STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_spos.data(), ctx->d_tmp2.p, (size_t)S * 12, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  tr.mark("centre + copy back");
   float mn[3] = {aabb[0], aabb[1], aabb[2]}, mx[3] = {aabb[3], aabb[4], aabb[5]};
   for (int k = 0; k < 3; ++k)
     if (!(mn[k] <= mx[k]) || !std::isfinite(mn[k]) || !std::isfinite(mx[k]))
       STOCS_FAIL(ctx, STOCS_E_ARG, "upload_scene: scene contains non-finite coordinates");
+
+  // the reference kd-tree is host work on the centred points: build it on a second host thread
+  // while this one drives the grid kernels
+  KdBuild kb;
+  std::vector<float4> kp((size_t)S);
+  std::thread kd_thread([&kb, &kp, ctx, S] {
+    kb.build(ctx->h_spos.data(), S);
+    for (int i = 0; i < S; ++i) {
+      float w;
+      const int id = kb.idx[i];
+      memcpy(&w, &id, 4);
+      kp[i] = make_float4(kb.x[i], kb.y[i], kb.z[i], w);
+    }
+  });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{kd_thread};
 
   // grid geometry: cell edge = 2*eps unless that needs more than kMaxCells cells
   const double eps = ctx->eps;
@@ -349,9 +384,11 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, cudaMemcpyAsync(&total, dense_start + g.ncells, 4, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->ncand = total;
+  tr.mark("alloc + count + scan");
   STOCS_CUDA(ctx, ctx->d_cand.ensure((size_t)(total ? total : 1) * 16));
   STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
   grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>());
+  tr.mark("fill candidates");
   // brick table + compact starts
   DevBuf &d_masks = ctx->pool[13], &d_occ = ctx->pool[14], &d_occ_scan = ctx->pool[15];
   STOCS_CUDA(ctx, d_masks.ensure((size_t)g.nbricks * 8));
@@ -384,17 +421,11 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, cudaGetLastError());
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->counters[4] = n_occ;
+  tr.mark("bricks + coarse");
 
-  // reference kd-tree (tie resolution only)
-  KdBuild kb;
-  kb.build(ctx->h_spos.data(), S);
-  std::vector<float4> kp(S);
-  for (int i = 0; i < S; ++i) {
-    float w;
-    int id = kb.idx[i];
-    memcpy(&w, &id, 4);
-    kp[i] = make_float4(kb.x[i], kb.y[i], kb.z[i], w);
-  }
+  // reference kd-tree (tie resolution only): built by the host thread started above
+  kd_thread.join();
+  tr.mark("kd-tree build (host)");
   ctx->kd_nodes = (int)kb.nodes.size();
   STOCS_CUDA(ctx, ctx->d_kd_nodes.ensure(kb.nodes.size() * sizeof(KdNodeDev)));
   STOCS_CUDA(ctx, ctx->d_kd_pts.ensure((size_t)S * 16));
@@ -402,6 +433,7 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
                                   cudaMemcpyHostToDevice, st));
   STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_pts.p, kp.data(), (size_t)S * 16, cudaMemcpyHostToDevice, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  tr.mark("kd-tree upload");
   ctx->counters[2] = g.ncells;
   ctx->counters[3] = total;
   return STOCS_OK;

@@ -106,7 +106,7 @@ struct stocs_b200_ctx {
   std::vector<uint32_t> h_ppf_bin_start, h_ppf_pairs;
 
   // grow-only scratch slots reused by the multi-kernel stages (no cudaMalloc/cudaFree per call)
-  DevBuf pool[32];
+  DevBuf pool[40];
   // scratch
   DevBuf d_T, d_lcp, d_inl, d_work, d_tmp, d_tmp2, d_small;
   void* h_pinned = nullptr;

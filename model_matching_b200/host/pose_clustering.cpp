@@ -3,7 +3,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <iostream>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/stocs_b200.h"
 
 namespace clustering {
 
@@ -102,13 +107,47 @@ void greedy_clustering(std::vector<PoseCandidate*>& hypotheses_set, float accept
   }
 }
 
-void point_to_plane_icp(PCLPointCloud::Ptr, PCLPointCloud::Ptr, Eigen::Matrix4f& offset_transform) {
-  static bool warned = false;
-  if (!warned) {
-    std::cerr << "point_to_plane_icp: PCL's ICP is not available in this build; offset left at identity" << std::endl;
-    warned = true;
+// reference src/pose_clustering.cpp:123-141.  PCL's ICP loop runs on the device
+// (stocs_b200_icp_point_to_plane); the context is created on first use and lives for the process.
+void point_to_plane_icp(PCLPointCloud::Ptr segment_cloud, PCLPointCloud::Ptr model_cloud, Eigen::Matrix4f& offset_transform) {
+  static stocs_b200_ctx* ctx = nullptr;
+  if (!ctx) {
+    const char* dev = getenv("STOCS_DEVICE");
+    if (stocs_b200_create(&ctx, dev ? atoi(dev) : 0) != 0) {
+      std::string why = ctx ? stocs_b200_last_error(ctx) : "no context";
+      if (ctx) { stocs_b200_destroy(ctx); ctx = nullptr; }
+      throw std::runtime_error("point_to_plane_icp: " + why);
+    }
   }
-  offset_transform = Eigen::Matrix4f::Identity();
+  const int ns = (int)segment_cloud->points.size(), nt = (int)model_cloud->points.size();
+  if (ns == 0 || nt == 0) return;
+  std::vector<float> sp((size_t)ns * 3), tp((size_t)nt * 3), tn((size_t)nt * 3), moved((size_t)ns * 3);
+  for (int i = 0; i < ns; ++i) {
+    const CloudPoint& p = segment_cloud->points[i];
+    sp[3 * i] = p.x; sp[3 * i + 1] = p.y; sp[3 * i + 2] = p.z;
+  }
+  for (int i = 0; i < nt; ++i) {
+    const CloudPoint& p = model_cloud->points[i];
+    tp[3 * i] = p.x; tp[3 * i + 1] = p.y; tp[3 * i + 2] = p.z;
+    tn[3 * i] = p.nx; tn[3 * i + 1] = p.ny; tn[3 * i + 2] = p.nz;
+  }
+  float T[16];
+  int32_t converged = 0;
+  if (stocs_b200_icp_point_to_plane(ctx, sp.data(), ns, tp.data(), tn.data(), nt, /*setMaximumIterations*/ 5,
+                                    /*setMaxCorrespondenceDistance*/ 0.035f, T, moved.data(), nullptr, nullptr,
+                                    &converged) != 0)
+    throw std::runtime_error(std::string("point_to_plane_icp: ") + stocs_b200_last_error(ctx));
+  for (int i = 0; i < ns; ++i) {  // icp->align(*segment_cloud) leaves the moved source in place
+    CloudPoint& p = segment_cloud->points[i];
+    p.x = moved[3 * i]; p.y = moved[3 * i + 1]; p.z = moved[3 * i + 2];
+    const float nx = p.nx, ny = p.ny, nz = p.nz;
+    p.nx = T[0] * nx + T[4] * ny + T[8] * nz;
+    p.ny = T[1] * nx + T[5] * ny + T[9] * nz;
+    p.nz = T[2] * nx + T[6] * ny + T[10] * nz;
+  }
+  if (converged)
+    for (int c = 0; c < 4; ++c)
+      for (int r = 0; r < 4; ++r) offset_transform(r, c) = T[c * 4 + r];
 }
 
 }  // namespace clustering

@@ -2,8 +2,9 @@
 // greedy_clustering is a faithful host restatement (the pass is serial and tiny: it runs over the
 // few hypotheses that survive `lcp > acceptable_fraction * best_score`; on large hypothesis lists
 // that filter + descending sort is available on the GPU as stocs_b200_select_above).
-// point_to_plane_icp needs pcl::IterativeClosestPointWithNormals, whose source is not part of the
-// reference tree: it is declared for source compatibility and leaves the offset at identity.
+// point_to_plane_icp (pcl::IterativeClosestPointWithNormals in the reference, PCL not being part
+// of the reference tree) runs PCL's published point-to-plane loop on the GPU through
+// stocs_b200_icp_point_to_plane (csrc/icp.cu, arithmetic in csrc/stocs_icp_math.h).
 // trimmed_icp is declared but never defined in the reference either.
 #ifndef STOCS_B200_POSE_CLUSTERING_HPP_
 #define STOCS_B200_POSE_CLUSTERING_HPP_

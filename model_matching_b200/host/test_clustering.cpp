@@ -1,11 +1,33 @@
 // test_clustering -- reads poses (n, then n x (16 col-major floats + lcp)) and parameters from
 // stdin, prints the indices greedy_clustering keeps; used by tests/test_clustering.py.
+// `test_clustering icp`: reads ns nt, ns source points (x y z), nt model points (x y z nx ny nz),
+// runs clustering::point_to_plane_icp (needs the GPU) and prints the 16 column-major entries of
+// the offset and the moved source; used by tests/test_icp_gpu.py.
 #include <cstdio>
+#include <cstring>
+#include <memory>
 #include <vector>
 
 #include "pose_clustering.hpp"
 
-int main() {
+static int icp_main() {
+  int ns, nt;
+  if (scanf("%d %d", &ns, &nt) != 2) return 1;
+  auto seg = std::make_shared<PCLPointCloud>(), model = std::make_shared<PCLPointCloud>();
+  seg->points.resize(ns);
+  model->points.resize(nt);
+  for (auto& p : seg->points) { if (scanf("%f %f %f", &p.x, &p.y, &p.z) != 3) return 1; p.nx = 0; p.ny = 0; p.nz = 1; }
+  for (auto& p : model->points) if (scanf("%f %f %f %f %f %f", &p.x, &p.y, &p.z, &p.nx, &p.ny, &p.nz) != 6) return 1;
+  Eigen::Matrix4f off = Eigen::Matrix4f::Identity();
+  clustering::point_to_plane_icp(seg, model, off);
+  for (int k = 0; k < 16; ++k) printf("%.9g ", off.data()[k]);
+  printf("\n");
+  for (auto& p : seg->points) printf("%.9g %.9g %.9g\n", p.x, p.y, p.z);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "icp")) return icp_main();
   int n, max_count;
   float frac, best, min_d, min_a, sym[3];
   if (scanf("%d %f %f %d %f %f %f %f %f", &n, &frac, &best, &max_count, &min_d, &min_a, &sym[0], &sym[1], &sym[2]) != 9) return 1;

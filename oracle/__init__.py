@@ -63,6 +63,9 @@ def lib():
     L.orc_est_kd_query.argtypes = [C.c_void_p, f32p, C.c_int, C.c_float, i32p]
     L.orc_est_kd_num_nodes.argtypes = [C.c_void_p]
     L.orc_est_score.argtypes = [C.c_void_p, f32p, C.c_longlong, f32p, i32p, C.c_int]
+    L.orc_icp_point_to_plane.restype = C.c_int
+    L.orc_icp_point_to_plane.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, i32p,
+                                         C.POINTER(C.c_int)]
     L.orc_best.argtypes = [f32p, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
     L.orc_est_sample_class_base.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, i32p, f32p,
                                             C.POINTER(C.c_int)]
@@ -269,3 +272,15 @@ def best(lcp):
     bi, bl = C.c_longlong(0), C.c_float(0)
     lib().orc_best(lcp, lcp.size, C.byref(bi), C.byref(bl))
     return bi.value, bl.value
+
+
+def icp_point_to_plane(src, tgt, tgt_nrm, max_iterations=5, max_dist=0.035):
+    """-> (T 4x4, aligned source, pairs per iteration, iterations done, converged)"""
+    src, tgt, tgt_nrm = (_f32(a).reshape(-1, 3) for a in (src, tgt, tgt_nrm))
+    T = np.zeros(16, np.float32)
+    out = np.empty_like(src)
+    pairs = np.zeros(max_iterations, np.int32)
+    done = C.c_int(0)
+    ok = lib().orc_icp_point_to_plane(src, src.shape[0], tgt, tgt_nrm, tgt.shape[0], max_iterations, max_dist, T, out,
+                                      pairs, C.byref(done))
+    return T.reshape(4, 4).T.copy(), out, pairs, done.value, bool(ok)

@@ -28,6 +28,13 @@
 //                 itself (rot*scale == linear up to 1 ulp).
 //   D5            Quaternion::setFromTwoVectors' SVD branch for antiparallel vectors uses
 //                 normalized(v0 x v1) (or +x) as the axis; Eigen's sign there is unspecified.
+//   D7            point_to_plane_icp (src/pose_clustering.cpp:123-141) is PCL's
+//                 IterativeClosestPointWithNormals; PCL is not in the reference tree and its
+//                 version is not pinned.  The loop restated here is the published one (nearest
+//                 neighbour within the distance gate, TransformationEstimationPointToPlaneLLS,
+//                 final = step * final); PCL's secondary stopping tests (transformation epsilon,
+//                 relative MSE) are not restated, and exact-distance ties take the lowest target
+//                 index (FLANN's choice is unspecified).
 #include <algorithm>
 #include <array>
 #include <chrono>
@@ -45,6 +52,7 @@
 
 #include "../model_matching_b200/csrc/stocs_math.h"
 #include "../model_matching_b200/csrc/stocs_scene_math.h"
+#include "../model_matching_b200/csrc/stocs_icp_math.h"
 #include <unordered_map>
 
 #include <atomic>
@@ -1042,6 +1050,81 @@ void orc_try_sampled_base(void* h, int* ids4, float* inv2, int* ok) {
   float a = 0, b = 0;
   *ok = e->try_sampled_base(ids4, a, b) ? 1 : 0;
   inv2[0] = a; inv2[1] = b;
+}
+
+// Point-to-plane ICP, reference src/pose_clustering.cpp:123-141 (pcl::IterativeClosestPointWithNormals,
+// restated from PCL's published algorithm, see stocs_icp_math.h; PCL's secondary convergence tests
+// -- transformation epsilon, relative MSE -- are version dependent and not restated: the loop runs
+// max_iterations steps, or stops "not converged" below 3 pairs / on a singular system).
+// Sums are taken in the order the header fixes: 256-point blocks, inside a block 32-point groups
+// by a xor butterfly (16, 8, 4, 2, 1), groups in order, blocks in order.
+int orc_icp_point_to_plane(const float* src3, int n_src, const float* tgt3, const float* tgtn3, int n_tgt,
+                           int max_iterations, float max_dist, float* T16, float* aligned3, int* pairs_per_it,
+                           int* iterations_done) {
+  using namespace stocsm;
+  std::vector<V3> s((size_t)n_src);
+  for (int i = 0; i < n_src; ++i) s[i] = v3(src3[3 * i], src3[3 * i + 1], src3[3 * i + 2]);
+  float step[16], fin[16];
+  for (int k = 0; k < 16; ++k) step[k] = fin[k] = (k % 5 == 0) ? 1.f : 0.f;
+  const double max_d2 = (double)max_dist * (double)max_dist;
+  const int nblocks = (n_src + kIcpBlock - 1) / kIcpBlock;
+  int done = 0, ok = 1;
+  for (int it = 0; it < max_iterations; ++it) {
+    std::vector<double> tot(kIcpTerms, 0.0);
+    for (int b = 0; b < nblocks; ++b) {
+      double blk[kIcpTerms];
+      for (int w = 0; w < kIcpBlock / 32; ++w) {
+        double lane[32][kIcpTerms];
+        for (int l = 0; l < 32; ++l) {
+          for (int k = 0; k < kIcpTerms; ++k) lane[l][k] = 0.0;
+          const int i = b * kIcpBlock + w * 32 + l;
+          if (i >= n_src) continue;
+          s[i] = xform_point(step, s[i]);
+          float best = 3.4e38f;
+          int bj = -1;
+          for (int j = 0; j < n_tgt; ++j) {
+            const float d2 = icp_sqdist(s[i], v3(tgt3[3 * j], tgt3[3 * j + 1], tgt3[3 * j + 2]));
+            if (d2 < best) { best = d2; bj = j; }
+          }
+          if (bj >= 0 && !((double)best > max_d2))
+            icp_pair_terms(s[i], v3(tgt3[3 * bj], tgt3[3 * bj + 1], tgt3[3 * bj + 2]),
+                           v3(tgtn3[3 * bj], tgtn3[3 * bj + 1], tgtn3[3 * bj + 2]), best, lane[l]);
+        }
+        for (int k = 0; k < kIcpTerms; ++k) {
+          double v[32], u[32];
+          for (int l = 0; l < 32; ++l) v[l] = lane[l][k];
+          for (int off = 16; off >= 1; off >>= 1) {
+            for (int l = 0; l < 32; ++l) u[l] = v[l] + v[l ^ off];
+            for (int l = 0; l < 32; ++l) v[l] = u[l];
+          }
+          blk[k] = (w == 0) ? v[0] : blk[k] + v[0];
+        }
+      }
+      for (int k = 0; k < kIcpTerms; ++k) tot[k] = (b == 0) ? blk[k] : tot[k] + blk[k];
+    }
+    const int pairs = (int)tot[27];
+    if (pairs_per_it) pairs_per_it[it] = pairs;
+    double x[6];
+    if (pairs < 3 || !icp_solve6(tot.data(), tot.data() + 21, x)) {
+      ok = 0;
+      for (int k = 0; k < 16; ++k) step[k] = (k % 5 == 0) ? 1.f : 0.f;
+      for (int r = it + 1; r < max_iterations; ++r) if (pairs_per_it) pairs_per_it[r] = 0;
+      break;
+    }
+    float m[16], f[16];
+    icp_construct(x, m);
+    mat4_mul(m, fin, f);
+    memcpy(step, m, 64);
+    memcpy(fin, f, 64);
+    ++done;
+  }
+  for (int i = 0; i < n_src; ++i) {
+    const V3 q = xform_point(step, s[i]);
+    if (aligned3) { aligned3[3 * i] = q.x; aligned3[3 * i + 1] = q.y; aligned3[3 * i + 2] = q.z; }
+  }
+  memcpy(T16, fin, 64);
+  if (iterations_done) *iterations_done = done;
+  return ok;
 }
 
 }  // extern "C"
