@@ -60,3 +60,13 @@ def test_packed_instance_mode(tmp_path):
     pre, out, scene_dir = _run(str(tmp_path), "packed", "dove", env)
     assert "After sampling |M|= 944" in pre
     _check_outputs(scene_dir, "dove", out)
+
+
+def test_linemod_class_mode(tmp_path):
+    """LINEMOD settings of the reference README (millimetre model, 1 mm depth units)"""
+    env = {"STOCS_CAM_INTRINSICS": "572.4114,325.2611,573.57043,242.04899", "STOCS_DEPTH_SCALE": "0.001",
+           "STOCS_MODEL_VOXEL_SIZE": "10", "STOCS_NORMAL_RADIUS": "5", "STOCS_MODEL_SCALE": "0.001"}
+    pre, out, scene_dir = _run(str(tmp_path), "linemod", "obj_06", env)
+    assert "After sampling |M|= 446" in pre
+    assert "|map(M)| = 443361" in out
+    _check_outputs(scene_dir, "obj_06", out)
