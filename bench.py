@@ -309,25 +309,35 @@ def main():
     hT = torch.from_numpy(T).pin_memory()
     hlcp = torch.empty(H, dtype=torch.float32).pin_memory()
     hinl = torch.empty(H, dtype=torch.int32).pin_memory()
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 20))
 
     def e2e_step():
         ctx.score_lcp_ptr(hT.data_ptr(), H, hlcp.data_ptr(), hinl.data_ptr())
         return ctx.reduce_best(None, K=TOPK)
 
-    e2e_step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        best = e2e_step()
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * H * e2e_steps / float(te[0])
+    def e2e_measure():
+        e2e_step()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            b = e2e_step()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * H * e2e_steps / float(te[0]), b
+
+    # headline: the kernel reads the page-locked transforms in place over PCIe (64 B per hypothesis
+    # cross the bus inside the timed region, no staging copy); second figure: the same call with
+    # the transforms staged through HBM by chunked cudaMemcpyAsync (what pageable callers get)
+    e2e_value, best = e2e_measure()
+    os.environ["STOCS_NO_ZERO_COPY"] = "1"
+    e2e_staged, best_staged = e2e_measure()
+    del os.environ["STOCS_NO_ZERO_COPY"]
+    assert best_staged[0] == best[0] and best_staged[1] == best[1]
 
     if rank == 0:
         M = N_MODEL
@@ -352,7 +362,10 @@ def main():
                           "l2": "inputs larger than L2 (64 MB transforms + ~%d MB scene index per step)" % int(
                               (ctx.counters()[3] * 16 + ctx.counters()[2] * 4 + N_SCENE * 16) / 1e6)},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": H * 64, "d2h_bytes_per_step": H * 8,
-                       "steps": e2e_steps, "best_index": int(best[0]), "best_lcp": float(best[1])},
+                       "steps": e2e_steps, "best_index": int(best[0]), "best_lcp": float(best[1]),
+                       "input_path": "pinned host transforms read in place by the kernel over PCIe (zero-copy), "
+                                     "results copied back with cudaMemcpyAsync",
+                       "staged_copy_value": e2e_staged},
                "gpu_launches": args.steps * 3,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -114,6 +114,7 @@ extern "C" int stocs_b200_select_above(stocs_b200_ctx* ctx, const float* lcp, in
     STOCS_CUDA(ctx, ctx->d_lcp.ensure((size_t)H * 4));
     STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_lcp.p, lcp, (size_t)H * 4, cudaMemcpyHostToDevice, st));
     ctx->last_H = H;
+    ctx->top_valid = false;
   } else if (ctx->last_H != H || !ctx->d_lcp.p) {
     STOCS_FAIL(ctx, STOCS_E_STATE, "select_above: no resident lcp array of that size");
   }

@@ -114,6 +114,10 @@ struct stocs_b200_ctx {
 
   // last score call
   int64_t last_H = 0;
+  // top-32 of the resident lcp array, computed by score_lcp behind its result copies
+  struct TopCache { int64_t idx[32]; float val[32]; };
+  TopCache* h_top = nullptr;   // page-locked
+  bool top_valid = false;
   int64_t counters[8] = {0};
   bool timing_valid = false;
 };

@@ -161,3 +161,40 @@ def test_multi_object_sweep_shares_one_scene_index(gpu_ctx, small_scene):
         assert np.array_equal(inl, oinl), M
         assert np.array_equal(lcp.view(np.uint32), olcp.view(np.uint32)), M
     assert gpu_ctx.counters()[2] == cells_before
+
+
+def test_host_call_pinned_and_pageable_buffers_agree(gpu_ctx, small_scene):
+    """stocs_b200_score_lcp reads page-locked transforms in place (zero-copy, one launch) and
+    stages pageable ones through HBM in chunks on two streams; both must give the same bits."""
+    import torch
+    sc, mpos, mnrm = small_scene
+    H = 150_000                                   # above the 2^16 threshold of the chunked path
+    T, _ = synth.make_hypotheses(H, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=5, near_fraction=0.03)
+    gpu_ctx.upload_model(mpos, mnrm)
+    gpu_ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    lcp_pg, inl_pg = gpu_ctx.score_lcp(T)        # numpy = pageable
+    hT = torch.from_numpy(T).pin_memory()
+    hl = torch.empty(H, dtype=torch.float32).pin_memory()
+    hi = torch.empty(H, dtype=torch.int32).pin_memory()
+    gpu_ctx.score_lcp_ptr(hT.data_ptr(), H, hl.data_ptr(), hi.data_ptr())
+    assert np.array_equal(hl.numpy().view(np.uint32), lcp_pg.view(np.uint32))
+    assert np.array_equal(hi.numpy(), inl_pg)
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+    olcp, oinl = est.score(T[:20000], threads=8)
+    assert np.array_equal(inl_pg[:20000], oinl) and np.array_equal(lcp_pg[:20000].view(np.uint32), olcp.view(np.uint32))
+    # the reduction of the resident array (score_lcp computes it behind its result copies) is the
+    # one an explicit array gives, for both paths and every K
+    want = gpu_ctx.reduce_best(lcp_pg, K=32)
+    assert (want[0], want[1]) == oracle.best(lcp_pg)
+    gpu_ctx.score_lcp_ptr(hT.data_ptr(), H, hl.data_ptr(), hi.data_ptr())
+    for K in (1, 7, 32):
+        got = gpu_ctx.reduce_best(None, K=K)
+        assert got[0] == want[0] and got[1] == want[1]
+        assert np.array_equal(got[2], want[2][:K]) and np.array_equal(got[3], want[3][:K])
+    gpu_ctx.score_lcp(T)
+    got = gpu_ctx.reduce_best(None, K=32)
+    assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
+    # a smaller second call must not be answered from the first call's cache
+    lcp_s, _ = gpu_ctx.score_lcp(T[:70000])
+    got = gpu_ctx.reduce_best(None, K=4)
+    assert (got[0], got[1]) == oracle.best(lcp_s)
