@@ -149,19 +149,24 @@ __global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc
 
 // per brick: occupancy mask and number of occupied cells
 __global__ void brick_mask_kernel(const uint32_t* __restrict__ cell_start, uint32_t nbricks,
-                                  unsigned long long* __restrict__ masks, uint32_t* __restrict__ occ) {
+                                  unsigned long long* __restrict__ masks, uint32_t* __restrict__ occ,
+                                  uint32_t* __restrict__ brick_occ) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbricks) return;
   unsigned long long m = 0ull;
-  const uint32_t* cs = cell_start + (size_t)b * 64;
-  uint32_t prev = cs[0];
-  for (int k = 0; k < 64; ++k) {
-    const uint32_t nxt = cs[k + 1];
-    if (nxt != prev) m |= 1ull << k;
-    prev = nxt;
+  if (b < nbricks) {
+    const uint32_t* cs = cell_start + (size_t)b * 64;
+    uint32_t prev = cs[0];
+    for (int k = 0; k < 64; ++k) {
+      const uint32_t nxt = cs[k + 1];
+      if (nxt != prev) m |= 1ull << k;
+      prev = nxt;
+    }
+    masks[b] = m;
+    occ[b] = (uint32_t)__popcll(m);
   }
-  masks[b] = m;
-  occ[b] = (uint32_t)__popcll(m);
+  // 1 bit per brick: "has an occupied cell" (the scoring kernel's second-level filter)
+  const unsigned w = __ballot_sync(0xffffffffu, m != 0ull);
+  if ((threadIdx.x & 31) == 0 && b < nbricks) brick_occ[b >> 5] = w;
 }
 
 // brick table {mask lo, mask hi, index of the brick's first occupied cell, 0} + compact starts
@@ -333,15 +338,21 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   });
   struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{kd_thread};
 
-  // grid geometry: cell edge = 2*eps unless that needs more than kMaxCells cells
+  // grid geometry.  Cell edge in units of eps, measured on B200 with the S1 workload (10^6
+  // hypotheses, all bit-identical): 2.0 -> 4.3 ms, 1.0 -> 2.93 ms, 0.6 -> 2.73 ms, 0.5 -> 2.64 ms,
+  // 0.45 -> 2.62 ms, 0.405 -> 2.65 ms, 0.4 -> 3.46 ms (one more coarse-map level).  Smaller cells
+  // mean shorter candidate lists (the list of a cell holds the points within eps of its box, a
+  // volume of (c^3 + 6c^2 + 3*pi*c + 4.19) eps^3: 20.6 at c = 1, 10.5 at c = 0.5, against the
+  // 4.19 of the query sphere itself) and a thinner occupied shell; a point is replicated into
+  // that volume / c^3 lists and the tables grow with 1/c^3.  0.5 is the default: 84 candidate records per scene point
+  // (1.4 GB at 2^20 points), 16 B of brick table per 64 cells.  The scale is raised until the
+  // candidate records fit in 8 GB and the cells in kMaxCells.  STOCS_CELL_SCALE / STOCS_MAX_CELLS
+  // override (tuning knobs).
   const double eps = ctx->eps;
-  const double kMaxCells = 96.0 * 1024 * 1024;
-  // cell edge in units of eps.  1.0 measured best on B200 (3.5 ms vs 4.3 ms at 2.0 for the S1
-  // workload): shorter candidate lists and a thinner occupied shell outweigh the larger tables.
-  // Replication of a point is ~ (c^3 + 6c^2 + 3*pi*c + 4.19) / c^3 lists; the scale is raised
-  // until the candidate records fit in 8 GB.  STOCS_CELL_SCALE overrides (tuning knob).
-  double cell_scale = 1.0;
-  if (const char* e = getenv("STOCS_CELL_SCALE")) { double v = atof(e); if (v >= 0.5 && v <= 16.0) cell_scale = v; }
+  double kMaxCells = 512.0 * 1024 * 1024;
+  if (const char* e = getenv("STOCS_MAX_CELLS")) { double v = atof(e); if (v >= 1e6 && v <= 4e9) kMaxCells = v; }
+  double cell_scale = 0.5;
+  if (const char* e = getenv("STOCS_CELL_SCALE")) { double v = atof(e); if (v >= 0.25 && v <= 16.0) cell_scale = v; }
   for (;;) {
     const double c = cell_scale;
     const double repl = (c * c * c + 6 * c * c + 3 * 3.14159265 * c + 4.19) / (c * c * c);
@@ -350,15 +361,20 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   }
   double cell = cell_scale * eps;
   double ext[3] = {(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]};
+  // apron: a query can lie up to eps outside the scene's bounding box and still have a neighbour,
+  // so the grid extends floor(eps / cell) + 1 cells beyond the box on every side
+  int apron = 2;
   for (;;) {
-    double n = (floor(ext[0] / cell) + 3) * (floor(ext[1] / cell) + 3) * (floor(ext[2] / cell) + 3);
+    apron = (int)floor(eps / cell) + 1;
+    double n = (floor(ext[0] / cell) + 1 + 2 * apron) * (floor(ext[1] / cell) + 1 + 2 * apron) * (floor(ext[2] / cell) + 1 + 2 * apron);
     if (n <= kMaxCells) break;
     cell *= 1.25;
   }
   GridDesc g;
-  g.ox = (float)(mn[0] - cell); g.oy = (float)(mn[1] - cell); g.oz = (float)(mn[2] - cell);
+  g.ox = (float)(mn[0] - apron * cell); g.oy = (float)(mn[1] - apron * cell); g.oz = (float)(mn[2] - apron * cell);
   g.inv_cell = (float)(1.0 / cell);
-  g.nx = (int)floor(ext[0] / cell) + 3; g.ny = (int)floor(ext[1] / cell) + 3; g.nz = (int)floor(ext[2] / cell) + 3;
+  g.nx = (int)floor(ext[0] / cell) + 1 + 2 * apron; g.ny = (int)floor(ext[1] / cell) + 1 + 2 * apron;
+  g.nz = (int)floor(ext[2] / cell) + 1 + 2 * apron;
   g.nbx = (g.nx + 3) / 4; g.nby = (g.ny + 3) / 4; g.nbz = (g.nz + 3) / 4;
   g.nbricks = (uint32_t)((size_t)g.nbx * g.nby * g.nbz);
   g.ncells = g.nbricks * 64u;
@@ -396,7 +412,9 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, d_occ_scan.ensure((size_t)(g.nbricks + 1) * 4));
   STOCS_CUDA(ctx, cudaMemsetAsync(d_occ.p, 0, (size_t)(g.nbricks + 1) * 4, st));
   const unsigned bb = (g.nbricks + 127) / 128;
-  brick_mask_kernel<<<bb, 128, 0, st>>>(dense_start, g.nbricks, d_masks.as<unsigned long long>(), d_occ.as<uint32_t>());
+  STOCS_CUDA(ctx, ctx->d_brick_occ.ensure(((size_t)g.nbricks + 31) / 32 * 4));
+  brick_mask_kernel<<<bb, 128, 0, st>>>(dense_start, g.nbricks, d_masks.as<unsigned long long>(), d_occ.as<uint32_t>(),
+                                        ctx->d_brick_occ.as<uint32_t>());
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
   STOCS_CUDA(ctx, ctx->d_tmp2.ensure(tmp_bytes));
   cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
@@ -406,7 +424,9 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, ctx->d_bricks.ensure((size_t)g.nbricks * 16));
   // coarse level: blocks of 2^k cells per axis, k >= 2 (brick), smallest k whose bitmap fits 16 KB
   int cshift = 2, cnx = g.nbx, cny = g.nby, cnz = g.nbz;
-  while ((size_t)cnx * cny * cnz > 16 * 1024 * 8) {
+  size_t coarse_bits = 16 * 1024 * 8;
+  if (const char* e = getenv("STOCS_COARSE_BITS")) { long v = atol(e); if (v >= 1024 && v <= 16 * 1024 * 8) coarse_bits = (size_t)v; }
+  while ((size_t)cnx * cny * cnz > coarse_bits) {
     ++cshift;
     cnx = (g.nx + (1 << cshift) - 1) >> cshift; cny = (g.ny + (1 << cshift) - 1) >> cshift; cnz = (g.nz + (1 << cshift) - 1) >> cshift;
   }

@@ -47,6 +47,7 @@ constexpr int kQueue = SCORE_QUEUE; // queued queries per warp
 struct ScoreArgs {
   const uint4* __restrict__ bricks;
   const uint32_t* __restrict__ coarse;   // 1 bit per block of 2^coarse_shift cells per axis: any occupied cell inside
+  const uint32_t* __restrict__ brick_occ;  // 1 bit per brick: any occupied cell inside
   int coarse_words;                      // words of `coarse` (always staged in shared memory, <= 16 KB)
   int coarse_shift, coarse_nx, coarse_ny;
   const uint32_t* __restrict__ starts;
@@ -119,7 +120,42 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
   return v;
 }
 
-#ifdef SCORE_STREAM_CAND
+// L2 policies (default on; -DSCORE_NO_L2_HINTS / -DSCORE_NO_BRICK_OCC are the A/B switches).  With
+// 0.5-eps cells the launch moves 12 GB through DRAM at ~4.4 TB/s and waits on memory (long
+// scoreboard is the top stall), so L2 residency matters: brick records (70 MB at S1, re-used by
+// every hypothesis) are loaded evict_last, candidate records (1.4 GB, touched once per query)
+// evict_first: 2.58 -> 2.50 ms; the one-bit-per-brick filter in front of the brick record:
+// 2.50 -> 2.48 ms.  (sm_100a accepts .L2::evict_* directly only on 256-bit loads, hence
+// createpolicy + .L2::cache_hint.)
+#ifndef SCORE_NO_L2_HINTS
+#define SCORE_L2_HINTS
+#endif
+#ifndef SCORE_NO_BRICK_OCC
+#define SCORE_BRICK_OCC
+#endif
+#ifdef SCORE_L2_HINTS
+__device__ __forceinline__ uint4 ld_brick_keep(const uint4* p) {
+  uint4 v;
+  asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n"
+               "  ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], pol; }"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_cand_first(const float4* p) {
+  float4 v;
+  asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n"
+               "  ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], pol; }"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+#define LD_BRICK ld_brick_keep
+#else
+#define LD_BRICK __ldg
+#endif
+
+#if defined(SCORE_L2_HINTS)
+#define LD_CAND ld_cand_first
+#elif defined(SCORE_STREAM_CAND)
 #define LD_CAND ld_stream
 #else
 #define LD_CAND __ldg
@@ -269,12 +305,15 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   Acc r;
   r.ties = 0;
 
+  // Work distribution: lane 0 claims the next hypothesis from the global counter when the warp has
+  // finished one.  (Claiming ahead does not pay: the result cannot stay in a register across a
+  // hypothesis at the 32-register cap, so the warp waits for the atomic either way -- 10 % of the
+  // stall samples when it was a prefetch; claiming 4 or 8 at a time lengthens the tail by more
+  // than it saves: 2.63 / 2.76 ms against 2.58 ms.)
   int h = 0;
   if (lane == 0) h = (int)atomicAdd(a.work_counter, 1ull);
   h = __shfl_sync(0xffffffffu, h, 0);
   while (h < a.H) {
-    int h_next = 0;
-    if (lane == 0) h_next = (int)atomicAdd(a.work_counter, 1ull);
     // lanes 0..11 fetch the 3x4 transform (column-major 4x4: element (r,c) at c*4+r) and publish
     // it, with its grid-coordinate version G = inv_cell * (T - origin), to the warp's shared slot
     if (lane < 12) {
@@ -326,7 +365,14 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
         const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
         const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy), iz = (unsigned)__float2int_rd(fz);
         uint4 br = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) br = __ldg(a.bricks + ((iz >> 2) * (unsigned)a.g.nby + (iy >> 2)) * (unsigned)a.g.nbx + (ix >> 2));
+        const unsigned bidx = ((iz >> 2) * (unsigned)a.g.nby + (iy >> 2)) * (unsigned)a.g.nbx + (ix >> 2);
+#ifdef SCORE_BRICK_OCC
+        // second-level filter: 1 bit per brick (L2-resident, 1/128 of the brick table) before the
+        // 16 B brick record, which for an empty brick would be a wasted DRAM access
+        if (valid && ((__ldg(a.brick_occ + (bidx >> 5)) >> (bidx & 31u)) & 1u)) br = LD_BRICK(a.bricks + bidx);
+#else
+        if (valid) br = LD_BRICK(a.bricks + bidx);
+#endif
         const unsigned bit = ((iz & 3u) << 4) | ((iy & 3u) << 2) | (ix & 3u);
         const unsigned half = (bit & 32u) ? br.y : br.x;      // 64-bit occupancy mask as two words
         const bool has = (half >> (bit & 31u)) & 1u;
@@ -355,7 +401,8 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
       a.lcp[h] = r.acc / (float)M;
       if (a.inl) a.inl[h] = r.inl;
     }
-    h = __shfl_sync(0xffffffffu, h_next, 0);
+    if (lane == 0) h = (int)atomicAdd(a.work_counter, 1ull);
+    h = __shfl_sync(0xffffffffu, h, 0);
     __syncwarp();
   }
   if (r.ties) atomicAdd(a.tie_counter, (unsigned long long)r.ties);
@@ -384,6 +431,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   ScoreArgs a;
   a.bricks = ctx->d_bricks.as<uint4>();
   a.coarse = ctx->d_coarse.as<uint32_t>();
+  a.brick_occ = ctx->d_brick_occ.as<uint32_t>();
   a.coarse_words = ctx->coarse_words;
   a.coarse_shift = ctx->coarse_shift; a.coarse_nx = ctx->coarse_nx; a.coarse_ny = ctx->coarse_ny;
   a.starts = ctx->d_cell_start.as<uint32_t>();

@@ -89,6 +89,7 @@ struct stocs_b200_ctx {
   DevBuf d_edge, d_inst_state, d_mask_store, d_frontier;
   int img_w = 0, img_h = 0;
   GridDesc grid{};
+  DevBuf d_brick_occ;                  // 1 bit per brick: brick has an occupied cell
   DevBuf d_coarse;                     // 1 bit per block of 2^coarse_shift cells/axis (>= brick): block has an occupied cell
   int coarse_shift = 2, coarse_nx = 0, coarse_ny = 0, coarse_nz = 0, coarse_words = 0;
   DevBuf d_bricks;                     // uint4 {mask lo, mask hi, first occupied-cell rank, 0} per brick

@@ -61,8 +61,9 @@ for r in rows[hi + 1:]:
         agg[name][1] += num(r[mv])
 tot = sum(v[1] for v in agg.values())
 out = [f"# per-kernel totals from profiles/{tag}_launches.csv (ncu gpu__time_duration.sum, cold-cache, serialised:",
-       "# compare SHARES).  The bench process also uploads the scene/model, runs 5 end-to-end steps (4 chunked launches each)",
-       "# and the YCB pose-latency pipeline, hence the other kernels."]
+       "# compare SHARES).  Besides the warm-up and timed steps the bench process uploads the scene/model (index build),",
+       "# runs the end-to-end steps (zero-copy: 1 launch each; staged: 4 chunked launches each) and the YCB pose-latency",
+       "# pipeline, hence the other kernels and the short score_lcp_kernel launches."]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:20]:
     out.append(f"{k:54s} n={v[0]:4d} total_ms={v[1] / 1e6:10.3f} share={v[1] / tot:.4f}")
 open(f"profiles/{tag}_launch_shares.txt", "w").write("\n".join(out) + "\n")
