@@ -173,14 +173,14 @@ __global__ void brick_mask_kernel(const uint32_t* __restrict__ cell_start, uint3
 __global__ void brick_table_kernel(const uint32_t* __restrict__ cell_start, const unsigned long long* __restrict__ masks,
                                    const uint32_t* __restrict__ occ_scan, uint32_t nbricks, uint32_t total_cand,
                                    uint4* __restrict__ bricks, uint32_t* __restrict__ starts,
-                                   uint32_t* __restrict__ coarse, GridDesc g, int cshift, int cnx, int cny) {
+                                   uint32_t* __restrict__ coarse, GridDesc g, int cshift, int csx, int csy) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbricks) return;
   const unsigned long long m = masks[b];
   if (m) {  // mark the coarse block (2^cshift cells per axis, cshift >= 2) this brick lies in
     const int bx = b % g.nbx, by = (b / g.nbx) % g.nby, bz = b / (g.nbx * g.nby);
     const int s = cshift - 2;
-    const uint32_t cidx = (uint32_t)(((bz >> s) * cny + (by >> s)) * cnx + (bx >> s));
+    const uint32_t cidx = (uint32_t)(((bz >> s) * csy + (by >> s)) * csx + (bx >> s));  // strides = blocks + 1
     atomicOr(&coarse[cidx >> 5], 1u << (cidx & 31));
   }
   const uint32_t base = occ_scan[b];
@@ -375,6 +375,19 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   g.inv_cell = (float)(1.0 / cell);
   g.nx = (int)floor(ext[0] / cell) + 1 + 2 * apron; g.ny = (int)floor(ext[1] / cell) + 1 + 2 * apron;
   g.nz = (int)floor(ext[2] / cell) + 1 + 2 * apron;
+  // Coarse occupancy map: blocks of 2^k cells per axis, k >= 2 (brick), smallest k whose bitmap
+  // fits 16 KB.  The map is laid out with one extra, always-empty block per axis (index = number
+  // of real blocks): the scoring kernel clamps block coordinates to it instead of testing grid
+  // bounds (cells left of the grid are negative ints = huge unsigned values, so they clamp there
+  // too).  The grid is padded to whole blocks so that "inside a real block" == "inside the grid".
+  int cshift = 2, cnx = (g.nx + 3) >> 2, cny = (g.ny + 3) >> 2, cnz = (g.nz + 3) >> 2;
+  size_t coarse_bits = 16 * 1024 * 8;
+  if (const char* e = getenv("STOCS_COARSE_BITS")) { long v = atol(e); if (v >= 1024 && v <= 16 * 1024 * 8) coarse_bits = (size_t)v; }
+  while ((size_t)(cnx + 1) * (cny + 1) * (cnz + 1) > coarse_bits) {
+    ++cshift;
+    cnx = (g.nx + (1 << cshift) - 1) >> cshift; cny = (g.ny + (1 << cshift) - 1) >> cshift; cnz = (g.nz + (1 << cshift) - 1) >> cshift;
+  }
+  g.nx = cnx << cshift; g.ny = cny << cshift; g.nz = cnz << cshift;
   g.nbx = (g.nx + 3) / 4; g.nby = (g.ny + 3) / 4; g.nbz = (g.nz + 3) / 4;
   g.nbricks = (uint32_t)((size_t)g.nbx * g.nby * g.nbz);
   g.ncells = g.nbricks * 64u;
@@ -422,22 +435,14 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, cudaMemcpyAsync(&n_occ, d_occ_scan.as<uint32_t>() + g.nbricks, 4, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   STOCS_CUDA(ctx, ctx->d_bricks.ensure((size_t)g.nbricks * 16));
-  // coarse level: blocks of 2^k cells per axis, k >= 2 (brick), smallest k whose bitmap fits 16 KB
-  int cshift = 2, cnx = g.nbx, cny = g.nby, cnz = g.nbz;
-  size_t coarse_bits = 16 * 1024 * 8;
-  if (const char* e = getenv("STOCS_COARSE_BITS")) { long v = atol(e); if (v >= 1024 && v <= 16 * 1024 * 8) coarse_bits = (size_t)v; }
-  while ((size_t)cnx * cny * cnz > coarse_bits) {
-    ++cshift;
-    cnx = (g.nx + (1 << cshift) - 1) >> cshift; cny = (g.ny + (1 << cshift) - 1) >> cshift; cnz = (g.nz + (1 << cshift) - 1) >> cshift;
-  }
   ctx->coarse_shift = cshift; ctx->coarse_nx = cnx; ctx->coarse_ny = cny; ctx->coarse_nz = cnz;
-  ctx->coarse_words = (int)(((size_t)cnx * cny * cnz + 31) / 32);
+  ctx->coarse_words = (int)(((size_t)(cnx + 1) * (cny + 1) * (cnz + 1) + 31) / 32);
   STOCS_CUDA(ctx, ctx->d_coarse.ensure((size_t)ctx->coarse_words * 4));
   STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_coarse.p, 0, (size_t)ctx->coarse_words * 4, st));
   STOCS_CUDA(ctx, ctx->d_cell_start.ensure((size_t)(n_occ + 1) * 4));
   brick_table_kernel<<<bb, 128, 0, st>>>(dense_start, d_masks.as<unsigned long long>(), d_occ_scan.as<uint32_t>(), g.nbricks,
                                          total, ctx->d_bricks.as<uint4>(), ctx->d_cell_start.as<uint32_t>(),
-                                         ctx->d_coarse.as<uint32_t>(), g, cshift, cnx, cny);
+                                         ctx->d_coarse.as<uint32_t>(), g, cshift, cnx + 1, cny + 1);
   STOCS_CUDA(ctx, cudaGetLastError());
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->counters[4] = n_occ;

@@ -49,7 +49,8 @@ struct ScoreArgs {
   const uint32_t* __restrict__ coarse;   // 1 bit per block of 2^coarse_shift cells per axis: any occupied cell inside
   const uint32_t* __restrict__ brick_occ;  // 1 bit per brick: any occupied cell inside
   int coarse_words;                      // words of `coarse` (always staged in shared memory, <= 16 KB)
-  int coarse_shift, coarse_nx, coarse_ny;
+  int coarse_shift, coarse_nx, coarse_ny, coarse_nz;  // real blocks per axis; index n* is the empty border block
+  int coarse_sx, coarse_sy;                           // row / slab strides of the map = blocks + 1
   const uint32_t* __restrict__ starts;
   const float4* __restrict__ cand;
   const float4* __restrict__ sattr;
@@ -345,12 +346,13 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
         const float fy = __fmaf_rn(g1, mp.x, __fmaf_rn(g4, mp.y, __fmaf_rn(g7, mp.z, g10)));
         const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
         const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy), iz = (unsigned)__float2int_rd(fz);
-        bool pass = false;
-        if (ix < (unsigned)a.g.nx && iy < (unsigned)a.g.ny && iz < (unsigned)a.g.nz) {
-          const unsigned k = (unsigned)a.coarse_shift;
-          const uint32_t cidx = ((iz >> k) * (unsigned)a.coarse_ny + (iy >> k)) * (unsigned)a.coarse_nx + (ix >> k);
-          pass = (s_coarse[cidx >> 5] >> (cidx & 31)) & 1u;
-        }
+        // block coordinates clamped to the always-empty border block (index = number of real
+        // blocks): no bounds test, no branch; cells left of the grid are huge as unsigned
+        const unsigned k = (unsigned)a.coarse_shift;
+        const unsigned cx = min(ix >> k, (unsigned)a.coarse_nx), cy = min(iy >> k, (unsigned)a.coarse_ny),
+                       cz = min(iz >> k, (unsigned)a.coarse_nz);
+        const uint32_t cidx = (cz * (unsigned)a.coarse_sy + cy) * (unsigned)a.coarse_sx + cx;
+        const bool pass = (s_coarse[cidx >> 5] >> (cidx & 31)) & 1u;
         const unsigned pm = __ballot_sync(0xffffffffu, pass);
         if (pass) q.plist[nl + __popc(pm & lt_mask)] = (uint8_t)(rr * 32 + lane);
         nl += __popc(pm);
@@ -433,7 +435,8 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.coarse = ctx->d_coarse.as<uint32_t>();
   a.brick_occ = ctx->d_brick_occ.as<uint32_t>();
   a.coarse_words = ctx->coarse_words;
-  a.coarse_shift = ctx->coarse_shift; a.coarse_nx = ctx->coarse_nx; a.coarse_ny = ctx->coarse_ny;
+  a.coarse_shift = ctx->coarse_shift; a.coarse_nx = ctx->coarse_nx; a.coarse_ny = ctx->coarse_ny; a.coarse_nz = ctx->coarse_nz;
+  a.coarse_sx = ctx->coarse_nx + 1; a.coarse_sy = ctx->coarse_ny + 1;
   a.starts = ctx->d_cell_start.as<uint32_t>();
   a.cand = ctx->d_cand.as<float4>();
   a.sattr = ctx->d_sattr.as<float4>();
