@@ -135,18 +135,27 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
 #define SCORE_BRICK_OCC
 #endif
 #ifdef SCORE_L2_HINTS
+// the policy words are pure values (plain asm, so the compiler may hoist or rematerialise them)
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ uint4 ld_brick_keep(const uint4* p) {
   uint4 v;
-  asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n"
-               "  ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], pol; }"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(l2_policy_evict_last()));
   return v;
 }
 __device__ __forceinline__ float4 ld_cand_first(const float4* p) {
   float4 v;
-  asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n"
-               "  ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], pol; }"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(l2_policy_evict_first()));
   return v;
 }
 #define LD_BRICK ld_brick_keep
