@@ -300,7 +300,10 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   float* s_model = reinterpret_cast<float*>(smem_raw);
   const int Mpad = a.Mpad;
   const int lane = (int)lane_id();
-  const int warp = threadIdx.x >> 5;
+  // warp index through redux: the result lives in a UNIFORM register, and so does everything
+  // derived from it (the warp's queue address), outside the 32-register budget -- as a plain
+  // tid >> 5 the queue address was spilled and re-loaded at 18 sites (37 local loads per hypothesis)
+  const int warp = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
   // dynamic shared memory: [model positions float4 x Mpad][coarse bitmap][one WarpQueue per warp]
   for (int i = threadIdx.x; i < 4 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
   uint32_t* s_coarse = reinterpret_cast<uint32_t*>(s_model + 4 * Mpad);
@@ -320,9 +323,10 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   // hypothesis at the 32-register cap, so the warp waits for the atomic either way -- 10 % of the
   // stall samples when it was a prefetch; claiming 4 or 8 at a time lengthens the tail by more
   // than it saves: 2.63 / 2.76 ms against 2.58 ms.)
+  // (claimed index broadcast by redux for the same reason: h stays in a uniform register)
   int h = 0;
   if (lane == 0) h = (int)atomicAdd(a.work_counter, 1ull);
-  h = __shfl_sync(0xffffffffu, h, 0);
+  h = (int)__reduce_max_sync(0xffffffffu, (unsigned)h);
   while (h < a.H) {
     // lanes 0..11 fetch the 3x4 transform (column-major 4x4: element (r,c) at c*4+r) and publish
     // it, with its grid-coordinate version G = inv_cell * (T - origin), to the warp's shared slot
@@ -412,8 +416,9 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
       a.lcp[h] = r.acc / (float)M;
       if (a.inl) a.inl[h] = r.inl;
     }
+    h = 0;
     if (lane == 0) h = (int)atomicAdd(a.work_counter, 1ull);
-    h = __shfl_sync(0xffffffffu, h, 0);
+    h = (int)__reduce_max_sync(0xffffffffu, (unsigned)h);
     __syncwarp();
   }
   if (r.ties) atomicAdd(a.tie_counter, (unsigned long long)r.ties);
