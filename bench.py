@@ -48,8 +48,9 @@ def workload(rank, H):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started before the warm-up (its
+    first sample can take a second); only samples stamped inside the timed region are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,31 +66,48 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def stop(self):
+    def wait_first_sample(self, timeout=3.0):
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.06)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
         self.f.seek(0)
-        sm, smax, reasons = [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); smax.append(float(c[2]))
+                ts = None
+                try:
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    pass
+                rows.append((ts, float(c[1]), float(c[2]),
+                             [nm for nm, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
+        inside = [r for r in rows if t_begin is not None and r[0] is not None and t_begin - 0.05 <= r[0] <= t_end + 0.05]
+        window = "timed region"
+        if not inside:  # clock skew / unparsable stamps: fall back to every sample (warm-up included)
+            inside, window = rows, "whole run"
+        sm, smax = [r[1] for r in inside], [r[2] for r in inside]
+        reasons = sorted({nm for r in inside for nm in r[3]})
         return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "sm_max_mhz": float(max(smax)) if smax else None, "reasons": reasons,
+                "samples": len(sm), "window": window}
 
 
 def cpu_baseline(sc, mpos, mnrm, T, seconds_target=15.0):
@@ -221,7 +239,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--hyp", type=int, default=H_PER_GPU, help="hypotheses per GPU (default: the named config)")
@@ -276,6 +294,10 @@ def main():
             dist.all_gather_into_tensor(gather_i, dtop_i)
             dist.all_gather_into_tensor(gather_v, dtop_v)
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first_sample()
     for _ in range(warm):
         step()
     torch.cuda.synchronize(dev)
@@ -283,9 +305,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    t_begin = time.time()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -296,7 +316,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_begin, time.time()) if sampler else None
     ms_total = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=dev)
