@@ -262,8 +262,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version / debug lines to stdout by default; stdout carries the JSON line
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the JSON line.
+        # (NCCL_DEBUG_FILE is honoured only above level VERSION, so VERSION is raised to WARN.)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     H = args.hyp
     warm = max(args.warmup, 3)
