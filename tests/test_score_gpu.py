@@ -198,3 +198,32 @@ def test_host_call_pinned_and_pageable_buffers_agree(gpu_ctx, small_scene):
     lcp_s, _ = gpu_ctx.score_lcp(T[:70000])
     got = gpu_ctx.reduce_best(None, K=4)
     assert (got[0], got[1]) == oracle.best(lcp_s)
+
+
+@pytest.mark.parametrize("scale,coarse_bits", [("0.25", None), ("0.5", "2048"), ("0.75", None), ("1.0", "1024"), ("2.0", None), ("3.7", None)])
+def test_index_geometry_knobs_do_not_change_results(small_scene, scale, coarse_bits, monkeypatch):
+    """Cell edge (in eps) and coarse-map capacity are tuning knobs of the scene index: apron width,
+    padding to whole coarse blocks and the always-empty border block must keep every setting
+    bit-identical to the oracle (hypotheses reach up to eps outside the scene's bounding box)."""
+    sc, mpos, mnrm = small_scene
+    monkeypatch.setenv("STOCS_CELL_SCALE", scale)
+    if coarse_bits:
+        monkeypatch.setenv("STOCS_COARSE_BITS", coarse_bits)
+    T, _ = synth.make_hypotheses(3000, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=21, near_fraction=0.05)
+    # poses that put model points just outside every face of the scene's bounding box
+    lo, hi = sc["pos"].min(0), sc["pos"].max(0)
+    ts = []
+    for axis in range(3):
+        for side, edge in ((-1, lo), (1, hi)):
+            for off in (0.0, 0.0049, 0.0051, 0.02):
+                c = (lo + hi) / 2
+                c[axis] = edge[axis] + side * off
+                ts.append(c - mpos.mean(0))
+    ts = np.array(ts, np.float32)
+    extra = synth.to_colmajor16(np.tile(np.eye(3, dtype=np.float32), (len(ts), 1, 1)), ts)
+    T = np.concatenate([T.reshape(-1, 16), extra.reshape(-1, 16)]).reshape(-1, 16)
+    ctx = Context(0)
+    try:
+        _check(ctx, sc, mpos, mnrm, T)
+    finally:
+        ctx.close()
