@@ -400,7 +400,12 @@ def main():
                "ties_resolved_by_kdtree": int(ctx.counters()[1])}
         out["roofline"]["note"] = ("algorithmic bytes follow SURVEY 8(d): 64 B for EVERY (hypothesis, model point) query; "
                                    "the kernel answers most queries from a shared-memory occupancy bitmap and a 16 B brick "
-                                   "record, so achieved/peak above 1 is expected; `traffic` is the measured DRAM bytes per launch")
+                                   "record, so achieved/peak above 1 is expected; `traffic` is the measured DRAM bytes per launch "
+                                   "(ncu), `dram_frac` = traffic / kernel time / peak; the ncu capture puts the L1 data pipe "
+                                   "at 91 % and instruction issue at 80 %: that is the binding limit")
+        if traffic:
+            out["roofline"]["dram_achieved"] = traffic / (kernel_ms_max * 1e-3) / 1e9
+            out["roofline"]["dram_frac"] = out["roofline"]["dram_achieved"] / peak
         if world == 1:
             out["pose_latency"] = pose_latency(lambda: Context(local), not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
