@@ -132,6 +132,37 @@ def cpu_baseline(sc, mpos, mnrm, T, seconds_target=15.0):
                  "single_thread": {"value": n1 / dt1, "unit": UNIT, "sample": f"first {n1} hypotheses, 1 thread, {dt1:.1f} s"}}, (lcp, inl, n)
 
 
+def pose_latency_fixture(ctx, name, label):
+    """GPU-only figures for another of the reference's example scenes (tests/golden/golden_<name>.npz):
+    upload + index, model table, fused pipeline, and scoring-only rate on the fixture's own
+    hypothesis list (a few thousand transforms: the launch-bound regime of the reference CLI)."""
+    path = os.path.join(ROOT, "tests", "golden", f"golden_{name}.npz")
+    if not os.path.exists(path):
+        return None
+    with np.load(path) as z:
+        g = {k: np.ascontiguousarray(z[k]) for k in ("mpos", "mnrm", "spos", "snrm", "scls", "spix", "T", "inliers")}
+    ctx.upload_model(g["mpos"], g["mnrm"])
+    ctx.upload_scene(g["spos"], g["snrm"], g["scls"], g["spix"])
+    tm, tu = [], []
+    for _ in range(5):
+        t0 = time.perf_counter(); ctx.upload_model(g["mpos"], g["mnrm"]); tm.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); ctx.upload_scene(g["spos"], g["snrm"], g["scls"], g["spix"]); tu.append(time.perf_counter() - t0)
+    ctx.run_pipeline(1, 100, 200)
+    tp, res = [], None
+    for seed in range(2, 12):
+        t0 = time.perf_counter(); res = ctx.run_pipeline(seed, 100, 200); tp.append(time.perf_counter() - t0)
+    T = np.ascontiguousarray(g["T"], np.float32)
+    lcp, inl = ctx.score_lcp(T)
+    ts = []
+    for _ in range(10):
+        t0 = time.perf_counter(); ctx.score_lcp(T); ts.append(time.perf_counter() - t0)
+    return {"workload": "%s (|S|=%d, |M|=%d), 100 bases, <=200 sets/base" % (label, len(g["spos"]), len(g["mpos"])),
+            "gpu_ms_per_pose": 1e3 * float(np.median(tp)), "gpu_upload_index_ms": 1e3 * float(np.median(tu)),
+            "gpu_model_table_ms": 1e3 * float(np.median(tm)), "transforms_scored": int(res.n_transforms),
+            "scoring_only_hyp_per_s": len(T) / float(np.median(ts)), "scoring_only_hypotheses": int(len(T)),
+            "scoring_matches_fixture": bool(np.array_equal(inl, g["inliers"]))}
+
+
 def pose_latency(ctx_factory, with_cpu):
     """Secondary BASELINE metric: end-to-end ms per object pose on the reference's YCB example
     (configs[0]): 100 bases -> congruent sets -> <=200 transforms per base -> score -> best, all on
@@ -181,6 +212,12 @@ def pose_latency(ctx_factory, with_cpu):
     except Exception as e:  # cv2 missing or data absent: the headline numbers do not depend on it
         out["gpu_scene_cloud_ms"] = None
         out["scene_cloud_error"] = str(e)[:100]
+    try:  # the other class-mode example of the reference (configs[1] of its README: LINEMOD obj_06)
+        out["linemod"] = pose_latency_fixture(ctx, "linemod", "LINEMOD obj_06 example scene")
+        out["ycb_scoring_only"] = {k: v for k, v in (pose_latency_fixture(ctx, "ycb", "YCB 024_bowl example scene") or {}).items()
+                                   if k.startswith("scoring")}
+    except Exception as e:
+        out["linemod_error"] = str(e)[:100]
     ctx.close()
     if with_cpu:
         import oracle
