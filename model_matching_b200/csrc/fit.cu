@@ -170,6 +170,7 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   if (n_bases <= 0 || max_sets <= 0 || !result) STOCS_FAIL(ctx, STOCS_E_ARG, "run_pipeline: bad argument");
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
+  StageTrace tr(st);
   memset(result, 0, sizeof(*result));
   result->best_index = -1;
   result->best_base = -1;
@@ -188,6 +189,7 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   STOCS_CUDA(ctx, cudaMemcpyAsync(h_inv.data(), d_inv, (size_t)n_bases * 8, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaMemcpyAsync(h_valid.data(), d_valid, (size_t)n_bases, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  tr.mark("pipeline: sample bases");
   // keep the valid bases, in order (base_set of the reference driver)
   std::vector<int> v_ids; std::vector<float> v_inv;
   for (int b = 0; b < n_bases; ++b)
@@ -206,6 +208,7 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   rc = stocs_congruent_device(ctx, nv, d_ids, d_inv, d_quads, quad_off, st);
   if (rc) return rc;
   result->n_congruent_sets = quad_off[nv];
+  tr.mark("pipeline: congruent sets");
   // 3. at most max_sets transforms per base
   std::vector<long long> item_off((size_t)nv + 1, 0);
   for (int b = 0; b < nv; ++b) {
@@ -237,6 +240,7 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   a.base_idx4 = d_ids; a.quads4 = d_quads.as<int>(); a.item_base = d_item_base; a.item_quad = d_item_quad;
   a.Tc = d_Tc; a.Tw = d_Tw; a.ok = d_ok; a.n = n_items;
   fit_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(a);
+  tr.mark("pipeline: select + fit");
   // 4. score + 5. best
   rc = stocs_launch_score(ctx, d_Tc, n_items, d_lcp, d_inl, st, true);
   if (rc) { cleanup(); return rc; }
@@ -250,6 +254,7 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   PL(cudaMemcpyAsync(&bv, d_bv, 4, cudaMemcpyDeviceToHost, st));
   PL(cudaMemcpyAsync(h_ok.data(), d_ok, (size_t)n_items, cudaMemcpyDeviceToHost, st));
   PL(cudaStreamSynchronize(st));
+  tr.mark("pipeline: score + best");
   long long n_ok = 0, rank_of_best = -1;
   for (long long i = 0; i < n_items; ++i) { if (i == bi) rank_of_best = n_ok; n_ok += h_ok[i] ? 1 : 0; }
   result->n_transforms = n_ok;

@@ -15,7 +15,6 @@
 // reproduce the reference's traversal-order tie rule (kdtree.h:416-428).
 #include <cub/device/device_scan.cuh>
 
-#include <chrono>
 #include <thread>
 #include <cstdio>
 #include <algorithm>
@@ -286,21 +285,6 @@ int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4*
     for (int k = 0; k < 6; ++k) h_aabb6[k] = ord2f(haabb[k]);
   return STOCS_OK;
 }
-
-namespace {
-// STOCS_TRACE=1: wall-clock of each stage of the index build on stderr (adds a synchronize per stage)
-struct StageTrace {
-  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
-  StageTrace(cudaStream_t s) : on(getenv("STOCS_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
-  void mark(const char* what) {
-    if (!on) return;
-    cudaStreamSynchronize(st);
-    const auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[stocs trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
-    t0 = t1;
-  }
-};
-}  // namespace
 
 int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   // expects ctx->d_tmp = raw pos3 (S*3 floats)

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -147,3 +150,17 @@ int stocs_launch_backproject(stocs_b200_ctx* ctx, const uint16_t* d_depth, const
                              float* d_xyz, uint32_t* d_rgb, cudaStream_t st);  // backproject.cu
 bool stocs_fmad_selftest(stocs_b200_ctx* ctx);                             // score.cu
 float stocs_angle_threshold_dot();                                         // capi.cu (host)
+
+// STOCS_TRACE=1: wall-clock of each stage of a host-driven sequence on stderr (adds a synchronize
+// per stage, so the total is not the untraced time).
+struct StageTrace {
+  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+  explicit StageTrace(cudaStream_t s) : on(getenv("STOCS_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[stocs trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = t1;
+  }
+};
