@@ -200,8 +200,10 @@ def test_host_call_pinned_and_pageable_buffers_agree(gpu_ctx, small_scene):
     assert (got[0], got[1]) == oracle.best(lcp_s)
 
 
-@pytest.mark.parametrize("scale,coarse_bits", [("0.25", None), ("0.5", "2048"), ("0.75", None), ("1.0", "1024"), ("2.0", None), ("3.7", None)])
-def test_index_geometry_knobs_do_not_change_results(small_scene, scale, coarse_bits, monkeypatch):
+@pytest.mark.parametrize("scale,coarse_bits,max_cells", [("0.25", None, None), ("0.5", "2048", None), ("0.75", None, None),
+                                                         ("1.0", "1024", None), ("2.0", None, None), ("3.7", None, None),
+                                                         ("0.5", None, "1000000")])
+def test_index_geometry_knobs_do_not_change_results(small_scene, scale, coarse_bits, max_cells, monkeypatch):
     """Cell edge (in eps) and coarse-map capacity are tuning knobs of the scene index: apron width,
     padding to whole coarse blocks and the always-empty border block must keep every setting
     bit-identical to the oracle (hypotheses reach up to eps outside the scene's bounding box)."""
@@ -209,6 +211,8 @@ def test_index_geometry_knobs_do_not_change_results(small_scene, scale, coarse_b
     monkeypatch.setenv("STOCS_CELL_SCALE", scale)
     if coarse_bits:
         monkeypatch.setenv("STOCS_COARSE_BITS", coarse_bits)
+    if max_cells:  # the cell edge is enlarged until the grid fits (the fallback for very large scenes)
+        monkeypatch.setenv("STOCS_MAX_CELLS", max_cells)
     T, _ = synth.make_hypotheses(3000, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=21, near_fraction=0.05)
     # poses that put model points just outside every face of the scene's bounding box
     lo, hi = sc["pos"].min(0), sc["pos"].max(0)
