@@ -212,6 +212,28 @@ def pose_latency(ctx_factory, with_cpu):
     except Exception as e:  # cv2 missing or data absent: the headline numbers do not depend on it
         out["gpu_scene_cloud_ms"] = None
         out["scene_cloud_error"] = str(e)[:100]
+    try:  # a1 alone: synthetic 640x480 depth frame, plane at 1 m + 3 boxes + 1 mm noise
+        rng = np.random.Generator(np.random.Philox(1234))
+        z = np.full((480, 640), 1.0)
+        for (r0, r1, c0, c1, zz) in ((100, 220, 80, 240, 0.80), (250, 400, 300, 420, 0.70), (60, 160, 450, 600, 0.85)):
+            z[r0:r1, c0:c1] = zz
+        depth16 = np.clip((z + rng.normal(0, 0.001, z.shape)) * 1000.0, 0, 65535).astype(np.uint16)
+        bgr8 = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+        kk = (572.4114, 325.2611, 573.57043, 242.04899)
+        xyz, _ = ctx.backproject(depth16, bgr8, *kk, 0.001)
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter(); ctx.backproject(depth16, bgr8, *kk, 0.001); ts.append(time.perf_counter() - t0)
+        tb = float(np.median(ts))
+        out["backproject"] = {"frame": "640x480 synthetic (Philox 1234), host buffers in and out", "ms": 1e3 * tb,
+                              "pixels_per_s": 307200 / tb, "algorithmic_GBps": 21 * 307200 / tb / 1e9,
+                              "note": "21 B per pixel (SURVEY 8d); the call is PCIe/launch bound: 1.5 MB in, 4.9 MB out"}
+        if with_cpu:
+            import oracle
+            oxyz, _ = oracle.backproject(depth16, bgr8, *kk, 0.001)
+            out["backproject"]["bit_exact_vs_oracle"] = bool(np.array_equal(xyz.view(np.uint32), np.asarray(oxyz, np.float32).reshape(xyz.shape).view(np.uint32)))
+    except Exception as e:
+        out["backproject_error"] = str(e)[:100]
     try:  # the other class-mode example of the reference (configs[1] of its README: LINEMOD obj_06)
         out["linemod"] = pose_latency_fixture(ctx, "linemod", "LINEMOD obj_06 example scene")
         out["ycb_scoring_only"] = {k: v for k, v in (pose_latency_fixture(ctx, "ycb", "YCB 024_bowl example scene") or {}).items()
