@@ -273,7 +273,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sc, mpos, mnrm, T = workload(0, 200_000)
     est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
-    n = 2500 * cores  # per step; sized so that steps+warmup end within a few minutes
+    n = min(2500 * cores, len(T) // 2)  # per step; sized so that steps+warmup end within a few minutes
     for w in range(args.warmup):
         est.score(T[:n // 4], threads=cores)
     t0 = time.perf_counter()
