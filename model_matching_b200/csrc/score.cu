@@ -5,15 +5,16 @@
 // (include/super4pcs/accelerators/kdtree.h:394-459).
 //
 // One warp per hypothesis, persistent CTAs, dynamic work counter.  Model points live in shared
-// memory (SoA, conflict-free).
+// memory as float4.
 //   Phase A (per block of 256 model points), two loops:
 //     1. the test every point takes: fused affine map "transform o world->grid" (9 FMAs), floor,
+//        block coordinates clamped to the always-empty border block (no bounds test, no branch),
 //        one bit of a multi-resolution occupancy bitmap held in shared memory; survivors (~35 %)
 //        are compacted, in model-point order, into a per-warp byte list;
-//     2. survivors only, 32 at a time: ONE 16-byte brick record of the eps-dilated voxel grid
-//        (64-bit occupancy mask + rank base); lanes whose cell is occupied are compacted (ballot +
-//        popc rank) into a per-warp shared-memory queue that runs ACROSS rounds, in model-point
-//        order.
+//     2. survivors only, 32 at a time: one bit of the per-brick bitmap, then -- occupied bricks
+//        only -- ONE 16-byte brick record of the eps-dilated voxel grid (64-bit occupancy mask +
+//        rank base); lanes whose cell is occupied are compacted (ballot + popc rank) into a
+//        per-warp shared-memory queue that runs ACROSS rounds, in model-point order.
 //   Phase B (queue more than half full, or end of the model), 32 queued queries at a time, one
 //     per "owner" lane: (1) owners fetch their candidate-list offsets and compute the exact
 //     transformed point; (2) the 32 candidate lists are swept as ONE flat list, 32 consecutive
