@@ -149,7 +149,7 @@ class PPFMap:
         self.h = lib().orc_ppfmap_build(self.mpos, self.mnrm, self.mpos.shape[0], tr, rot)
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:  # module globals may be gone at interpreter exit
             lib().orc_ppfmap_free(self.h)
             self.h = None
 
@@ -192,7 +192,7 @@ class Estimator:
                                       distance_threshold, tr, rot)
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:  # module globals may be gone at interpreter exit
             lib().orc_est_free(self.h)
             self.h = None
 
