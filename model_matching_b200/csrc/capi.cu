@@ -316,7 +316,7 @@ int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float
   // geometrically (H/8, H/8, H/4, H/2) so that scoring starts early and most of the work runs in
   // large launches.  Consecutive chunks alternate between two compute streams, each launch with
   // its own work counter, so the CTAs of chunk k+1 move in as the straggler warps of chunk k
-  // retire (a launch's tail is ~0.2 ms on the S1 workload); each chunk's results go back on its
+  // retire (a launch's tail is 0.1-0.2 ms on the S1 workload); each chunk's results go back on its
   // own stream right behind its kernel.
   std::vector<int64_t> bounds;
   int nequal = 0;
