@@ -263,6 +263,34 @@ def pose_latency(ctx_factory, with_cpu):
     return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs: pin this process to the CPUs next to its GPU (sysfs local_cpulist of the
+    PCI device) so that the pinned host buffers the kernels read in place are allocated on that
+    NUMA node.  Best effort: returns the CPU list used, or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        devid = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, devid)
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation (oracle port; the reference
     itself cannot be compiled here: no Eigen/PCL/OpenCV/Boost) on all host cores."""
@@ -319,6 +347,7 @@ def main():
         raise SystemExit("bench.py needs a B200: libstocs_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version / debug lines to stdout by default; stdout carries the JSON line.
@@ -449,7 +478,7 @@ def main():
                        "steps": e2e_steps, "best_index": int(best[0]), "best_lcp": float(best[1]),
                        "input_path": "pinned host transforms read in place by the kernel over PCIe (zero-copy), "
                                      "results copied back with cudaMemcpyAsync",
-                       "staged_copy_value": e2e_staged},
+                       "staged_copy_value": e2e_staged, "numa_cpus": numa},
                "gpu_launches": args.steps * 3,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
