@@ -67,6 +67,8 @@ out = [f"# per-kernel totals from profiles/{tag}_launches.csv (ncu gpu__time_dur
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:20]:
     out.append(f"{k:54s} n={v[0]:4d} total_ms={v[1] / 1e6:10.3f} share={v[1] / tot:.4f}")
 open(f"profiles/{tag}_launch_shares.txt", "w").write("\n".join(out) + "\n")
-shutil.copy(bench, f"profiles/{tag}_bench_n1.json")
+import os
+if os.path.abspath(bench) != os.path.abspath(f"profiles/{tag}_bench_n1.json"):
+    shutil.copy(bench, f"profiles/{tag}_bench_n1.json")
 print("\n".join(lines[-14:]))
 print("\n".join(out[:12]))
