@@ -66,6 +66,18 @@ out = [f"# per-kernel totals from profiles/{tag}_launches.csv (ncu gpu__time_dur
        "# pipeline, hence the other kernels and the short score_lcp_kernel launches."]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:20]:
     out.append(f"{k:54s} n={v[0]:4d} total_ms={v[1] / 1e6:10.3f} share={v[1] / tot:.4f}")
+# share of the dominant kernel inside ONE bench step (score 10^6 hypotheses + top-32 reduction)
+big = [num(r[mv]) for r in rows[hi + 1:] if len(r) > mv and "score_lcp_kernel" in r[kn] and num(r[mv]) > 1.5e6]
+tp = [num(r[mv]) for r in rows[hi + 1:] if len(r) > mv and "topk_partial_kernel" in r[kn]]
+tm = [num(r[mv]) for r in rows[hi + 1:] if len(r) > mv and "topk_merge_kernel" in r[kn]]
+if big and tp and tm:
+    mean = lambda v: sum(v) / len(v)
+    step = mean(big) + mean(tp) + mean(tm)
+    bj = json.load(open(bench))
+    out.append("# one bench step = score_lcp_kernel (10^6 hypotheses) + topk_partial + topk_merge:")
+    out.append(f"#   ncu: {mean(big) / 1e6:.3f} + {mean(tp) / 1e6:.3f} + {mean(tm) / 1e6:.3f} ms -> score share {mean(big) / step:.3f}")
+    out.append(f"#   bench.py (CUDA events): kernel_ms {bj['roofline']['kernel_ms']:.3f} of ms_per_step {bj['ms_per_step']:.3f}"
+               f" -> share {bj['roofline']['kernel_ms'] / bj['ms_per_step']:.3f}")
 open(f"profiles/{tag}_launch_shares.txt", "w").write("\n".join(out) + "\n")
 import os
 if os.path.abspath(bench) != os.path.abspath(f"profiles/{tag}_bench_n1.json"):
