@@ -2,11 +2,13 @@
 """bench.py -- hypotheses scored / second on the synthetic S1 workload (BASELINE.json configs[3]).
 
 One "step" = one pass of the hot path over one batch: score H = 10^6 rigid-transform hypotheses
-(|M| = 512 model points each) against the 1,048,576-point scene, then the best-pose / top-K
-reduction (and, for N > 1, the single NCCL all-gather of the per-rank top-K records).
-Weak scaling: every rank holds a replica of the scene index and scores its own 10^6 hypotheses.
+(|M| = 512 model points each) against the 1,048,576-point scene and reduce them to the K = 32 best
+64-byte records.  With N > 1 GPUs the 10^6 hypotheses are SHARDED (strong scaling, the named
+config): every rank holds a replica of the scene index, scores ceil(H/N) hypotheses, and ONE
+ncclAllGather + a device merge give every rank the global top-K -- all inside the C ABI call
+stocs_b200_score_sharded_device.  The weak-scaling figure (10^6 per GPU) is reported under `extra`.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload s1|s2]
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is produced.
 """
@@ -27,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 N_SCENE = 1 << 20
 N_MODEL = 512
-H_PER_GPU = 1_000_000
+H_TOTAL = 1_000_000
 TOPK = 32
 METRIC = "hypotheses_scored_per_second"
 UNIT = "hypotheses/s"
@@ -291,6 +293,27 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
+WORKLOAD_S1 = "S1: 1,048,576-point synthetic scene, |M|=512, 1e6 hypotheses (1% near-truth), hypothesis-sharded over the GPUs"
+WORKLOAD_S2 = "S2: 8 models (|M| 384..1024) x 1e7 hypotheses each, 1,048,576-point scene with per-object class maps, hypothesis-sharded"
+S2_MODEL_POINTS = (384, 448, 512, 576, 640, 768, 896, 1024)
+S2_H_PER_OBJECT = 10_000_000
+
+
+def s1_config(world, H=H_TOTAL):
+    """The `config` object of the S1 line -- identical in the b200 and the reference arm."""
+    return {"workload": WORKLOAD_S1, "scene_points": N_SCENE, "model_points": N_MODEL, "hypotheses": H,
+            "hypotheses_per_gpu": -(-H // world),
+            "parallelism": f"hypothesis-sharded x{world}, replicated scene index, one all-gather of top-{TOPK} 64-byte records",
+            "l2": "inputs larger than L2 (64 MB of transforms per 1e6 hypotheses + ~1.7 GB scene index)"}
+
+
+def s2_config(world):
+    return {"workload": WORKLOAD_S2, "scene_points": N_SCENE, "model_points": list(S2_MODEL_POINTS),
+            "hypotheses": 8 * S2_H_PER_OBJECT, "hypotheses_per_gpu": 8 * -(-S2_H_PER_OBJECT // world),
+            "parallelism": f"every object hypothesis-sharded x{world}, one all-gather of top-{TOPK} records per object",
+            "l2": "inputs larger than L2"}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation (oracle port; the reference
     itself cannot be compiled here: no Eigen/PCL/OpenCV/Boost) on all host cores."""
@@ -298,29 +321,99 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
+    from model_matching_b200 import synth
     cores = os.cpu_count() or 1
-    sc, mpos, mnrm, T = workload(0, 200_000)
-    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
-    n = min(2500 * cores, len(T) // 2)  # per step; sized so that steps+warmup end within a few minutes
-    for w in range(args.warmup):
-        est.score(T[:n // 4], threads=cores)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        off = (k * n) % (len(T) - n)
-        est.score(T[off:off + n], threads=cores)
-    dt = time.perf_counter() - t0
-    v = n * args.steps / dt
+    if args.workload == "s2":
+        sc = synth.make_scene(n_points=N_SCENE, seed=1234)
+        ests, Ts = [], []
+        for k, m in enumerate(S2_MODEL_POINTS[:2]):   # bounded: two of the eight objects
+            mpos, mnrm = synth.make_model(m)
+            cls = synth.class_map(len(sc["pos"]), 1000 + k)
+            T, _ = synth.make_hypotheses(20000, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=1000 + k)
+            ests.append(oracle.Estimator(sc["pos"], sc["nrm"], cls, mpos, mnrm)); Ts.append(T)
+        n = min(1000 * cores, 10000)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for e, T in zip(ests, Ts):
+                e.score(T[:n], threads=cores)
+        dt = time.perf_counter() - t0
+        v = n * len(ests) * args.steps / dt
+        cfg, sample = s2_config(args.gpus), f"{n} hypotheses of each of 2 of the 8 objects per step, {cores} threads"
+    else:
+        sc, mpos, mnrm, T = workload(0, 200_000)
+        est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+        n = min(2500 * cores, len(T) // 2)  # per step; sized so that steps+warmup end within a few minutes
+        for w in range(args.warmup):
+            est.score(T[:n // 4], threads=cores)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            off = (k * n) % (len(T) - n)
+            est.score(T[off:off + n], threads=cores)
+        dt = time.perf_counter() - t0
+        v = n * args.steps / dt
+        cfg, sample = s1_config(args.gpus), f"{n} hypotheses per step ({args.steps} steps) of the S1 list, {cores} threads"
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic",
-           "config": {"workload": "S1: 1,048,576-point synthetic scene, |M|=512, 1e6 hypotheses/GPU (1% near-truth)",
-                      "scene_points": N_SCENE, "model_points": N_MODEL, "hypotheses_per_gpu": H_PER_GPU},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{n} hypotheses per step ({args.steps} steps) of the S1 workload, {cores} threads"},
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
+
+
+def source_stamp():
+    """sha256 over the sources that define the scoring kernel and the index it reads: an ncu capture
+    (profiles/score_kernel_traffic.json) is only quoted when it was taken on these sources."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("score.cu", "scene_index.cu", "stocs_ctx.h", "stocs_math.h"):
+        h.update(open(os.path.join(ROOT, "model_matching_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def fitted_hypotheses(ctx, H, seed=20260, max_sets=2000, batch=256, budget_s=90.0):
+    """H hypotheses as StoCS produces them (src/stocs.cpp:871-941): bases sampled on the uploaded
+    scene, congruent sets on the model, one 3-point fit per (base, quad) -- every transform lands
+    the model on scene surface.  Uses the repo's own GPU stages; not timed."""
+    out, n, base_no, nb_valid, t0 = [], 0, 0, 0, time.time()
+    while n < H and time.time() - t0 < budget_s:
+        ids, inv, valid = ctx.sample_bases(seed, base_no, batch)
+        base_no += batch
+        ids, inv = ids[valid], inv[valid]
+        if len(ids) == 0:
+            continue
+        quads, offs = ctx.find_congruent(ids, inv, cap=1 << 22)
+        cnt = np.diff(offs)
+        take = np.minimum(cnt, max_sets)
+        tot = int(take.sum())
+        if tot == 0:
+            continue
+        b = np.repeat(np.arange(len(ids)), take)
+        k = np.arange(tot) - np.repeat(np.cumsum(take) - take, take)
+        src = np.where(cnt[b] < max_sets, k, (k * cnt[b]) // max_sets)   # the CLI's even spread
+        Tc, _, ok = ctx.fit_transforms(ids[b], quads[offs[b] + src])
+        out.append(Tc[ok]); n += int(ok.sum()); nb_valid += len(ids)
+    if not out:
+        return None, {}
+    T = np.concatenate(out)
+    info = {"unique": int(min(len(T), H)), "bases_sampled": base_no, "bases_valid": nb_valid, "max_sets": max_sets,
+            "generation_s": round(time.time() - t0, 1)}
+    if len(T) < H:   # generation budget exhausted: repeat what there is (stated in the line)
+        T = np.concatenate([T] * (-(-H // len(T))))
+    return np.ascontiguousarray(T[:H], np.float32), info
+
+
+def counter_bytes(c):
+    """Data-dependent byte figures from the kernel's exact work counters.
+    survey: SURVEY 8(d)'s formula 32 B per query + 16 B per candidate examined + 16 B per hit.
+    kernel_min: what THIS kernel must fetch from beyond shared memory: transform in / results out,
+    4 B of brick bitmap per coarse survivor, 16 B per brick record, 8 B of offsets per queued query,
+    16 B per candidate examined, 16 B of scene attributes + 16 B of model normal per hit."""
+    survey = 32 * c["queries"] + 16 * c["candidates"] + 16 * c["hits"]
+    kmin = (56 * c["hypotheses"] + 4 * c["coarse_survivors"] + 16 * c["brick_records"] + 8 * c["queued"]
+            + 16 * c["candidates"] + 32 * c["hits"])
+    return survey, kmin
 
 
 def main():
@@ -329,8 +422,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--hyp", type=int, default=H_PER_GPU, help="hypotheses per GPU (default: the named config)")
+    ap.add_argument("--workload", default="s1", choices=["s1", "s2"])
+    ap.add_argument("--hyp", type=int, default=H_TOTAL, help="hypotheses in the list (default: the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip S1-fit, weak scaling and pose latency")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -338,7 +433,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from model_matching_b200 import Context
+    import model_matching_b200 as mm
+    from model_matching_b200 import Context, RECORD, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -351,106 +447,153 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version / debug lines to stdout by default; stdout carries the JSON line.
-        # (NCCL_DEBUG_FILE is honoured only above level VERSION, so VERSION is raised to WARN.)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    H = args.hyp
-    warm = max(args.warmup, 3)
+        dist.init_process_group("nccl", device_id=dev)   # plumbing: barrier, max-over-ranks, id broadcast
 
-    sc, mpos, mnrm, T = workload(rank, H)
-    ctx = Context(local)
-    ctx.upload_model(mpos, mnrm)
-    ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    def new_comm(ctx):
+        """library-level communicator: rank 0 makes the NCCL id, torch.distributed only carries it"""
+        if world == 1:
+            return
+        box = [mm.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
 
-    # a dedicated (non-default) stream: the C ABI treats a NULL stream as "the context's own"
-    stream = torch.cuda.Stream(dev)
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    stream = torch.cuda.Stream(dev)   # a dedicated (non-default) stream: NULL means "the context's own" to the ABI
     torch.cuda.set_stream(stream)
     sptr = ctypes.c_void_p(stream.cuda_stream)
-    dT = torch.from_numpy(T).to(dev)
-    dlcp = torch.empty(H, dtype=torch.float32, device=dev)
-    dinl = torch.empty(H, dtype=torch.int32, device=dev)
-    dtop_i = torch.empty(TOPK, dtype=torch.int64, device=dev)
-    dtop_v = torch.empty(TOPK, dtype=torch.float32, device=dev)
-    gather_i = torch.empty(world * TOPK, dtype=torch.int64, device=dev) if world > 1 else None
-    gather_v = torch.empty(world * TOPK, dtype=torch.float32, device=dev) if world > 1 else None
+    warm = max(args.warmup, 3)
 
-    def step(ev=None):
-        if ev is not None:
-            ev[0].record(stream)
-        ctx.score_lcp_device(dT.data_ptr(), H, dlcp.data_ptr(), dinl.data_ptr(), sptr)
-        if ev is not None:
-            ev[1].record(stream)
-        ctx.reduce_best_device(dlcp.data_ptr(), H, TOPK, rank * H, dtop_i.data_ptr(), dtop_v.data_ptr(), sptr)
-        if world > 1:  # the path's one collective: all-gather of K (index, lcp) records per rank
-            dist.all_gather_into_tensor(gather_i, dtop_i)
-            dist.all_gather_into_tensor(gather_v, dtop_v)
+    def timed_steps(step, steps, ctxs):
+        """warm-up, then `steps` steps between barriers; -> (ms total max over ranks, mean kernel ms max over ranks)"""
+        for _ in range(warm):
+            step()
+        barrier()
+        for c in ctxs:
+            c.kernel_ms_stats(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        t_end = time.time()
+        kms = float(np.sum([c.kernel_ms_stats()[1] for c in ctxs]))   # per step: one launch per context
+        ms_total, kms = max_over_ranks(e0.elapsed_time(e1), kms)
+        return ms_total, kms, t_begin, t_end
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         sampler.wait_first_sample()
-    for _ in range(warm):
-        step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
 
-    t_begin = time.time()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for k in range(args.steps):
-        step(kev[k])
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    clocks = sampler.stop(t_begin, time.time()) if sampler else None
-    ms_total = e0.elapsed_time(e1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, kernel_ms_max = float(t[0]), float(t[1])
-    value = world * H * args.steps / (ms_total * 1e-3)
+    if args.workload == "s2":
+        run_s2(args, locals())
+        return
 
-    # ---- e2e: the drop-in host-buffer call (pinned host memory in, results out), every step
-    hT = torch.from_numpy(T).pin_memory()
-    hlcp = torch.empty(H, dtype=torch.float32).pin_memory()
-    hinl = torch.empty(H, dtype=torch.int32).pin_memory()
+    # ---------------------------------------------------------------- S1, strong scaling (the named config)
+    H = args.hyp
+    sc, mpos, mnrm, T = workload(0, H)            # every rank builds the same list and takes its block
+    lo, hi = mm.shard_range(H, rank, world)
+    Hl = hi - lo
+    ctx = Context(local)
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    new_comm(ctx)
+    dT = torch.from_numpy(T[lo:hi]).to(dev)
+    drec = torch.zeros(TOPK * 64, dtype=torch.uint8, device=dev)
+
+    def step():
+        ctx.score_sharded_device(dT.data_ptr(), Hl, lo, TOPK, drec.data_ptr(), sptr)
+
+    ms_total, kernel_ms, t_begin, t_end = timed_steps(step, args.steps, [ctx])
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    value = H * args.steps / (ms_total * 1e-3)
+    rec = drec.cpu().numpy().view(RECORD).copy()
+
+    # ---- merged result == single-GPU result of the whole list (asserted on every run)
+    dTf = torch.from_numpy(T).to(dev) if world > 1 else dT
+    dlcp = torch.empty(H, dtype=torch.float32, device=dev)
+    dinl = torch.empty(H, dtype=torch.int32, device=dev)
+    dti = torch.empty(TOPK, dtype=torch.int64, device=dev)
+    dtv = torch.empty(TOPK, dtype=torch.float32, device=dev)
+    ctx.score_lcp_device(dTf.data_ptr(), H, dlcp.data_ptr(), dinl.data_ptr(), sptr)
+    ctx.reduce_best_device(dlcp.data_ptr(), H, TOPK, 0, dti.data_ptr(), dtv.data_ptr(), sptr)
+    torch.cuda.synchronize(dev)
+    ti, tv, inl_full = dti.cpu().numpy(), dtv.cpu().numpy(), dinl.cpu().numpy()
+    live = ti >= 0
+    T34 = T.reshape(-1, 4, 4).transpose(0, 2, 1)[:, :3, :].reshape(-1, 12)
+    merge_ok = bool(np.array_equal(rec["index"], ti) and np.array_equal(rec["lcp"].view(np.uint32), tv.view(np.uint32))
+                    and np.array_equal(rec["inliers"][live], inl_full[ti[live]])
+                    and np.array_equal(rec["T"][live].view(np.uint32), T34[ti[live]].view(np.uint32)))
+    if world > 1:   # every rank must hold the same merged records
+        allrec = [None] * world
+        dist.all_gather_object(allrec, rec.tobytes())
+        merge_ok = merge_ok and all(b == allrec[0] for b in allrec)
+    if not merge_ok:
+        raise SystemExit(f"rank {rank}: merged top-{TOPK} differs from the single-GPU result of the whole list")
+    del dTf
+
+    # ---- e2e: the host-buffer call (pinned host memory in, records + per-hypothesis results out)
+    hT = torch.from_numpy(T[lo:hi]).pin_memory()
+    hlcp = torch.empty(Hl, dtype=torch.float32).pin_memory()
+    hinl = torch.empty(Hl, dtype=torch.int32).pin_memory()
+    hrec = np.zeros(TOPK, RECORD)
     e2e_steps = max(1, min(args.steps, 20))
 
-    def e2e_step():
-        ctx.score_lcp_ptr(hT.data_ptr(), H, hlcp.data_ptr(), hinl.data_ptr())
-        return ctx.reduce_best(None, K=TOPK)
+    def e2e_step(hT=hT, n=Hl, off=lo):
+        ctx.score_sharded_ptr(hT.data_ptr(), n, off, TOPK, hrec, hlcp.data_ptr(), hinl.data_ptr())
 
-    def e2e_measure():
-        e2e_step()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
+    def e2e_measure(stepfn, Htot):
+        stepfn()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            b = e2e_step()
+            stepfn()
         torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        return world * H * e2e_steps / float(te[0]), b
+        dt, = max_over_ranks(time.perf_counter() - t0)
+        return Htot * e2e_steps / dt
 
-    # headline: the kernel reads the page-locked transforms in place over PCIe (64 B per hypothesis
-    # cross the bus inside the timed region, no staging copy); second figure: the same call with
-    # the transforms staged through HBM by chunked cudaMemcpyAsync (what pageable callers get)
-    e2e_value, best = e2e_measure()
+    e2e_value = e2e_measure(e2e_step, H)
+    e2e_rec = hrec.copy()
     os.environ["STOCS_NO_ZERO_COPY"] = "1"
-    e2e_staged, best_staged = e2e_measure()
+    e2e_staged = e2e_measure(e2e_step, H)
     del os.environ["STOCS_NO_ZERO_COPY"]
-    assert best_staged[0] == best[0] and best_staged[1] == best[1]
+    if not (np.array_equal(e2e_rec["index"], rec["index"]) and np.array_equal(hrec["index"], rec["index"])):
+        raise SystemExit("e2e records differ from the device-resident run")
+
+    # ---- weak scaling (N > 1): 1e6 hypotheses PER GPU
+    extra = {}
+    if world > 1 and not args.no_extras:
+        Tw, _ = synth.make_hypotheses(H, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=4321 + rank)
+        dTw = torch.from_numpy(Tw).to(dev)
+        wsteps = max(1, min(args.steps, 50))
+
+        def wstep():
+            ctx.score_sharded_device(dTw.data_ptr(), H, rank * H, TOPK, drec.data_ptr(), sptr)
+
+        wms, wk, _, _ = timed_steps(wstep, wsteps, [ctx])
+        hTw = torch.from_numpy(Tw).pin_memory()
+        hlcp = torch.empty(H, dtype=torch.float32).pin_memory()
+        hinl = torch.empty(H, dtype=torch.int32).pin_memory()
+        we2e = e2e_measure(lambda: e2e_step(hTw, H, rank * H), world * H)
+        extra["weak"] = {"workload": "1e6 hypotheses per GPU (round-1 configuration)", "value": world * H * wsteps / (wms * 1e-3),
+                         "ms_per_step": wms / wsteps, "steps": wsteps, "kernel_ms": wk, "e2e_value": we2e, "scaling": "weak"}
+        del dTw, hTw
 
     if rank == 0:
         M = N_MODEL
@@ -460,41 +603,59 @@ def main():
             peaks = json.load(open(pk))
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        alg_bytes = H * algorithmic_bytes_per_hypothesis(M)
-        achieved = alg_bytes / (kernel_ms_max * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        stamp = source_stamp()
+
+        def roofline_of(kms, n_hyp, counters, traffic_key):
+            alg = n_hyp * algorithmic_bytes_per_hypothesis(M)
+            r = {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                 "kernel": "score_lcp_kernel", "kernel_ms": kms, "hypotheses_per_launch": n_hyp,
+                 "algorithmic_bytes_per_launch": alg, "peak_source": peak_src, "traffic": None}
+            r["frac"] = r["achieved"] / peak
+            if counters:
+                survey, kmin = counter_bytes(counters)
+                r["counters"] = counters
+                r["data_bytes_per_launch"] = survey
+                r["frac_data"] = survey / (kms * 1e-3) / 1e9 / peak
+                r["kernel_min_bytes_per_launch"] = kmin
+                r["frac_kernel_min"] = kmin / (kms * 1e-3) / 1e9 / peak
+            tp = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
+            if os.path.exists(tp):
+                t = json.load(open(tp)).get(traffic_key)
+                if t and t.get("hypotheses_per_launch") == n_hyp:
+                    r["traffic"] = t["dram_bytes_per_launch"]
+                    r["traffic_capture"] = {k: t.get(k) for k in ("source_stamp", "workload", "captured", "file")}
+                    r["traffic_capture"]["current_source_stamp"] = stamp
+                    r["traffic_capture"]["stale"] = t.get("source_stamp") != stamp
+                    r["dram_achieved"] = r["traffic"] / (kms * 1e-3) / 1e9
+                    r["dram_frac"] = r["dram_achieved"] / peak
+            return r
+
+        cnt = ctx.score_counters(dT.data_ptr(), Hl)
+        roof = roofline_of(kernel_ms, Hl, cnt, "s1")
+        roof["note"] = ("frac: contract accounting of SURVEY 8(d), 64 B for EVERY (hypothesis, model point) query -- not a "
+                        "physical fraction (the kernel answers most queries from an on-chip occupancy map); frac_data: "
+                        "SURVEY 8(d)'s data-dependent counter 32 B/query + 16 B/candidate examined + 16 B/hit from the kernel's "
+                        "exact work counters; frac_kernel_min: bytes this kernel must fetch from beyond shared memory; "
+                        "dram_frac: DRAM bytes of the committed ncu capture (stamped) over the live kernel time")
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "S1: 1,048,576-point synthetic scene, |M|=512, 1e6 hypotheses/GPU (1% near-truth)",
-                          "scene_points": N_SCENE, "model_points": M, "hypotheses_per_gpu": H,
-                          "parallelism": f"hypothesis-sharded x{world}, replicated scene index, one all-gather of top-{TOPK}",
-                          "l2": "inputs larger than L2 (64 MB transforms + ~%d MB scene index per step)" % int(
-                              (ctx.counters()[3] * 16 + ctx.counters()[2] * 4 + N_SCENE * 16) / 1e6)},
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": H * 64, "d2h_bytes_per_step": H * 8,
-                       "steps": e2e_steps, "best_index": int(best[0]), "best_lcp": float(best[1]),
-                       "input_path": "pinned host transforms read in place by the kernel over PCIe (zero-copy), "
-                                     "results copied back with cudaMemcpyAsync",
+               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": s1_config(world, H),
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Hl * 64, "d2h_bytes_per_step": Hl * 8 + TOPK * 64,
+                       "bytes_note": "per rank", "steps": e2e_steps, "best_index": int(rec["index"][0]), "best_lcp": float(rec["lcp"][0]),
+                       "input_path": "pinned host transforms read in place by the kernel over PCIe (zero-copy); per-hypothesis "
+                                     "lcp + inlier counts and the merged top-K records copied back",
                        "staged_copy_value": e2e_staged, "numa_cpus": numa},
-               "gpu_launches": args.steps * 3,
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                            "kernel": "score_lcp_kernel", "kernel_ms": kernel_ms_max,
-                            "algorithmic_bytes_per_launch": alg_bytes},
-               "clocks": clocks,
-               "ties_resolved_by_kdtree": int(ctx.counters()[1])}
-        out["roofline"]["note"] = ("algorithmic bytes follow SURVEY 8(d): 64 B for EVERY (hypothesis, model point) query; "
-                                   "the kernel answers most queries from a shared-memory occupancy bitmap and a 16 B brick "
-                                   "record, so achieved/peak above 1 is expected; `traffic` is the measured DRAM bytes per launch "
-                                   "(ncu), `dram_frac` = traffic / kernel time / peak; the ncu capture puts the L1 data pipe "
-                                   "at 91 % and instruction issue at 80 %: that is the binding limit")
-        if traffic:
-            out["roofline"]["dram_achieved"] = traffic / (kernel_ms_max * 1e-3) / 1e9
-            out["roofline"]["dram_frac"] = out["roofline"]["dram_achieved"] / peak
-        if world == 1:
+               "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+               "collectives_per_step": 1 if world > 1 else 0,
+               "merge_check": {"merged_topk_equals_single_gpu_topk_of_whole_list": merge_ok, "ranks_agree": True, "K": TOPK},
+               "roofline": roof, "clocks": clocks, "ties_resolved_by_kdtree": int(ctx.counters()[1]), "extra": extra}
+        if world == 1 and not args.no_extras:
+            try:
+                extra["s1_fit"] = s1_fit(ctx, H, stream, sptr, dev, timed_steps, e2e_measure, roofline_of, min(args.steps, 50),
+                                         sc, mpos, mnrm, not args.no_cpu_baseline)
+            except Exception as e:  # the headline does not depend on it
+                extra["s1_fit"] = {"error": str(e)[:300]}
             out["pose_latency"] = pose_latency(lambda: Context(local), not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             est, cb, (olcp, oinl, n) = cpu_baseline(sc, mpos, mnrm, T)
@@ -503,7 +664,121 @@ def main():
             glcp, ginl = hlcp.numpy()[:n], hinl.numpy()[:n]
             out["parity"] = {"checked": int(n), "inliers_equal": bool(np.array_equal(ginl, oinl)),
                              "lcp_bits_equal": bool(np.array_equal(glcp.view(np.uint32), olcp.view(np.uint32)))}
+            # the same data-dependent counter on the reference's own structure (kd-tree), same prefix
+            npre = min(n, 20000)
+            oc = est.score_counters(T[:npre], threads=os.cpu_count() or 1)
+            gc = ctx.score_counters(dT.data_ptr(), npre)
+            out["roofline"]["oracle_counter"] = {"prefix": npre, "kdtree": oc, "grid_hits": gc["hits"], "grid_inliers": gc["inliers"],
+                                                 "grid_candidates": gc["candidates"],
+                                                 "hits_equal": oc["hits"] == gc["hits"], "inliers_equal": oc["inliers"] == gc["inliers"],
+                                                 "kdtree_bytes_per_query": oc["bytes"] / oc["queries"],
+                                                 "grid_bytes_per_query": counter_bytes(gc)[0] / gc["queries"]}
         print(json.dumps(out), flush=True)
+    barrier()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def s1_fit(ctx, H, stream, sptr, dev, timed_steps, e2e_measure, roofline_of, steps, sc, mpos, mnrm, with_cpu):
+    """Second named workload: 1e6 hypotheses produced by the repo's own pipeline on the S1 scene --
+    every one a 3-point fit onto scene surface, as src/stocs.cpp:871-941 produces them."""
+    import torch
+    from model_matching_b200 import RECORD
+    T, info = fitted_hypotheses(ctx, H)
+    if T is None:
+        return {"error": "no fitted hypotheses (no valid base)"}
+    dT = torch.from_numpy(T).to(dev)
+    drec = torch.zeros(TOPK * 64, dtype=torch.uint8, device=dev)
+
+    def step():
+        ctx.score_sharded_device(dT.data_ptr(), H, 0, TOPK, drec.data_ptr(), sptr)
+
+    ms, kms, _, _ = timed_steps(step, steps, [ctx])
+    hT = torch.from_numpy(T).pin_memory()
+    hlcp = torch.empty(H, dtype=torch.float32).pin_memory()
+    hinl = torch.empty(H, dtype=torch.int32).pin_memory()
+    hrec = np.zeros(TOPK, RECORD)
+    e2e = e2e_measure(lambda: ctx.score_sharded_ptr(hT.data_ptr(), H, 0, TOPK, hrec, hlcp.data_ptr(), hinl.data_ptr()), H)
+    cnt = ctx.score_counters(dT.data_ptr(), H)
+    out = {"workload": "S1-fit: the S1 scene and model, 1e6 hypotheses fitted by the repo's own sampling -> congruent sets -> "
+                       "3-point fit stages (all land the model on scene surface)",
+           "generation": info, "value": H * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "e2e_value": e2e, "roofline": roofline_of(kms, H, cnt, "s1_fit"),
+           "mean_inliers": float(hinl.numpy().mean()), "best_lcp": float(hrec["lcp"][0]),
+           "target_1e8_met": bool(H * steps / (ms * 1e-3) >= 1e8)}
+    if with_cpu:
+        import oracle
+        est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+        n = 4000
+        olcp, oinl = est.score(T[:n], threads=os.cpu_count() or 1)
+        out["parity"] = {"checked": n, "inliers_equal": bool(np.array_equal(hinl.numpy()[:n], oinl)),
+                         "lcp_bits_equal": bool(np.array_equal(hlcp.numpy()[:n].view(np.uint32), olcp.view(np.uint32)))}
+    return out
+
+
+def run_s2(args, env):
+    """BASELINE.json configs[4]: 8 models x 1e7 hypotheses each, every object hypothesis-sharded over
+    the GPUs (balanced, rather than object-per-GPU).  One context per object and rank (the
+    class map, hence the scene attributes, differ per object); one all-gather per object and step."""
+    import torch
+    import torch.distributed as dist
+    import model_matching_b200 as mm
+    from model_matching_b200 import Context, RECORD, synth
+    rank, world, local, dev, stream, sptr = (env[k] for k in ("rank", "world", "local", "dev", "stream", "sptr"))
+    timed_steps, new_comm, sampler, warm = env["timed_steps"], env["new_comm"], env["sampler"], env["warm"]
+    Hobj = args.hyp if args.hyp != H_TOTAL else S2_H_PER_OBJECT
+    sc = synth.make_scene(n_points=N_SCENE, seed=1234)
+    lo, hi = mm.shard_range(Hobj, rank, world)
+    Hl = hi - lo
+    ctxs, dTs, drecs = [], [], []
+    for k, m in enumerate(S2_MODEL_POINTS):
+        mpos, mnrm = synth.make_model(m)
+        c = Context(local)
+        c.upload_model(mpos, mnrm)
+        c.upload_scene(sc["pos"], sc["nrm"], synth.class_map(len(sc["pos"]), 1000 + k))
+        new_comm(c)
+        # each rank generates only its own block (seeded by object and rank)
+        T, _ = synth.make_hypotheses(Hl, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=1000 + k + 100 * rank)
+        ctxs.append(c); dTs.append(torch.from_numpy(T).to(dev))
+        drecs.append(torch.zeros(TOPK * 64, dtype=torch.uint8, device=dev))
+        del T
+
+    def step():
+        for c, dT, dr in zip(ctxs, dTs, drecs):
+            c.score_sharded_device(dT.data_ptr(), Hl, lo, TOPK, dr.data_ptr(), sptr)
+
+    ms_total, kernel_ms, t_begin, t_end = timed_steps(step, args.steps, ctxs)
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    recs = [dr.cpu().numpy().view(RECORD).copy() for dr in drecs]
+    if world > 1:
+        allrec = [None] * world
+        dist.all_gather_object(allrec, b"".join(r.tobytes() for r in recs))
+        if not all(b == allrec[0] for b in allrec):
+            raise SystemExit("S2: ranks disagree on the merged records")
+    if rank == 0:
+        Htot = len(S2_MODEL_POINTS) * Hobj
+        alg = sum(Hl * algorithmic_bytes_per_hypothesis(m) for m in S2_MODEL_POINTS)
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        out = {"metric": METRIC, "value": Htot * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+               "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": s2_config(world),
+               "gpu_launches": args.steps * len(ctxs) * (3 + (1 if world > 1 else 0)),
+               "collectives_per_step": len(ctxs) if world > 1 else 0,
+               "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "score_lcp_kernel",
+                            "kernel_ms": kernel_ms, "note": "sum over the 8 per-object launches of one step; contract accounting (see the S1 line)"},
+               "best_per_object": [{"model_points": m, "index": int(r["index"][0]), "lcp": float(r["lcp"][0]), "inliers": int(r["inliers"][0])}
+                                   for m, r in zip(S2_MODEL_POINTS, recs)],
+               "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    env["barrier"]()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 

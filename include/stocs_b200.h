@@ -30,10 +30,11 @@ enum {
   STOCS_E_CUDA = -2,       /* CUDA runtime error (see last_error) */
   STOCS_E_STATE = -3,      /* call order violated (e.g. score before upload_scene) */
   STOCS_E_NODEVICE = -4,   /* no sm_100 device / driver */
-  STOCS_E_CAPACITY = -5    /* caller-provided output capacity too small */
+  STOCS_E_CAPACITY = -5,   /* caller-provided output capacity too small */
+  STOCS_E_NCCL = -6        /* NCCL missing or failed (see last_error) */
 };
 
-#define STOCS_B200_ABI_VERSION 1
+#define STOCS_B200_ABI_VERSION 2
 int stocs_b200_abi_version(void);
 
 /* One context per GPU (one process per GPU in multi-GPU runs).  device = CUDA ordinal. */
@@ -169,8 +170,9 @@ int stocs_b200_select_above(stocs_b200_ctx* ctx, const float* lcp, int64_t H, fl
  * Host arrays in, xyz triples.  T16_out: accumulated transform (column-major), identity when the
  * first iteration already fails; aligned_pos3 (optional): the moved source, as the reference leaves
  * it in segment_cloud; pairs_per_iteration (optional): max_iterations entries; *converged = 0 when
- * an iteration found fewer than 3 correspondences or a singular system (PCL's "not converged",
- * the reference then leaves offset_transform untouched).  Needs no uploaded model or scene. */
+ * an iteration found fewer than 3 correspondences or a singular system (PCL's "not converged";
+ * the reference then sets offset_transform to identity, src/pose_clustering.cpp:136-139, and so
+ * does the host shim clustering::point_to_plane_icp).  Needs no uploaded model or scene. */
 int stocs_b200_icp_point_to_plane(stocs_b200_ctx* ctx, const float* src_pos3, int n_src,
                                   const float* tgt_pos3, const float* tgt_nrm3, int n_tgt,
                                   int max_iterations, float max_correspondence_distance,
@@ -178,8 +180,9 @@ int stocs_b200_icp_point_to_plane(stocs_b200_ctx* ctx, const float* src_pos3, in
                                   int32_t* iterations_done, int32_t* converged);
 
 /* ---- fused online pipeline (run_stocs_estimation, src/stocs_match_one_object.cpp:79-165) ----
- * sample n_bases bases -> congruent sets -> at most max_sets transforms per base (the first
- * max_sets quads in set order when a base has more; see DESIGN.md on quirk 5) -> score -> best.
+ * sample n_bases bases -> congruent sets -> at most max_sets transforms per base (when a base has
+ * max_sets quads or more: the even spread floor(k * count / max_sets), k = 0..max_sets-1, over its
+ * list in set order; see DESIGN.md on quirk 5) -> score -> best.
  * Everything stays on the device; only the summary comes back.  Outputs may be NULL. */
 typedef struct stocs_b200_pipeline_result {
   int32_t n_valid_bases;
@@ -194,13 +197,87 @@ typedef struct stocs_b200_pipeline_result {
 int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets,
                             stocs_b200_pipeline_result* result);
 
+/* ---- e: multi-GPU, hypothesis sharding -------------------------------
+ * The reference scores its hypotheses in one sequential loop (src/stocs.cpp:990-998); they are
+ * independent, so the list is split into contiguous blocks, one per GPU.  Every GPU holds a replica
+ * of the scene index and model tables (upload_model / upload_scene on each context), scores its
+ * block, keeps its K best as 64-byte records, and ONE ncclAllGather (NVLink / NVSwitch) hands every
+ * rank all nranks*K records; the merge orders them by (lcp descending, global index ascending), so
+ * record 0 is the reference's first strict maximum over the whole list (src/stocs.cpp:994).
+ * NCCL is loaded at run time (dlopen of libnccl.so.2, or $STOCS_NCCL_LIB): contexts that never
+ * call comm_* do not need it.
+ *
+ * One process per GPU: rank 0 calls comm_unique_id, the caller distributes the 128 bytes by any
+ * transport (MPI, torch.distributed, a file), every rank calls comm_init (collective).
+ * One process, several GPUs (what stocs_single uses with STOCS_DEVICES=0,1,..): group_create. */
+typedef struct stocs_b200_record {
+  float lcp;          /* 0 and index -1: empty slot */
+  int32_t inliers;
+  int64_t index;      /* position in the GLOBAL hypothesis list */
+  float T[12];        /* rows 0..2 of the scored (centred) transform, row-major */
+} stocs_b200_record;  /* 64 bytes */
+
+#define STOCS_B200_UNIQUE_ID_BYTES 128
+int stocs_b200_comm_unique_id(void* id128);
+int stocs_b200_comm_init(stocs_b200_ctx* ctx, const void* id128, int rank, int nranks);
+int stocs_b200_comm_destroy(stocs_b200_ctx* ctx);
+/* Block [lo, hi) of ceil(H / nranks) hypotheses owned by `rank`. */
+void stocs_b200_shard_range(int64_t H, int rank, int nranks, int64_t* lo, int64_t* hi);
+
+/* Score the local block (H_local transforms whose first global index is index_offset), reduce it to
+ * the K best (K <= 32), all-gather, merge: d_topk_out receives the K best records of the WHOLE list
+ * on every rank.  Device pointers; runs on `stream` (NULL: the context stream) without
+ * synchronising.  Without comm_init (or nranks 1) the collective is skipped.  Collective call:
+ * every rank must make it, also with H_local == 0. */
+int stocs_b200_score_sharded_device(stocs_b200_ctx* ctx, const float* d_T16_local, int64_t H_local,
+                                    int64_t index_offset, int K, stocs_b200_record* d_topk_out,
+                                    void* stream);
+/* Same with host buffers (page-locked transforms are read in place, pageable ones are staged);
+ * synchronises.  lcp_local / inliers_local (may be NULL) receive the local block's results. */
+int stocs_b200_score_sharded(stocs_b200_ctx* ctx, const float* T16_local, int64_t H_local,
+                             int64_t index_offset, int K, stocs_b200_record* topk_out,
+                             float* lcp_local, int32_t* inliers_local);
+
+/* Single-process group over n_dev devices (create(device_ids, n_dev)).
+ * group_ctx(i) is the context of device i (upload model / scene through group_upload_* or per
+ * context).  group_score_best splits the H host transforms across the devices, scores, gathers and
+ * merges as above; lcp / inliers (may be NULL) receive the full per-hypothesis results. */
+typedef struct stocs_b200_group stocs_b200_group;
+int stocs_b200_group_create(stocs_b200_group** out, const int* device_ids, int n_dev);
+void stocs_b200_group_destroy(stocs_b200_group* g);
+int stocs_b200_group_size(stocs_b200_group* g);
+stocs_b200_ctx* stocs_b200_group_ctx(stocs_b200_group* g, int i);
+const char* stocs_b200_group_last_error(stocs_b200_group* g);
+int stocs_b200_group_set_params(stocs_b200_group* g, float distance_threshold, int ppf_tr_discretization,
+                                int ppf_rot_discretization);
+int stocs_b200_group_upload_model(stocs_b200_group* g, const float* pos3, const float* nrm3, int M);
+int stocs_b200_group_upload_scene(stocs_b200_group* g, const float* pos3, const float* nrm3,
+                                  const float* class_probability, const int32_t* pixel_rc, int S);
+int stocs_b200_group_score_best(stocs_b200_group* g, const float* T16, int64_t H, int K,
+                                stocs_b200_record* topk_out, float* lcp, int32_t* inliers);
+
 /* ---- diagnostics ---------------------------------------------------------------------------
- * counters of the most recent score call: [0] kernels launched, [1] NN queries resolved by the
- * kd-tree tie path, [2] grid cells, [3] replicated candidate records. */
+ * [0] score kernels launched and [1] NN queries resolved by the kd-tree tie path, both accumulated
+ * over the lifetime of the context; [2] grid cells and [3] replicated candidate records of the
+ * current scene index. */
 int stocs_b200_get_counters(stocs_b200_ctx* ctx, int64_t* counters, int n);
+/* Data-dependent work of ONE scoring launch over H device-resident transforms, counted exactly by a
+ * counting instantiation of the scoring kernel (results discarded, not for timing).  counters (up
+ * to 9): [0] NN queries = H*|M|, [1] queries that survive the shared-memory coarse occupancy test,
+ * [2] 16-byte brick records fetched, [3] queries whose grid cell is occupied (queued),
+ * [4] candidate records examined (16 B each), [5] queries with a scene point within the distance
+ * threshold (one 16-byte attribute fetch each), [6] inliers, [7] queue drains, [8] H.
+ * bench.py derives SURVEY.md section 8(d)'s data-dependent byte figure from these. */
+int stocs_b200_score_counters(stocs_b200_ctx* ctx, const float* d_T16, int64_t H, int64_t* counters,
+                              int n);
 /* name + average duration (ms, CUDA events on the context stream) of the dominant kernel of the
  * most recent score call; used by bench.py for the roofline line. */
 int stocs_b200_last_kernel_ms(stocs_b200_ctx* ctx, float* ms);
+/* Mean / max duration (ms) of the scoring kernel over the timed launches since the last reset (at
+ * most the 512 most recent), from CUDA event pairs recorded around each launch on the stream it
+ * ran on.  Synchronises with those launches.  reset != 0 restarts the window. */
+int stocs_b200_kernel_ms_stats(stocs_b200_ctx* ctx, int reset, int32_t* n_launches, float* mean_ms,
+                               float* max_ms);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,12 @@ SYMBOLS = [
     "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device", "stocs_b200_select_above",
     "stocs_b200_icp_point_to_plane",
     "stocs_b200_run_pipeline", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
+    "stocs_b200_score_counters", "stocs_b200_kernel_ms_stats",
+    "stocs_b200_comm_unique_id", "stocs_b200_comm_init", "stocs_b200_comm_destroy", "stocs_b200_shard_range",
+    "stocs_b200_score_sharded_device", "stocs_b200_score_sharded",
+    "stocs_b200_group_create", "stocs_b200_group_destroy", "stocs_b200_group_size", "stocs_b200_group_ctx",
+    "stocs_b200_group_last_error", "stocs_b200_group_set_params", "stocs_b200_group_upload_model",
+    "stocs_b200_group_upload_scene", "stocs_b200_group_score_best",
 ]
 
 
@@ -83,6 +89,27 @@ def lib():
     L.stocs_b200_run_pipeline.argtypes = [vp, u64, i32, i32, C.POINTER(PipelineResult)]
     L.stocs_b200_get_counters.argtypes = [vp, vp, i32]
     L.stocs_b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
+    L.stocs_b200_score_counters.argtypes = [vp, vp, i64, vp, i32]
+    L.stocs_b200_kernel_ms_stats.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
+    L.stocs_b200_comm_unique_id.argtypes = [vp]
+    L.stocs_b200_comm_init.argtypes = [vp, vp, i32, i32]
+    L.stocs_b200_comm_destroy.argtypes = [vp]
+    L.stocs_b200_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.stocs_b200_shard_range.restype = None
+    L.stocs_b200_score_sharded_device.argtypes = [vp, vp, i64, i64, i32, vp, vp]
+    L.stocs_b200_score_sharded.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp]
+    L.stocs_b200_group_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32]
+    L.stocs_b200_group_destroy.argtypes = [vp]
+    L.stocs_b200_group_destroy.restype = None
+    L.stocs_b200_group_size.argtypes = [vp]
+    L.stocs_b200_group_ctx.argtypes = [vp, i32]
+    L.stocs_b200_group_ctx.restype = vp
+    L.stocs_b200_group_last_error.argtypes = [vp]
+    L.stocs_b200_group_last_error.restype = C.c_char_p
+    L.stocs_b200_group_set_params.argtypes = [vp, f32, i32, i32]
+    L.stocs_b200_group_upload_model.argtypes = [vp, vp, vp, i32]
+    L.stocs_b200_group_upload_scene.argtypes = [vp, vp, vp, vp, vp, i32]
+    L.stocs_b200_group_score_best.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     _LIB = L
     return L
 
@@ -94,6 +121,27 @@ def _ptr(a):
 def _f32(a, shape=None):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a if shape is None else a.reshape(shape)
+
+
+# stocs_b200_record (include/stocs_b200.h): the 64-byte unit of the multi-GPU all-gather
+RECORD = np.dtype([("lcp", np.float32), ("inliers", np.int32), ("index", np.int64), ("T", np.float32, (12,))])
+assert RECORD.itemsize == 64
+
+
+def shard_range(H, rank, nranks):
+    """[lo, hi) of ceil(H / nranks) hypotheses owned by `rank` (stocs_b200_shard_range)."""
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    lib().stocs_b200_shard_range(H, rank, nranks, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def comm_unique_id():
+    """128 bytes for Context.comm_init; rank 0 creates them, the caller distributes them."""
+    buf = C.create_string_buffer(128)
+    rc = lib().stocs_b200_comm_unique_id(buf)
+    if rc != 0:
+        raise StocsError(f"stocs_b200_comm_unique_id failed ({rc}): NCCL not loadable")
+    return bytes(buf.raw)
 
 
 class Context:
@@ -321,6 +369,34 @@ class Context:
         self._check(self._L.stocs_b200_reduce_best_device(self.h, dlcp_ptr, H, K, index_offset, didx_ptr,
                                                            dval_ptr, stream))
 
+    # ---- multi-GPU (one process per GPU)
+    def comm_init(self, unique_id, rank, nranks):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._L.stocs_b200_comm_init(self.h, buf, int(rank), int(nranks)))
+
+    def comm_destroy(self):
+        self._check(self._L.stocs_b200_comm_destroy(self.h))
+
+    def score_sharded_device(self, dT_ptr, H_local, index_offset, K, dout_ptr, stream=None):
+        """Device pointers; enqueues score -> local top-K records -> ONE all-gather -> merge."""
+        self._check(self._L.stocs_b200_score_sharded_device(self.h, dT_ptr, H_local, index_offset, K, dout_ptr, stream))
+
+    def score_sharded(self, T_local, index_offset, K=32, want_local=False):
+        """Host buffers -> K best records of the whole list (numpy RECORD array) [, local lcp, inliers]."""
+        T_local = _f32(T_local, (-1, 16))
+        H = T_local.shape[0]
+        out = np.zeros(K, RECORD)
+        lcp = np.empty(H, np.float32) if want_local else None
+        inl = np.empty(H, np.int32) if want_local else None
+        self._check(self._L.stocs_b200_score_sharded(self.h, _ptr(T_local), H, int(index_offset), K, _ptr(out),
+                                                      _ptr(lcp), _ptr(inl)))
+        return (out, lcp, inl) if want_local else out
+
+    def score_sharded_ptr(self, T_ptr, H_local, index_offset, K, out, lcp_ptr=None, inl_ptr=None):
+        """Raw host pointers (e.g. pinned torch tensors); out: RECORD array of K."""
+        self._check(self._L.stocs_b200_score_sharded(self.h, T_ptr, H_local, int(index_offset), K, _ptr(out),
+                                                      lcp_ptr, inl_ptr))
+
     def run_pipeline(self, seed, n_bases=100, max_sets=200):
         r = PipelineResult()
         self._check(self._L.stocs_b200_run_pipeline(self.h, int(seed), n_bases, max_sets, C.byref(r)))
@@ -331,7 +407,90 @@ class Context:
         self._check(self._L.stocs_b200_get_counters(self.h, _ptr(c), 8))
         return c
 
+    SCORE_COUNTER_NAMES = ("queries", "coarse_survivors", "brick_records", "queued", "candidates", "hits",
+                           "inliers", "drains", "hypotheses")
+
+    def score_counters(self, dT_ptr, H):
+        """Exact data-dependent work of one scoring launch (device transforms) -> dict."""
+        c = np.zeros(9, np.int64)
+        self._check(self._L.stocs_b200_score_counters(self.h, dT_ptr, H, _ptr(c), 9))
+        return dict(zip(self.SCORE_COUNTER_NAMES, (int(v) for v in c)))
+
+    def kernel_ms_stats(self, reset=False):
+        """(launches, mean ms, max ms) of the scoring kernel since the last reset (<= 512 launches)."""
+        n, mean, mx = C.c_int32(0), C.c_float(0), C.c_float(0)
+        self._check(self._L.stocs_b200_kernel_ms_stats(self.h, int(reset), C.byref(n), C.byref(mean), C.byref(mx)))
+        return n.value, mean.value, mx.value
+
     def last_kernel_ms(self):
         ms = C.c_float(0)
         self._check(self._L.stocs_b200_last_kernel_ms(self.h, C.byref(ms)))
         return ms.value
+
+
+class _BorrowedContext(Context):
+    """A context owned by a Group (never destroyed from Python)."""
+
+    def __init__(self, handle, device):
+        self._L = lib()
+        self.h = C.c_void_p(handle)
+        self.device = device
+        self.M = self.S = 0
+        self._last_H = 0
+
+    def close(self):
+        self.h = None
+
+
+class Group:
+    """stocs_b200_group: one process driving several GPUs (hypothesis sharding + one all-gather)."""
+
+    def __init__(self, device_ids, distance_threshold=0.005, ppf_tr_discretization=5, ppf_rot_discretization=5):
+        self._L = lib()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        g = C.c_void_p()
+        rc = self._L.stocs_b200_group_create(C.byref(g), ids, len(device_ids))
+        if rc != 0:
+            msg = self._L.stocs_b200_last_error(None)
+            raise StocsError(f"stocs_b200_group_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.g = g
+        self.n = len(device_ids)
+        self._check(self._L.stocs_b200_group_set_params(self.g, distance_threshold, ppf_tr_discretization,
+                                                         ppf_rot_discretization))
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.stocs_b200_group_last_error(self.g)
+            raise StocsError(f"libstocs_b200 group error {rc}: {msg.decode() if msg else ''}")
+
+    def ctx(self, i):
+        return _BorrowedContext(self._L.stocs_b200_group_ctx(self.g, i), i)
+
+    def upload_model(self, pos, nrm):
+        pos, nrm = _f32(pos, (-1, 3)), _f32(nrm, (-1, 3))
+        self._check(self._L.stocs_b200_group_upload_model(self.g, _ptr(pos), _ptr(nrm), pos.shape[0]))
+
+    def upload_scene(self, pos, nrm, cls, pix=None):
+        pos, nrm, cls = _f32(pos, (-1, 3)), _f32(nrm, (-1, 3)), _f32(cls, (-1,))
+        pix = None if pix is None else np.ascontiguousarray(pix, np.int32).reshape(-1, 2)
+        self._check(self._L.stocs_b200_group_upload_scene(self.g, _ptr(pos), _ptr(nrm), _ptr(cls), _ptr(pix), pos.shape[0]))
+
+    def score_best(self, T, K=32, want_all=False):
+        T = _f32(T, (-1, 16))
+        H = T.shape[0]
+        out = np.zeros(K, RECORD)
+        lcp = np.empty(H, np.float32) if want_all else None
+        inl = np.empty(H, np.int32) if want_all else None
+        self._check(self._L.stocs_b200_group_score_best(self.g, _ptr(T), H, K, _ptr(out), _ptr(lcp), _ptr(inl)))
+        return (out, lcp, inl) if want_all else out
+
+    def close(self):
+        if getattr(self, "g", None):
+            self._L.stocs_b200_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

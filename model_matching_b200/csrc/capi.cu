@@ -9,8 +9,6 @@
 
 #include "stocs_ctx.h"
 
-int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
-                      int64_t* d_idx, float* d_val, cudaStream_t st);  // reduce.cu
 int stocs_build_ppf_table(stocs_b200_ctx* ctx);                         // ppf_table.cu
 
 // "acos(d)*180/pi < 30" (src/stocs.cpp:1028-1032) is monotone in d: find the smallest binary32 d
@@ -55,7 +53,6 @@ int stocs_b200_create(stocs_b200_ctx** out, int device) {
   ctx->num_sms = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->join_ev[0], cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->join_ev[1], cudaEventDisableTiming) == cudaSuccess;
@@ -82,6 +79,7 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  stocs_b200_comm_destroy(ctx);
   DevBuf* bufs[] = {&ctx->d_model, &ctx->d_mpos4, &ctx->d_mnrm4, &ctx->d_spos4, &ctx->d_sattr, &ctx->d_spix,
                     &ctx->d_coarse, &ctx->d_brick_occ, &ctx->d_bricks, &ctx->d_cell_start, &ctx->d_cand, &ctx->d_kd_nodes, &ctx->d_kd_pts, &ctx->d_ppf_bin_start,
                     &ctx->d_ppf_pairs, &ctx->d_ppf_keybits, &ctx->d_T, &ctx->d_lcp, &ctx->d_inl, &ctx->d_work,
@@ -90,8 +88,7 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   for (DevBuf& b : ctx->pool) b.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->ev_ring) if (e) cudaEventDestroy(e);
   for (int i = 0; i < stocs_b200_ctx::kMaxChunks; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
   for (int i = 0; i < 2; ++i) if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -189,7 +186,10 @@ int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float*
   if (S > (1 << 27)) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_scene: at most 2^27 scene points are supported");
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  ctx->S = S;
+  // The previous scene is invalid from here on; S is committed only when the new index is complete,
+  // so an early error return cannot leave S > 0 describing buffers that were half replaced.
+  ctx->S = 0;
+  ctx->S_pending = S;
   // attributes: d_tmp = nrm3 | cls
   STOCS_CUDA(ctx, ctx->d_tmp.ensure((size_t)S * 16));
   float* d_n = ctx->d_tmp.as<float>();
@@ -197,7 +197,7 @@ int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float*
   STOCS_CUDA(ctx, cudaMemcpyAsync(d_n, nrm3, (size_t)S * 12, cudaMemcpyHostToDevice, st));
   STOCS_CUDA(ctx, cudaMemcpyAsync(d_c, class_probability, (size_t)S * 4, cudaMemcpyHostToDevice, st));
   int rc = stocs_pack_scene_attr(ctx, d_n, d_c, S);
-  if (rc) return rc;
+  if (rc) { ctx->S_pending = 0; return rc; }
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   STOCS_CUDA(ctx, ctx->d_spix.ensure((size_t)S * 8));
   if (pixel_rc) STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_spix.p, pixel_rc, (size_t)S * 8, cudaMemcpyHostToDevice, st));
@@ -218,7 +218,9 @@ int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float*
   // positions -> centre -> index
   STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp.p, pos3, (size_t)S * 12, cudaMemcpyHostToDevice, st));
   rc = stocs_build_scene_index(ctx);
+  ctx->S_pending = 0;
   if (rc) { ctx->S = 0; return rc; }
+  ctx->S = S;
   return STOCS_OK;
 }
 
@@ -254,7 +256,7 @@ int stocs_b200_score_lcp_device(stocs_b200_ctx* ctx, const float* d_T16, int64_t
 
 // Top-32 of the resident lcp array into the page-locked cache, on stream st (no synchronize).
 static int enqueue_resident_topk(stocs_b200_ctx* ctx, int64_t H, cudaStream_t st) {
-  DevBuf& d_top = ctx->pool[37];
+  DevBuf& d_top = ctx->pool[POOL_TOPK_RESIDENT];
   STOCS_CUDA(ctx, d_top.ensure(32 * 12));
   int64_t* d_idx = d_top.as<int64_t>();
   float* d_val = (float*)(d_idx + 32);
@@ -272,6 +274,7 @@ int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float
   if (H == 0) return STOCS_OK;
   cudaSetDevice(ctx->device);
   ctx->top_valid = false;
+  ctx->last_T_dev = nullptr;
   STOCS_CUDA(ctx, ctx->d_lcp.ensure((size_t)H * 4));
   STOCS_CUDA(ctx, ctx->d_inl.ensure((size_t)H * 4));
   // Page-locked, device-mapped transforms (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch
@@ -290,6 +293,7 @@ int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float
       int rc = stocs_launch_score(ctx, (const float*)pa.devicePointer, H, ctx->d_lcp.as<float>(),
                                   ctx->d_inl.as<int32_t>(), ctx->stream, true);
       if (rc != STOCS_OK) return rc;
+      ctx->last_T_dev = (const float*)pa.devicePointer;
       // the top-32 reduction (what stocs_b200_reduce_best returns for the resident array) runs on
       // the second stream while the copy engine returns the results
       cudaError_t e = cudaEventRecord(ctx->join_ev[0], ctx->stream);
@@ -312,12 +316,14 @@ int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float
   }
   // Pageable transforms are staged through HBM in chunks:
   STOCS_CUDA(ctx, ctx->d_T.ensure((size_t)H * 64));
+  ctx->last_T_dev = ctx->d_T.as<float>();
   // chunked: the H2D copy of chunk k+1 (copy stream) overlaps the scoring of chunk k.  Chunks grow
   // geometrically (H/8, H/8, H/4, H/2) so that scoring starts early and most of the work runs in
   // large launches.  Consecutive chunks alternate between two compute streams, each launch with
   // its own work counter, so the CTAs of chunk k+1 move in as the straggler warps of chunk k
   // retire (a launch's tail is 0.1-0.2 ms on the S1 workload); each chunk's results go back on its
-  // own stream right behind its kernel.
+  // own stream behind its kernel.  (H2D from pageable memory is staged by the driver through its
+  // own pinned buffer and returns early; D2H into pageable memory does not -- see below.)
   std::vector<int64_t> bounds;
   int nequal = 0;
   if (const char* e = getenv("STOCS_SCORE_CHUNKS")) nequal = atoi(e);
@@ -351,6 +357,14 @@ int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float
     rc = stocs_launch_score(ctx, ctx->d_T.as<float>() + off * 16, n, ctx->d_lcp.as<float>() + off,
                             ctx->d_inl.as<int32_t>() + off, st, false, (int)c);
     if (rc != STOCS_OK) break;
+  }
+  // Result copies are enqueued only after EVERY chunk's H2D copy and kernel: a cudaMemcpyAsync into
+  // pageable memory returns when the copy is done, so issuing it inside the loop above would hold
+  // back the enqueue of chunk k+1's H2D until chunk k's kernel has finished (no overlap at all).
+  for (int64_t c = 0; c < nchunks && rc == STOCS_OK && e == cudaSuccess; ++c) {
+    const int64_t off = bounds[c], n = bounds[c + 1] - bounds[c];
+    if (n <= 0) continue;
+    cudaStream_t st = cs[c & 1];
     e = cudaMemcpyAsync(lcp + off, ctx->d_lcp.as<float>() + off, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && inliers)
       e = cudaMemcpyAsync(inliers + off, ctx->d_inl.as<int32_t>() + off, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
@@ -436,9 +450,53 @@ int stocs_b200_get_counters(stocs_b200_ctx* ctx, int64_t* counters, int n) {
   return STOCS_OK;
 }
 
+// Data-dependent work of one scoring launch, counted by the counting variant of the kernel.
+int stocs_b200_score_counters(stocs_b200_ctx* ctx, const float* d_T16, int64_t H, int64_t* counters, int n) {
+  if (!ctx) return STOCS_E_ARG;
+  if (ctx->S <= 0 || ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "score_counters: upload_model and upload_scene first");
+  if (H <= 0 || !d_T16 || !counters || n < 1) STOCS_FAIL(ctx, STOCS_E_ARG, "score_counters: bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  DevBuf &d_lcp = ctx->pool[POOL_SHARD_LCP], &d_inl = ctx->pool[POOL_SHARD_INL];
+  STOCS_CUDA(ctx, d_lcp.ensure((size_t)H * 4));
+  STOCS_CUDA(ctx, d_inl.ensure((size_t)H * 4));
+  unsigned long long* d_cnt = (unsigned long long*)(ctx->d_small.as<char>() + 3072);
+  STOCS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 128, st));
+  int rc = stocs_launch_score(ctx, d_T16, H, d_lcp.as<float>(), d_inl.as<int32_t>(), st, false, 0, d_cnt);
+  if (rc) return rc;
+  unsigned long long h[16] = {0};
+  STOCS_CUDA(ctx, cudaMemcpyAsync(h, d_cnt, 128, cudaMemcpyDeviceToHost, st));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  int64_t out[9] = {H * (int64_t)ctx->M, (int64_t)h[0], (int64_t)h[1], (int64_t)h[2], (int64_t)h[3],
+                    (int64_t)h[4], (int64_t)h[5], (int64_t)h[6], H};
+  for (int i = 0; i < n && i < 9; ++i) counters[i] = out[i];
+  return STOCS_OK;
+}
+
+int stocs_b200_kernel_ms_stats(stocs_b200_ctx* ctx, int reset, int32_t* n_launches, float* mean_ms, float* max_ms) {
+  if (!ctx) return STOCS_E_ARG;
+  cudaSetDevice(ctx->device);
+  const int64_t n = ctx->ev_count < stocs_b200_ctx::kEvRing ? ctx->ev_count : stocs_b200_ctx::kEvRing;
+  double sum = 0;
+  float mx = 0.f;
+  for (int64_t i = 0; i < n; ++i) {
+    const int k = (int)((ctx->ev_count - 1 - i) % stocs_b200_ctx::kEvRing);
+    float ms = 0.f;
+    STOCS_CUDA(ctx, cudaEventSynchronize(ctx->ev_ring[2 * k + 1]));
+    STOCS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_ring[2 * k], ctx->ev_ring[2 * k + 1]));
+    sum += ms;
+    if (ms > mx) mx = ms;
+  }
+  if (n_launches) *n_launches = (int32_t)n;
+  if (mean_ms) *mean_ms = n ? (float)(sum / (double)n) : 0.f;
+  if (max_ms) *max_ms = mx;
+  if (reset) ctx->ev_count = 0;
+  return STOCS_OK;
+}
+
 int stocs_b200_last_kernel_ms(stocs_b200_ctx* ctx, float* ms) {
   if (!ctx || !ms) return STOCS_E_ARG;
-  if (!ctx->timing_valid) STOCS_FAIL(ctx, STOCS_E_STATE, "no timed launch");
+  if (!ctx->timing_valid || !ctx->ev0) STOCS_FAIL(ctx, STOCS_E_STATE, "no timed launch");
   cudaSetDevice(ctx->device);
   STOCS_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
   STOCS_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));

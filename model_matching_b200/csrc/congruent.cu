@@ -291,9 +291,9 @@ int stocs_congruent_device(stocs_b200_ctx* ctx, int n_bases, const int* d_base_i
   h_quad_off.assign((size_t)n_bases + 1, 0);
   if (n_bases == 0) return STOCS_OK;
   const PpfView v = stocs_ppf_view(ctx);
-  DevBuf &d_info = ctx->pool[0], &d_seg = ctx->pool[1], &d_codes_a = ctx->pool[2], &d_codes_b = ctx->pool[3], &d_tmp = ctx->pool[4],
-         &d_pe = ctx->pool[5], &d_qe = ctx->pool[6], &d_qcell = ctx->pool[7], &d_cnt = ctx->pool[8], &d_scan = ctx->pool[9],
-         &d_qoff = ctx->pool[10];
+  DevBuf &d_info = ctx->pool[POOL_CONG_INFO], &d_seg = ctx->pool[POOL_CONG_SEG], &d_codes_a = ctx->pool[POOL_CONG_CODES_A], &d_codes_b = ctx->pool[POOL_CONG_CODES_B], &d_tmp = ctx->pool[POOL_CONG_TMP],
+         &d_pe = ctx->pool[POOL_CONG_PE], &d_qe = ctx->pool[POOL_CONG_QE], &d_qcell = ctx->pool[POOL_CONG_QCELL], &d_cnt = ctx->pool[POOL_CONG_CNT], &d_scan = ctx->pool[POOL_CONG_SCAN],
+         &d_qoff = ctx->pool[POOL_CONG_QOFF];
   auto cleanup = [&]() {};  // pool slots persist
 #define CG(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
   CG(d_info.ensure((size_t)n_bases * sizeof(BaseInfo)));
@@ -380,7 +380,7 @@ extern "C" int stocs_b200_find_congruent(stocs_b200_ctx* ctx, int n_bases, const
     STOCS_CUDA(ctx, cudaMemcpyAsync(d_ids, base_idx4, (size_t)n_bases * 16, cudaMemcpyHostToDevice, st));
     STOCS_CUDA(ctx, cudaMemcpyAsync(d_inv, inv2, (size_t)n_bases * 8, cudaMemcpyHostToDevice, st));
   }
-  DevBuf& quads = ctx->pool[11];
+  DevBuf& quads = ctx->pool[POOL_CONG_QUADS];
   std::vector<long long> off;
   int rc = stocs_congruent_device(ctx, n_bases, d_ids, d_inv, quads, off, st);
   if (rc) return rc;

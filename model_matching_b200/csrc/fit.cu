@@ -19,8 +19,6 @@ int stocs_launch_sample(stocs_b200_ctx* ctx, uint64_t seed, uint32_t first_base_
                         float* d_inv, uint8_t* d_valid, cudaStream_t st);
 int stocs_congruent_device(stocs_b200_ctx* ctx, int n_bases, const int* d_base_idx4, const float* d_inv2,
                            DevBuf& quads_buf, std::vector<long long>& h_quad_off, cudaStream_t st);
-int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
-                      int64_t* d_idx, float* d_val, cudaStream_t st);
 
 namespace {
 
@@ -175,7 +173,7 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   result->best_index = -1;
   result->best_base = -1;
   // 1. bases
-  DevBuf& d_bases = ctx->pool[0 + 31 - 0];
+  DevBuf& d_bases = ctx->pool[POOL_PIPE_BASES];
   STOCS_CUDA(ctx, d_bases.ensure((size_t)n_bases * 25 + 64));
   int* d_ids = d_bases.as<int>();
   float* d_inv = (float*)(d_ids + 4 * (size_t)n_bases);
@@ -203,7 +201,7 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   STOCS_CUDA(ctx, cudaMemcpyAsync(d_ids, v_ids.data(), (size_t)nv * 16, cudaMemcpyHostToDevice, st));
   STOCS_CUDA(ctx, cudaMemcpyAsync(d_inv, v_inv.data(), (size_t)nv * 8, cudaMemcpyHostToDevice, st));
   // 2. congruent sets
-  DevBuf& d_quads = ctx->pool[11];
+  DevBuf& d_quads = ctx->pool[POOL_CONG_QUADS];
   std::vector<long long> quad_off;
   rc = stocs_congruent_device(ctx, nv, d_ids, d_inv, d_quads, quad_off, st);
   if (rc) return rc;
@@ -217,7 +215,7 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   }
   const long long n_items = item_off[nv];
   if (n_items == 0) return STOCS_OK;
-  DevBuf &d_off = ctx->pool[28], &d_items = ctx->pool[29], &d_fit = ctx->pool[30];
+  DevBuf &d_off = ctx->pool[POOL_PIPE_OFF], &d_items = ctx->pool[POOL_PIPE_ITEMS], &d_fit = ctx->pool[POOL_PIPE_FIT];
   auto cleanup = [&]() {};  // pool slots persist
 #define PL(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
   PL(d_off.ensure((size_t)(nv + 1) * 16));

@@ -144,7 +144,7 @@ extern "C" int stocs_b200_icp_point_to_plane(stocs_b200_ctx* ctx, const float* s
   if (!(max_correspondence_distance > 0)) STOCS_FAIL(ctx, STOCS_E_ARG, "icp: max_correspondence_distance must be positive");
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  DevBuf &d_src = ctx->pool[32], &d_tgt = ctx->pool[33], &d_tn = ctx->pool[34], &d_part = ctx->pool[35], &d_state = ctx->pool[36];
+  DevBuf &d_src = ctx->pool[POOL_ICP_SRC], &d_tgt = ctx->pool[POOL_ICP_TGT], &d_tn = ctx->pool[POOL_ICP_TN], &d_part = ctx->pool[POOL_ICP_PART], &d_state = ctx->pool[POOL_ICP_STATE];
   const int nblocks = (n_src + kIcpBlock - 1) / kIcpBlock;
   STOCS_CUDA(ctx, d_src.ensure((size_t)n_src * 16));
   STOCS_CUDA(ctx, d_tgt.ensure((size_t)n_tgt * 16));

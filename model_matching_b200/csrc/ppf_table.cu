@@ -161,7 +161,7 @@ int stocs_build_ppf_table(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, ctx->d_ppf_bin_start.ensure((size_t)(nbins + 1) * 4));
   STOCS_CUDA(ctx, ctx->d_ppf_keybits.ensure((size_t)((nkeybits + 31) / 32) * 4));
   STOCS_CUDA(ctx, ctx->d_work.ensure((size_t)(nbins + 1) * 4));
-  DevBuf &keys_a = ctx->pool[16], &keys_b = ctx->pool[17], &cub_tmp = ctx->pool[18];
+  DevBuf &keys_a = ctx->pool[POOL_PPF_KEYS_A], &keys_b = ctx->pool[POOL_PPF_KEYS_B], &cub_tmp = ctx->pool[POOL_PPF_CUB_TMP];
   STOCS_CUDA(ctx, keys_a.ensure((size_t)MM * 8));
   STOCS_CUDA(ctx, keys_b.ensure((size_t)MM * 8));
   uint32_t* counts = ctx->d_work.as<uint32_t>();

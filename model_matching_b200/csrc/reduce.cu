@@ -62,9 +62,12 @@ __global__ void __launch_bounds__(256) topk_partial_kernel(const float* __restri
 }
 
 // final merge of nlists sorted lists: 32 warps take a strided share each, warp 0 merges the rest
+// With rec_out != NULL the K winners are also packed as 64-byte records {lcp, inliers, global
+// index, rows 0..2 of the transform} -- the unit of the multi-GPU all-gather (comm.cu).
 __global__ void __launch_bounds__(1024) topk_merge_kernel(const unsigned long long* __restrict__ keys, long long nlists,
                                                           int K, long long index_offset, long long* __restrict__ out_idx,
-                                                          float* __restrict__ out_lcp) {
+                                                          float* __restrict__ out_lcp, const float* __restrict__ T16,
+                                                          const int* __restrict__ inl, stocs_b200_record* __restrict__ rec_out) {
   __shared__ unsigned long long s_keys[32 * 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned long long mine = 0ull;
@@ -74,10 +77,30 @@ __global__ void __launch_bounds__(1024) topk_merge_kernel(const unsigned long lo
   if (w != 0) return;
   for (int k = 1; k < 32; ++k) warp_offer(mine, s_keys[k * 32 + lane], lane);
   if (lane < K) {
-    if (mine == 0ull) { out_idx[lane] = -1; out_lcp[lane] = 0.f; }
-    else {
-      out_idx[lane] = (long long)(0xffffffffull - (mine & 0xffffffffull)) + index_offset;
-      out_lcp[lane] = __uint_as_float((unsigned)(mine >> 32));
+    const long long local = (long long)(0xffffffffull - (mine & 0xffffffffull));
+    if (out_idx) {
+      if (mine == 0ull) { out_idx[lane] = -1; out_lcp[lane] = 0.f; }
+      else {
+        out_idx[lane] = local + index_offset;
+        out_lcp[lane] = __uint_as_float((unsigned)(mine >> 32));
+      }
+    }
+    if (rec_out) {
+      stocs_b200_record r;
+      r.lcp = 0.f; r.inliers = 0; r.index = -1;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) r.T[k] = 0.f;
+      if (mine != 0ull) {
+        r.lcp = __uint_as_float((unsigned)(mine >> 32));
+        r.inliers = inl ? inl[local] : 0;
+        r.index = local + index_offset;
+        const float* t = T16 + 16 * local;   // column-major 4x4 -> rows 0..2, row-major
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) r.T[rr * 4 + c] = t[c * 4 + rr];
+      }
+      rec_out[lane] = r;
     }
   }
 }
@@ -149,7 +172,8 @@ extern "C" int stocs_b200_select_above(stocs_b200_ctx* ctx, const float* lcp, in
 }
 
 int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
-                      int64_t* d_idx, float* d_val, cudaStream_t st) {
+                      int64_t* d_idx, float* d_val, cudaStream_t st, const float* d_T16, const int32_t* d_inl,
+                      stocs_b200_record* d_rec) {
   if (K < 1 || K > 32) STOCS_FAIL(ctx, STOCS_E_ARG, "reduce_best: K must be in 1..32");
   if (H >= (1ll << 32)) STOCS_FAIL(ctx, STOCS_E_ARG, "reduce_best: H must be < 2^32");
   int blocks = ctx->num_sms * 2;
@@ -159,7 +183,7 @@ int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K,
   STOCS_CUDA(ctx, ctx->d_work.ensure((size_t)blocks * 32 * 8));
   topk_partial_kernel<<<blocks, 256, 0, st>>>(d_lcp, H, ctx->d_work.as<unsigned long long>());
   topk_merge_kernel<<<1, 1024, 0, st>>>(ctx->d_work.as<unsigned long long>(), blocks, K, index_offset,
-                                        (long long*)d_idx, d_val);
+                                        (long long*)d_idx, d_val, d_T16, d_inl, d_rec);
   STOCS_CUDA(ctx, cudaGetLastError());
   return STOCS_OK;
 }

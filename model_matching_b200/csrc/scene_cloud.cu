@@ -195,25 +195,25 @@ extern "C" int stocs_b200_build_scene_cloud(stocs_b200_ctx* ctx, const uint16_t*
   cudaStream_t st = ctx->stream;
   const int n = W * H;
   const int nb = (n + 255) / 256;
-  DevBuf& d_depth = ctx->pool[12];
-  DevBuf& d_bgr = ctx->pool[13];
-  DevBuf& d_prob = ctx->pool[14];
-  DevBuf& d_edge = ctx->pool[15];
-  DevBuf& d_xyz = ctx->pool[16];
-  DevBuf& d_keys_a = ctx->pool[17];
-  DevBuf& d_keys_b = ctx->pool[18];
-  DevBuf& d_idx_a = ctx->pool[19];
-  DevBuf& d_idx_b = ctx->pool[20];
-  DevBuf& d_tmp = ctx->pool[21];
-  DevBuf& d_flags = ctx->pool[22];
-  DevBuf& d_scan = ctx->pool[23];
-  DevBuf& d_starts = ctx->pool[24];
-  DevBuf& d_ukeys = ctx->pool[25];
-  DevBuf& d_cent = ctx->pool[26];
-  DevBuf& d_keep = ctx->pool[27];
-  DevBuf& d_nrm = ctx->pool[28];
-  DevBuf& d_rc = ctx->pool[29];
-  DevBuf& d_out = ctx->pool[30];
+  DevBuf& d_depth = ctx->pool[POOL_CLOUD_DEPTH];
+  DevBuf& d_bgr = ctx->pool[POOL_CLOUD_BGR];
+  DevBuf& d_prob = ctx->pool[POOL_CLOUD_PROB];
+  DevBuf& d_edge = ctx->pool[POOL_CLOUD_EDGE];
+  DevBuf& d_xyz = ctx->pool[POOL_CLOUD_XYZ];
+  DevBuf& d_keys_a = ctx->pool[POOL_CLOUD_KEYS_A];
+  DevBuf& d_keys_b = ctx->pool[POOL_CLOUD_KEYS_B];
+  DevBuf& d_idx_a = ctx->pool[POOL_CLOUD_IDX_A];
+  DevBuf& d_idx_b = ctx->pool[POOL_CLOUD_IDX_B];
+  DevBuf& d_tmp = ctx->pool[POOL_CLOUD_TMP];
+  DevBuf& d_flags = ctx->pool[POOL_CLOUD_FLAGS];
+  DevBuf& d_scan = ctx->pool[POOL_CLOUD_SCAN];
+  DevBuf& d_starts = ctx->pool[POOL_CLOUD_STARTS];
+  DevBuf& d_ukeys = ctx->pool[POOL_CLOUD_UKEYS];
+  DevBuf& d_cent = ctx->pool[POOL_CLOUD_CENT];
+  DevBuf& d_keep = ctx->pool[POOL_CLOUD_KEEP];
+  DevBuf& d_nrm = ctx->pool[POOL_CLOUD_NRM];
+  DevBuf& d_rc = ctx->pool[POOL_CLOUD_RC];
+  DevBuf& d_out = ctx->pool[POOL_CLOUD_OUT];
   auto cleanup = [&]() {};  // pool slots persist
 #define SC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
   SC(d_depth.ensure((size_t)n * 2)); SC(d_prob.ensure((size_t)n * 2)); SC(d_xyz.ensure((size_t)n * 12));

@@ -288,7 +288,7 @@ int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4*
 
 int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   // expects ctx->d_tmp = raw pos3 (S*3 floats)
-  const int S = ctx->S;
+  const int S = ctx->S_pending;   // committed to ctx->S by upload_scene once the index is complete
   cudaStream_t st = ctx->stream;
   StageTrace tr(st);
   STOCS_CUDA(ctx, ctx->d_spos4.ensure((size_t)S * 16));
@@ -382,7 +382,7 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   const float r = (float)(eps * (1.0 + 1.0 / 256.0) + cell / 256.0);
 
   size_t nc1 = (size_t)g.ncells + 1;
-  DevBuf& d_dense = ctx->pool[12];  // dense per-cell starts (scratch)
+  DevBuf& d_dense = ctx->pool[POOL_INDEX_DENSE];  // dense per-cell starts (scratch)
   STOCS_CUDA(ctx, d_dense.ensure(nc1 * 4));
   STOCS_CUDA(ctx, ctx->d_work.ensure(nc1 * 4));
   uint32_t* counts = ctx->d_work.as<uint32_t>();
@@ -403,7 +403,7 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>());
   tr.mark("fill candidates");
   // brick table + compact starts
-  DevBuf &d_masks = ctx->pool[13], &d_occ = ctx->pool[14], &d_occ_scan = ctx->pool[15];
+  DevBuf &d_masks = ctx->pool[POOL_INDEX_MASKS], &d_occ = ctx->pool[POOL_INDEX_OCC], &d_occ_scan = ctx->pool[POOL_INDEX_OCC_SCAN];
   STOCS_CUDA(ctx, d_masks.ensure((size_t)g.nbricks * 8));
   STOCS_CUDA(ctx, d_occ.ensure((size_t)(g.nbricks + 1) * 4));
   STOCS_CUDA(ctx, d_occ_scan.ensure((size_t)(g.nbricks + 1) * 4));

@@ -63,6 +63,7 @@ struct ScoreArgs {
   int* __restrict__ inl;
   unsigned long long* work_counter;
   unsigned long long* tie_counter;
+  unsigned long long* cnt;   // counting variant only (stocs_b200_score_counters): see ScoreCounter
   long long H;
   GridDesc g;
   int M, Mpad;
@@ -189,6 +190,14 @@ struct WarpQueue {   // one per warp, shared memory (single base register, const
 
 struct Acc { float acc; int inl; unsigned ties; };
 
+// Work counters of the counting variant (template parameter kCount; the timed kernel carries none
+// of this).  One global atomic per warp-level event, issued by lane 0.
+enum ScoreCounter { SC_SURVIVORS = 0, SC_BRICK_RECORDS, SC_QUEUED, SC_CANDIDATES, SC_HITS, SC_INLIERS, SC_DRAINS, SC_N };
+template <bool kCount>
+__device__ __forceinline__ void count(const ScoreArgs& a, int lane, int slot, unsigned v) {
+  if (kCount) { if (lane == 0 && v) atomicAdd(a.cnt + slot, (unsigned long long)v); }
+}
+
 // Phase B.  The queued queries are processed 32 at a time, one per lane ("owner" lane e holds
 // query e: exact transformed point, candidate offset, candidate count).
 //   1. owners fetch their candidate-list offsets and compute the EXACT transformed point
@@ -204,6 +213,7 @@ struct Acc { float acc; int inl; unsigned ties; };
 //   3. owners fetch the matched scene point's normal + class probability, apply the 30-degree test
 //      and the class probabilities are accumulated in lane order == model-point order, which makes
 //      the LCP bit-identical to the reference's sequential fp32 sum.
+template <bool kCount>
 __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, int qn, int lane,
                                             const float4* __restrict__ mp4, const float4* __restrict__ mn4, Acc& r) {
   __syncwarp();
@@ -234,6 +244,8 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
     }
     const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
     pre -= cnt;
+    count<kCount>(a, lane, SC_CANDIDATES, total);
+    count<kCount>(a, lane, SC_DRAINS, 1u);
     __syncwarp();
     // 2.
     unsigned flag = 0;          // queries this lane wants answered by the kd-tree (exact d^2 ties)
@@ -286,6 +298,8 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
       }
     }
     unsigned mm = __ballot_sync(0xffffffffu, match);
+    if (kCount) count<kCount>(a, lane, SC_HITS, __popc(__ballot_sync(0xffffffffu, has && mine != ~0ull)));
+    count<kCount>(a, lane, SC_INLIERS, __popc(mm));
     r.inl += __popc(mm);
     while (mm) {  // ordered fp32 accumulation == the reference's sequential loop
       const int b = __ffs(mm) - 1;
@@ -296,6 +310,7 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
   }
 }
 
+template <bool kCount>
 __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kernel(ScoreArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_model = reinterpret_cast<float*>(smem_raw);
@@ -371,6 +386,7 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
         if (pass) q.plist[nl + __popc(pm & lt_mask)] = (uint8_t)(rr * 32 + lane);
         nl += __popc(pm);
       }
+      count<kCount>(a, lane, SC_SURVIVORS, (unsigned)nl);
       __syncwarp();
       for (int e0 = 0; e0 < nl; e0 += 32) {
         const bool valid = e0 + lane < nl;
@@ -389,6 +405,14 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
 #else
         if (valid) br = LD_BRICK(a.bricks + bidx);
 #endif
+        if (kCount) {
+#ifdef SCORE_BRICK_OCC
+          const bool fetched = valid && ((__ldg(a.brick_occ + (bidx >> 5)) >> (bidx & 31u)) & 1u);
+#else
+          const bool fetched = valid;
+#endif
+          count<kCount>(a, lane, SC_BRICK_RECORDS, __popc(__ballot_sync(0xffffffffu, fetched)));
+        }
         const unsigned bit = ((iz & 3u) << 4) | ((iy & 3u) << 2) | (ix & 3u);
         const unsigned half = (bit & 32u) ? br.y : br.x;      // 64-bit occupancy mask as two words
         const bool has = (half >> (bit & 31u)) & 1u;
@@ -401,9 +425,10 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
             q.pi[slot] = (uint32_t)i;
           }
           qn += __popc(hm);
+          count<kCount>(a, lane, SC_QUEUED, __popc(hm));
         }
         if (qn > kQueue - 32) {
-          drain_queue(a, q, qn, lane, mp4, mn4, r);
+          drain_queue<kCount>(a, q, qn, lane, mp4, mn4, r);
           qn = 0;
           // the map is re-read after a drain so that it is not live (in registers) across it
           g0 = q.G[0]; g1 = q.G[1]; g2 = q.G[2]; g3 = q.G[3]; g4 = q.G[4]; g5 = q.G[5];
@@ -412,7 +437,7 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
       }
       __syncwarp();
     }
-    if (qn > 0) drain_queue(a, q, qn, lane, mp4, mn4, r);
+    if (qn > 0) drain_queue<kCount>(a, q, qn, lane, mp4, mn4, r);
     if (lane == 0) {
       a.lcp[h] = r.acc / (float)M;
       if (a.inl) a.inl[h] = r.inl;
@@ -442,7 +467,7 @@ bool stocs_fmad_selftest(stocs_b200_ctx* ctx) {
 }
 
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp, int32_t* d_inl,
-                       cudaStream_t st, bool time_it, int slot) {
+                       cudaStream_t st, bool time_it, int slot, unsigned long long* d_counters) {
   if (H <= 0) return STOCS_OK;
   if (H >= (1ll << 31)) STOCS_FAIL(ctx, STOCS_E_ARG, "score: at most 2^31-1 hypotheses per call");
   ScoreArgs a;
@@ -467,6 +492,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   unsigned long long* wctr = slot == 0 ? ctr : (unsigned long long*)(ctx->d_small.as<char>() + 2048) + slot;
   a.work_counter = wctr;
   a.tie_counter = ctr + 1;
+  a.cnt = d_counters;
   a.H = H;
   a.g = ctx->grid;
   a.M = ctx->M;
@@ -475,17 +501,26 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.dot_thr = ctx->dot_thr;
   size_t smem = (size_t)4 * ctx->Mpad * 4 + (size_t)((a.coarse_words + 3) & ~3) * 4 + (size_t)kWarps * sizeof(WarpQueue);
   // static (per-warp queues) + dynamic (model, coarse bitmap) may exceed the 48 KB default
-  STOCS_CUDA(ctx, cudaFuncSetAttribute(score_lcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // d_counters != NULL selects the counting variant (same code + one global atomic per warp event)
+  void (*kernel)(ScoreArgs) = d_counters ? score_lcp_kernel<true> : score_lcp_kernel<false>;
+  STOCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  STOCS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_lcp_kernel, kWarps * 32, smem));
+  STOCS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarps * 32, smem));
   if (per_sm < 1) STOCS_FAIL(ctx, STOCS_E_ARG, "score: model too large for shared memory");
   long long want = (H + kWarps - 1) / kWarps;
   long long grid = (long long)ctx->num_sms * per_sm;
   if (grid > want) grid = want;
   STOCS_CUDA(ctx, cudaMemsetAsync(wctr, 0, 8, st));  // work counter only; tie counter accumulates
-  if (time_it) STOCS_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  score_lcp_kernel<<<(unsigned)grid, kWarps * 32, smem, st>>>(a);
-  if (time_it) STOCS_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+  if (time_it) {  // next pair of the ring (events are created on first use)
+    const int k = (int)(ctx->ev_count % stocs_b200_ctx::kEvRing);
+    for (int j = 0; j < 2; ++j)
+      if (!ctx->ev_ring[2 * k + j]) STOCS_CUDA(ctx, cudaEventCreate(&ctx->ev_ring[2 * k + j]));
+    ctx->ev0 = ctx->ev_ring[2 * k];
+    ctx->ev1 = ctx->ev_ring[2 * k + 1];
+    STOCS_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  }
+  kernel<<<(unsigned)grid, kWarps * 32, smem, st>>>(a);
+  if (time_it) { STOCS_CUDA(ctx, cudaEventRecord(ctx->ev1, st)); ctx->ev_count++; }
   STOCS_CUDA(ctx, cudaGetLastError());
   ctx->counters[0] += 1;
   ctx->timing_valid = time_it;

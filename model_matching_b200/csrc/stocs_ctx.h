@@ -54,13 +54,45 @@ struct PpfTableDesc {
   int64_t nexpanded;   // keys of the reference's expanded map
 };
 
+// Scratch-pool slot names (stocs_b200_ctx::pool).  Ranges that overlap belong to stages that are
+// never active inside the same ABI call on the same stream.
+enum PoolSlot : int {
+  // congruent.cu (stocs_congruent_device): 0..11; POOL_CONG_QUADS is its output, read by run_pipeline
+  POOL_CONG_INFO = 0, POOL_CONG_SEG, POOL_CONG_CODES_A, POOL_CONG_CODES_B, POOL_CONG_TMP, POOL_CONG_PE,
+  POOL_CONG_QE, POOL_CONG_QCELL, POOL_CONG_CNT, POOL_CONG_SCAN, POOL_CONG_QOFF, POOL_CONG_QUADS = 11,
+  // scene_index.cu (upload_scene): 12..15
+  POOL_INDEX_DENSE = 12, POOL_INDEX_MASKS, POOL_INDEX_OCC, POOL_INDEX_OCC_SCAN,
+  // scene_cloud.cu (build_scene_cloud): 12..30
+  POOL_CLOUD_DEPTH = 12, POOL_CLOUD_BGR, POOL_CLOUD_PROB, POOL_CLOUD_EDGE, POOL_CLOUD_XYZ, POOL_CLOUD_KEYS_A,
+  POOL_CLOUD_KEYS_B, POOL_CLOUD_IDX_A, POOL_CLOUD_IDX_B, POOL_CLOUD_TMP, POOL_CLOUD_FLAGS, POOL_CLOUD_SCAN,
+  POOL_CLOUD_STARTS, POOL_CLOUD_UKEYS, POOL_CLOUD_CENT, POOL_CLOUD_KEEP, POOL_CLOUD_NRM, POOL_CLOUD_RC,
+  POOL_CLOUD_OUT = 30,
+  // ppf_table.cu (upload_model / upload_ppf_table): 16..18
+  POOL_PPF_KEYS_A = 16, POOL_PPF_KEYS_B, POOL_PPF_CUB_TMP,
+  // fit.cu (run_pipeline): 28..31
+  POOL_PIPE_OFF = 28, POOL_PIPE_ITEMS, POOL_PIPE_FIT, POOL_PIPE_BASES = 31,
+  // icp.cu: 32..36
+  POOL_ICP_SRC = 32, POOL_ICP_TGT, POOL_ICP_TN, POOL_ICP_PART, POOL_ICP_STATE,
+  // capi.cu: top-32 of the resident lcp array
+  POOL_TOPK_RESIDENT = 37,
+  // comm.cu: packed 64-byte records (local K, gathered world*K, merged K)
+  POOL_COMM_SEND = 38, POOL_COMM_RECV, POOL_COMM_OUT, POOL_COMM_TOPK,
+  // sharded scoring scratch (transforms / lcp / inliers of the local shard)
+  POOL_SHARD_T = 42, POOL_SHARD_LCP, POOL_SHARD_INL,
+  POOL_COUNT = 48
+};
+
 struct stocs_b200_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // second compute stream: consecutive score chunks overlap their tails
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // the most recent timed scoring launch (aliases into ev_ring)
+  // ring of event pairs around the timed scoring launches (stocs_b200_kernel_ms_stats)
+  static constexpr int kEvRing = 512;
+  cudaEvent_t ev_ring[2 * kEvRing] = {};
+  int64_t ev_count = 0;
   static constexpr int kMaxChunks = 16;
   cudaEvent_t chunk_ev[kMaxChunks] = {};  // H2D-complete events of score_lcp's chunks
   cudaEvent_t join_ev[2] = {nullptr, nullptr};
@@ -81,6 +113,7 @@ struct stocs_b200_ctx {
 
   // scene (centred)
   int S = 0;
+  int S_pending = 0;                   // size of the scene being uploaded (S is committed on success)
   float cs[3] = {0, 0, 0};
   std::vector<float> h_spos;           // centred positions (S*3)
   DevBuf d_spos4;                      // float4 (x,y,z,bits(idx))
@@ -109,8 +142,10 @@ struct stocs_b200_ctx {
   DevBuf d_ppf_keybits;                // bitmap of keys present in the reference's expanded map
   std::vector<uint32_t> h_ppf_bin_start, h_ppf_pairs;
 
-  // grow-only scratch slots reused by the multi-kernel stages (no cudaMalloc/cudaFree per call)
-  DevBuf pool[40];
+  // grow-only scratch slots reused by the multi-kernel stages (no cudaMalloc/cudaFree per call).
+  // Slots are named by PoolSlot below.  Rule: a slot is single-stream scratch -- NO slot may hold
+  // state across ABI calls, so stages that never run inside one another may share a number.
+  DevBuf pool[48];
   // scratch
   DevBuf d_T, d_lcp, d_inl, d_work, d_tmp, d_tmp2, d_small;
   void* h_pinned = nullptr;
@@ -118,12 +153,17 @@ struct stocs_b200_ctx {
 
   // last score call
   int64_t last_H = 0;
+  const float* last_T_dev = nullptr;   // device-visible transforms of the last host-buffer score call
   // top-32 of the resident lcp array, computed by score_lcp behind its result copies
   struct TopCache { int64_t idx[32]; float val[32]; };
   TopCache* h_top = nullptr;   // page-locked
   bool top_valid = false;
   int64_t counters[8] = {0};
   bool timing_valid = false;
+
+  // multi-GPU (comm.cu): one NCCL communicator per context; ncclComm_t kept opaque here
+  void* comm = nullptr;
+  int comm_rank = 0, comm_nranks = 1;
 };
 
 #define STOCS_CUDA(ctx, call)                                                            \
@@ -144,11 +184,16 @@ int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4*
                         float* d_out3, float* h_centroid3, float* h_aabb6);
 int stocs_pack_scene_attr(stocs_b200_ctx* ctx, const float* d_nrm3, const float* d_cls, int S);
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp,
-                       int32_t* d_inl, cudaStream_t st, bool time_it, int slot = 0);  // score.cu
+                       int32_t* d_inl, cudaStream_t st, bool time_it, int slot = 0,
+                       unsigned long long* d_counters = nullptr);  // score.cu
 int stocs_launch_backproject(stocs_b200_ctx* ctx, const uint16_t* d_depth, const uint8_t* d_bgr,
                              int W, int H, float fx, float cx, float fy, float cy, float scale,
                              float* d_xyz, uint32_t* d_rgb, cudaStream_t st);  // backproject.cu
 bool stocs_fmad_selftest(stocs_b200_ctx* ctx);                             // score.cu
+// top-K of a device lcp array (reduce.cu); d_idx/d_val may be NULL when only records are wanted
+int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
+                      int64_t* d_idx, float* d_val, cudaStream_t st, const float* d_T16 = nullptr,
+                      const int32_t* d_inl = nullptr, stocs_b200_record* d_rec = nullptr);
 float stocs_angle_threshold_dot();                                         // capi.cu (host)
 
 // STOCS_TRACE=1: wall-clock of each stage of a host-driven sequence on stderr (adds a synchronize

@@ -20,6 +20,7 @@ struct Matrix {
   Matrix() { for (int i = 0; i < Rows * Cols; ++i) m[i] = Scalar(0); }
   Matrix(Scalar x, Scalar y, Scalar z) { static_assert(Rows * Cols == 3, "3-vector only"); m[0] = x; m[1] = y; m[2] = z; }
   static Matrix Zero() { return Matrix(); }
+  void setIdentity() { *this = Identity(); }
   static Matrix Identity() { Matrix r; for (int i = 0; i < (Rows < Cols ? Rows : Cols); ++i) r(i, i) = Scalar(1); return r; }
   Scalar& operator()(int r, int c) { return m[c * Rows + r]; }
   const Scalar& operator()(int r, int c) const { return m[c * Rows + r]; }

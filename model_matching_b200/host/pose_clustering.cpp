@@ -114,13 +114,14 @@ void point_to_plane_icp(PCLPointCloud::Ptr segment_cloud, PCLPointCloud::Ptr mod
   if (!ctx) {
     const char* dev = getenv("STOCS_DEVICE");
     if (stocs_b200_create(&ctx, dev ? atoi(dev) : 0) != 0) {
-      std::string why = ctx ? stocs_b200_last_error(ctx) : "no context";
-      if (ctx) { stocs_b200_destroy(ctx); ctx = nullptr; }
-      throw std::runtime_error("point_to_plane_icp: " + why);
+      ctx = nullptr;  // create leaves *out NULL on failure; its message is kept per thread
+      throw std::runtime_error(std::string("point_to_plane_icp: ") + stocs_b200_last_error(nullptr));
     }
   }
   const int ns = (int)segment_cloud->points.size(), nt = (int)model_cloud->points.size();
-  if (ns == 0 || nt == 0) return;
+  // PCL's align() on an empty source or target does not converge; the reference then resets the
+  // caller's matrix (src/pose_clustering.cpp:136-139)
+  if (ns == 0 || nt == 0) { offset_transform.setIdentity(); return; }
   std::vector<float> sp((size_t)ns * 3), tp((size_t)nt * 3), tn((size_t)nt * 3), moved((size_t)ns * 3);
   for (int i = 0; i < ns; ++i) {
     const CloudPoint& p = segment_cloud->points[i];
@@ -145,9 +146,13 @@ void point_to_plane_icp(PCLPointCloud::Ptr segment_cloud, PCLPointCloud::Ptr mod
     p.ny = T[1] * nx + T[5] * ny + T[9] * nz;
     p.nz = T[2] * nx + T[6] * ny + T[10] * nz;
   }
-  if (converged)
+  // src/pose_clustering.cpp:136-139: final transformation when converged, identity otherwise
+  if (converged) {
     for (int c = 0; c < 4; ++c)
       for (int r = 0; r < 4; ++r) offset_transform(r, c) = T[c * 4 + r];
+  } else {
+    offset_transform.setIdentity();
+  }
 }
 
 }  // namespace clustering

@@ -10,7 +10,9 @@
 
 #include "pose_clustering.hpp"
 
-static int icp_main() {
+// `icp stale`: offset_transform enters as a non-identity matrix, so a run that does not converge
+// must come back as identity (src/pose_clustering.cpp:136-139)
+static int icp_main(bool stale) {
   int ns, nt;
   if (scanf("%d %d", &ns, &nt) != 2) return 1;
   auto seg = std::make_shared<PCLPointCloud>(), model = std::make_shared<PCLPointCloud>();
@@ -19,6 +21,7 @@ static int icp_main() {
   for (auto& p : seg->points) { if (scanf("%f %f %f", &p.x, &p.y, &p.z) != 3) return 1; p.nx = 0; p.ny = 0; p.nz = 1; }
   for (auto& p : model->points) if (scanf("%f %f %f %f %f %f", &p.x, &p.y, &p.z, &p.nx, &p.ny, &p.nz) != 6) return 1;
   Eigen::Matrix4f off = Eigen::Matrix4f::Identity();
+  if (stale) for (int k = 0; k < 16; ++k) off.data()[k] = 7.0f + (float)k;
   clustering::point_to_plane_icp(seg, model, off);
   for (int k = 0; k < 16; ++k) printf("%.9g ", off.data()[k]);
   printf("\n");
@@ -27,7 +30,7 @@ static int icp_main() {
 }
 
 int main(int argc, char** argv) {
-  if (argc > 1 && !strcmp(argv[1], "icp")) return icp_main();
+  if (argc > 1 && !strcmp(argv[1], "icp")) return icp_main(argc > 2 && !strcmp(argv[2], "stale"));
   int n, max_count;
   float frac, best, min_d, min_a, sym[3];
   if (scanf("%d %f %f %d %f %f %f %f %f", &n, &frac, &best, &max_count, &min_d, &min_a, &sym[0], &sym[1], &sym[2]) != 9) return 1;

@@ -168,6 +168,12 @@ def make_scene(n_points=1 << 20, seed=1234, extent=(2.0, 1.5, 1.4), n_objects=64
     return dict(pos=pos, nrm=nrm, cls=cls, gt_R=gt_R, gt_t=gt_t)
 
 
+def class_map(n_points, seed):
+    """Per-object class probability of every scene point, U{0..10000}/10000 (seeds 1000+k)."""
+    rng = _rng(seed)
+    return (rng.integers(0, 10001, size=n_points).astype(np.float32) * np.float32(1.0 / 10000)).astype(np.float32)
+
+
 def to_colmajor16(R, t):
     """(n,3,3),(n,3) -> (n,16) float32 in Eigen::Matrix4f memory order."""
     n = R.shape[0]

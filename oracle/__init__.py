@@ -63,6 +63,7 @@ def lib():
     L.orc_est_kd_query.argtypes = [C.c_void_p, f32p, C.c_int, C.c_float, i32p]
     L.orc_est_kd_num_nodes.argtypes = [C.c_void_p]
     L.orc_est_score.argtypes = [C.c_void_p, f32p, C.c_longlong, f32p, i32p, C.c_int]
+    L.orc_est_score_counters.argtypes = [C.c_void_p, f32p, C.c_longlong, C.c_int, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
     L.orc_icp_point_to_plane.restype = C.c_int
     L.orc_icp_point_to_plane.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, i32p,
                                          C.POINTER(C.c_int)]
@@ -218,6 +219,15 @@ class Estimator:
         lcp, inl = np.empty(H, np.float32), np.empty(H, np.int32)
         lib().orc_est_score(self.h, T, H, lcp, inl, threads)
         return lcp, inl
+
+    def score_counters(self, T, threads=1):
+        """Data-dependent work of the reference's own loop: dict(queries, examined, hits,
+        inliers, bytes) with bytes = 32*queries + 16*examined + 16*hits."""
+        T = _f32(T).reshape(-1, 16)
+        c = np.zeros(4, np.int64)
+        lib().orc_est_score_counters(self.h, T, T.shape[0], threads, c)
+        return dict(queries=int(c[0]), examined=int(c[1]), hits=int(c[2]), inliers=int(c[3]),
+                    bytes=int(32 * c[0] + 16 * c[1] + 16 * c[2]))
 
     def sample_class_base(self, seed, base_no):
         ids, inv, st = np.empty(4, np.int32), np.empty(2, np.float32), C.c_int(0)

@@ -153,7 +153,9 @@ struct KdTree {
   }
 
   // kdtree.h:394-459.  Thread-safe variant (the reference keeps the stack in a member).
-  int query(const V3& q, float sqdist) const {
+  // examined (optional): += number of leaf points whose distance was computed (kdtree.h:421-428),
+  // the "candidates_examined" of SURVEY.md section 8(d)'s data-dependent byte counter.
+  int query(const V3& q, float sqdist, long long* examined = nullptr) const {
     struct QN { unsigned nodeId; float sq; };
     QN stack[64];
     int cl_id = -1;
@@ -167,6 +169,7 @@ struct KdTree {
         if (node.leaf) {
           --count;
           const int end = (int)(node.start + node.size);
+          if (examined) *examined += node.size;
           for (int i = (int)node.start; i < end; ++i) {
             const float d = stocsm::sqnorm(stocsm::sub(q, pts[i]));
             if (d <= cl_dist) { cl_dist = d; cl_id = idx[i]; }
@@ -993,6 +996,42 @@ void orc_est_score(void* h, const float* T, long long H, float* lcp, int* inlier
     int inl; lcp[i] = e->score(T + 16 * i, &inl);
     if (inliers) inliers[i] = inl;
   }
+}
+// The data-dependent work counter of SURVEY.md section 8(d) for the reference's own loop
+// (src/stocs.cpp:1016-1036 + kdtree.h:416-428): counters = {NN queries, leaf points examined,
+// queries with a neighbour within eps ("hit"), inliers}.  bytes = 32*queries + 16*examined + 16*hits.
+void orc_est_score_counters(void* h, const float* T, long long H, int threads, long long* counters) {
+  auto* e = (orc::Estimator*)h;
+  const int M = (int)e->model.pos.size();
+  const float sq_eps = e->distance_threshold * e->distance_threshold;
+  std::atomic<long long> next(0), q_(0), c_(0), h_(0), i_(0);
+  auto work = [&]() {
+    long long nq = 0, nc = 0, nh = 0, ni = 0;
+    for (;;) {
+      long long b = next.fetch_add(64);
+      if (b >= H) break;
+      long long en = std::min(H, b + 64);
+      for (long long k = b; k < en; ++k) {
+        const float* Tk = T + 16 * k;
+        for (int i = 0; i < M; ++i) {
+          V3 q = stocsm::xform_point(Tk, e->model.pos[i]);
+          int id = e->kd.query(q, sq_eps, &nc);
+          ++nq;
+          if (id != -1) {
+            ++nh;
+            V3 nqv = stocsm::xform_dir(Tk, e->model.nrm[i]);
+            float angle = (float)stocsm::rad_to_deg_ref(stocsm::acos_f(stocsm::dot(e->snrm[id], nqv)));
+            if (angle < 30) ++ni;
+          }
+        }
+      }
+    }
+    q_ += nq; c_ += nc; h_ += nh; i_ += ni;
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < (threads < 1 ? 1 : threads); ++t) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
+  counters[0] = q_; counters[1] = c_; counters[2] = h_; counters[3] = i_;
 }
 // src/stocs.cpp:982-1004: first strict maximum, -1 when every score is 0.
 void orc_best(const float* lcp, long long H, long long* best_index, float* best_lcp) {

@@ -81,3 +81,26 @@ def test_host_point_to_plane_icp_wrapper():
     moved = np.array([l.split() for l in out[1:1 + len(src)]], np.float32)
     want = oracle.icp_point_to_plane(src, tgt, tn, 5, 0.035)
     assert _same(T, want[0]) and _same(moved, want[1])
+
+
+def test_host_icp_wrapper_resets_offset_when_not_converged():
+    """src/pose_clustering.cpp:136-139: the caller's matrix becomes identity when PCL's ICP has not
+    converged -- checked from a NON-identity starting matrix (a stale value must not survive)."""
+    exe = os.path.join(ROOT, "model_matching_b200", "host", "test_clustering")
+    tgt, tn = _cloud(300, 3)
+    src = tgt[:50] + np.float32(1.0)            # nothing within the correspondence distance
+    text = "%d %d\n" % (len(src), len(tgt))
+    text += "\n".join("%.9g %.9g %.9g" % tuple(p) for p in src) + "\n"
+    text += "\n".join("%.9g %.9g %.9g %.9g %.9g %.9g" % (*p, *n) for p, n in zip(tgt, tn)) + "\n"
+    out = subprocess.run([exe, "icp", "stale"], input=text, capture_output=True, text=True, timeout=120, check=True).stdout.split("\n")
+    T = np.array(out[0].split(), np.float32).reshape(4, 4).T
+    assert np.array_equal(T, np.eye(4, dtype=np.float32))
+    # and a converging run from the same stale matrix returns the ICP transform, not a product with it
+    R = synth.axis_angle(np.array([0.2, 0.9, -0.1]), 0.04)
+    src2 = (tgt[::3] @ R.T).astype(np.float32)
+    text = "%d %d\n" % (len(src2), len(tgt))
+    text += "\n".join("%.9g %.9g %.9g" % tuple(p) for p in src2) + "\n"
+    text += "\n".join("%.9g %.9g %.9g %.9g %.9g %.9g" % (*p, *n) for p, n in zip(tgt, tn)) + "\n"
+    out = subprocess.run([exe, "icp", "stale"], input=text, capture_output=True, text=True, timeout=120, check=True).stdout.split("\n")
+    T2 = np.array(out[0].split(), np.float32).reshape(4, 4).T
+    assert _same(T2, oracle.icp_point_to_plane(src2, tgt, tn, 5, 0.035)[0])
