@@ -83,6 +83,15 @@ int stocs_b200_get_centroids(stocs_b200_ctx* ctx, float* scene3, float* model3);
  * include/stocs.hpp:136-149).  Either pointer may be NULL. */
 int stocs_b200_get_centred(stocs_b200_ctx* ctx, float* scene_pos3, float* model_pos3);
 
+/* Replace the PPF table that upload_model derived from the points by a preloaded one (the
+ * reference's ppf_map_preloaded, src/stocs.cpp:94; src/stocs_match_one_object.cpp:201-203) in the
+ * layout of stocs_b200_ppf_export: n entries, keys4 = own-bin key (mm, deg, deg, deg), pairs2 = model
+ * ids.  The header values must match the estimator (set_params discretisations, |M| of the uploaded
+ * model) and every entry must fit the model: otherwise STOCS_E_ARG with an explanatory message --
+ * a table built for something else is never silently ignored. */
+int stocs_b200_upload_ppf_table(stocs_b200_ctx* ctx, const int32_t* keys4, const int32_t* pairs2, int64_t n,
+                                int tr_discretization, int rot_discretization, int num_model_points);
+
 /* PPF table queries (replace ppf_map.find, src/stocs.cpp:403,780-786).
  * ppf_lookup: number of pairs stored under key4 in the reference's expanded map, -1 if the key is
  * absent; copies up to cap pairs (id1,id2) in the reference's list order. */
@@ -120,6 +129,9 @@ int stocs_b200_sample_instance_base(stocs_b200_ctx* ctx, uint64_t seed, int base
 /* current per-point class probability (instance sampling decays it; LCP uses the decayed value,
  * src/stocs.cpp:577,1033) */
 int stocs_b200_get_class_probability(stocs_b200_ctx* ctx, float* out);
+/* overwrite it (S floats): keeps the replicas of a multi-GPU group consistent after instance
+ * sampling changed the prior on one device */
+int stocs_b200_set_class_probability(stocs_b200_ctx* ctx, const float* class_probability);
 
 /* ---- a9: congruent-set lookup (src/stocs.cpp:753-869) --------------------------------------
  * For each of n_bases bases returns its quadrilaterals (4 model indices each) in the reference's

@@ -19,8 +19,9 @@ SYMBOLS = [
     "stocs_b200_set_params", "stocs_b200_backproject", "stocs_b200_build_scene_cloud", "stocs_b200_upload_model",
     "stocs_b200_upload_scene", "stocs_b200_get_centroids", "stocs_b200_get_centred",
     "stocs_b200_ppf_num_pairs", "stocs_b200_ppf_num_expanded_keys", "stocs_b200_ppf_export",
-    "stocs_b200_ppf_lookup", "stocs_b200_sample_bases",
+    "stocs_b200_ppf_lookup", "stocs_b200_upload_ppf_table", "stocs_b200_sample_bases",
     "stocs_b200_upload_edge_map", "stocs_b200_sample_instance_base", "stocs_b200_get_class_probability",
+    "stocs_b200_set_class_probability",
     "stocs_b200_find_congruent", "stocs_b200_fit_transforms", "stocs_b200_score_lcp",
     "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device", "stocs_b200_select_above",
     "stocs_b200_icp_point_to_plane",
@@ -72,12 +73,14 @@ def lib():
     L.stocs_b200_get_centred.argtypes = [vp, vp, vp]
     L.stocs_b200_ppf_num_pairs.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.stocs_b200_ppf_lookup.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
+    L.stocs_b200_upload_ppf_table.argtypes = [vp, vp, vp, i64, i32, i32, i32]
     L.stocs_b200_ppf_num_expanded_keys.argtypes = [vp, C.POINTER(i64)]
     L.stocs_b200_ppf_export.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     L.stocs_b200_sample_bases.argtypes = [vp, u64, u32, i32, vp, vp, vp]
     L.stocs_b200_upload_edge_map.argtypes = [vp, vp, i32, i32]
     L.stocs_b200_sample_instance_base.argtypes = [vp, u64, i32, f32, vp, vp, vp, vp, vp]
     L.stocs_b200_get_class_probability.argtypes = [vp, vp]
+    L.stocs_b200_set_class_probability.argtypes = [vp, vp]
     L.stocs_b200_find_congruent.argtypes = [vp, i32, vp, vp, vp, i64, vp]
     L.stocs_b200_fit_transforms.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.stocs_b200_score_lcp.argtypes = [vp, vp, i64, vp, vp]
@@ -254,6 +257,17 @@ class Context:
         self._check(self._L.stocs_b200_ppf_export(self.h, _ptr(keys), _ptr(pairs), n.value, C.byref(n)))
         return keys, pairs
 
+    def upload_ppf_table(self, keys4, pairs2, tr, rot, num_model_points):
+        keys4 = np.ascontiguousarray(keys4, np.int32).reshape(-1, 4)
+        pairs2 = np.ascontiguousarray(pairs2, np.int32).reshape(-1, 2)
+        assert keys4.shape[0] == pairs2.shape[0]
+        try:
+            self._check(self._L.stocs_b200_upload_ppf_table(self.h, _ptr(keys4), _ptr(pairs2), keys4.shape[0], tr, rot,
+                                                             num_model_points))
+        except StocsError:
+            self.M = 0
+            raise
+
     def ppf_lookup(self, key):
         key = np.ascontiguousarray(key, np.int32).reshape(4)
         n = C.c_int64(0)
@@ -290,6 +304,11 @@ class Context:
         out = np.empty(self.S, np.float32)
         self._check(self._L.stocs_b200_get_class_probability(self.h, _ptr(out)))
         return out
+
+    def set_class_probability(self, cls):
+        cls = _f32(cls, (-1,))
+        assert cls.shape[0] == self.S
+        self._check(self._L.stocs_b200_set_class_probability(self.h, _ptr(cls)))
 
     def find_congruent(self, base_idx, inv, cap=1 << 20):
         base_idx = np.ascontiguousarray(base_idx, np.int32).reshape(-1, 4)

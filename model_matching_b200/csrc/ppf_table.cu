@@ -36,6 +36,24 @@ __global__ void ppf_pairs_kernel(const float* __restrict__ pos3, const float4* _
   atomicAdd(&counts[bin], 1u);
 }
 
+// the same sort keys from a caller-provided table (key4 = own-bin key in mm / degrees, pair = ids);
+// *bad counts entries that do not fit this model / discretisation
+__global__ void ppf_from_list_kernel(const int* __restrict__ keys4, const int* __restrict__ pairs2, long long n, int M,
+                                     int n1, int na, int tr, int rot, unsigned long long* __restrict__ keys,
+                                     uint32_t* __restrict__ counts, unsigned long long* __restrict__ bad) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int k1 = keys4[4 * t], k2 = keys4[4 * t + 1], k3 = keys4[4 * t + 2], k4 = keys4[4 * t + 3];
+  const int id1 = pairs2[2 * t], id2 = pairs2[2 * t + 1];
+  const int b1 = k1 / tr, b2 = k2 / rot, b3 = k3 / rot, b4 = k4 / rot;
+  const bool ok = k1 >= 0 && k2 >= 0 && k3 >= 0 && k4 >= 0 && k1 % tr == 0 && k2 % rot == 0 && k3 % rot == 0 && k4 % rot == 0 &&
+                  b1 < n1 && b2 < na && b3 < na && b4 < na && id1 >= 0 && id1 < M && id2 >= 0 && id2 < M && id1 != id2;
+  if (!ok) { keys[t] = ~0ull; atomicAdd(bad, 1ull); return; }
+  const uint32_t bin = (uint32_t)(((b1 * na + b2) * na + b3) * na + b4);
+  keys[t] = ((unsigned long long)bin << 32) | ((unsigned long long)id1 << 16) | (unsigned long long)id2;
+  atomicAdd(&counts[bin], 1u);
+}
+
 __global__ void ppf_strip_kernel(const unsigned long long* __restrict__ keys, long long n, uint32_t* __restrict__ pairs) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) pairs[t] = (uint32_t)(keys[t] & 0xffffffffull);
@@ -135,8 +153,9 @@ PpfView stocs_ppf_view(const stocs_b200_ctx* ctx) {
   return v;
 }
 
-// expects ctx->d_tmp = raw (un-centred) model pos3, ctx->d_mnrm4 = normals
-int stocs_build_ppf_table(stocs_b200_ctx* ctx) {
+// expects ctx->d_tmp = raw (un-centred) model pos3, ctx->d_mnrm4 = normals -- or, with list_n >= 0, a
+// caller-provided table (device arrays d_keys4 / d_pairs2 of list_n entries) instead of the pair loop
+static int build_ppf_table(stocs_b200_ctx* ctx, const int* d_keys4, const int* d_pairs2, long long list_n) {
   const int M = ctx->M;
   cudaStream_t st = ctx->stream;
   // bound on f1: the model diagonal (centred AABB == raw AABB extents up to rounding; add slack)
@@ -157,7 +176,7 @@ int stocs_build_ppf_table(stocs_b200_ctx* ctx) {
   const long long nkeybits = (long long)(n1 + 1) * (na + 1) * (na + 1) * (na + 1);
   if (nbins > (1ll << 30)) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_model: PPF bin space too large (coarser discretisation needed)");
   ctx->ppf.n1 = n1; ctx->ppf.na = na; ctx->ppf.tr = tr; ctx->ppf.rot = rot;
-  const long long MM = (long long)M * M;
+  const long long MM = list_n >= 0 ? (list_n > 0 ? list_n : 1) : (long long)M * M;
   STOCS_CUDA(ctx, ctx->d_ppf_bin_start.ensure((size_t)(nbins + 1) * 4));
   STOCS_CUDA(ctx, ctx->d_ppf_keybits.ensure((size_t)((nkeybits + 31) / 32) * 4));
   STOCS_CUDA(ctx, ctx->d_work.ensure((size_t)(nbins + 1) * 4));
@@ -167,8 +186,22 @@ int stocs_build_ppf_table(stocs_b200_ctx* ctx) {
   uint32_t* counts = ctx->d_work.as<uint32_t>();
   STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)(nbins + 1) * 4, st));
   STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_ppf_keybits.p, 0, (size_t)((nkeybits + 31) / 32) * 4, st));
-  ppf_pairs_kernel<<<(unsigned)((MM + 255) / 256), 256, 0, st>>>(ctx->d_tmp.as<float>(), ctx->d_mnrm4.as<float4>(), M, n1,
-                                                                  na, tr, rot, keys_a.as<unsigned long long>(), counts);
+  if (list_n >= 0) {
+    unsigned long long* d_bad = (unsigned long long*)(ctx->d_small.as<char>() + 272);
+    STOCS_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 8, st));
+    STOCS_CUDA(ctx, cudaMemsetAsync(keys_a.p, 0xff, (size_t)MM * 8, st));
+    if (list_n > 0)
+      ppf_from_list_kernel<<<(unsigned)((list_n + 255) / 256), 256, 0, st>>>(d_keys4, d_pairs2, list_n, M, n1, na, tr, rot,
+                                                                             keys_a.as<unsigned long long>(), counts, d_bad);
+    unsigned long long bad = 0;
+    STOCS_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (bad) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_ppf_table: " + std::to_string(bad) + " entries do not fit this model / discretisation "
+                                          "(ids >= |M|, keys off the bin lattice or beyond the model diagonal)");
+  } else {
+    ppf_pairs_kernel<<<(unsigned)((MM + 255) / 256), 256, 0, st>>>(ctx->d_tmp.as<float>(), ctx->d_mnrm4.as<float4>(), M, n1,
+                                                                    na, tr, rot, keys_a.as<unsigned long long>(), counts);
+  }
   size_t tb = 0, tb2 = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, tb, keys_a.as<unsigned long long>(), keys_b.as<unsigned long long>(), (int)MM, 0, 64, st);
   cub::DeviceScan::ExclusiveSum(nullptr, tb2, counts, ctx->d_ppf_bin_start.as<uint32_t>(), (int)(nbins + 1), st);
@@ -199,7 +232,41 @@ int stocs_build_ppf_table(stocs_b200_ctx* ctx) {
   return STOCS_OK;
 }
 
+int stocs_build_ppf_table(stocs_b200_ctx* ctx) { return build_ppf_table(ctx, nullptr, nullptr, -1); }
+
 extern "C" {
+
+// The table a caller preloaded (reference: ppf_map_preloaded, src/stocs.cpp:94) replaces the one
+// upload_model derived from the points.  A table that cannot belong to this model is an error, never
+// silently ignored.  On failure the context keeps no PPF table (M is reset: upload the model again).
+int stocs_b200_upload_ppf_table(stocs_b200_ctx* ctx, const int32_t* keys4, const int32_t* pairs2, int64_t n,
+                                int tr_discretization, int rot_discretization, int num_model_points) {
+  if (!ctx) return STOCS_E_ARG;
+  if (ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "upload_ppf_table: upload_model first");
+  if (n < 0 || (n > 0 && (!keys4 || !pairs2))) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_ppf_table: bad argument");
+  if (tr_discretization != ctx->tr || rot_discretization != ctx->rot)
+    STOCS_FAIL(ctx, STOCS_E_ARG, "upload_ppf_table: the table was built with discretisation (" + std::to_string(tr_discretization) + ", " +
+                                     std::to_string(rot_discretization) + "), the estimator uses (" + std::to_string(ctx->tr) + ", " +
+                                     std::to_string(ctx->rot) + ")");
+  if (num_model_points != ctx->M)
+    STOCS_FAIL(ctx, STOCS_E_ARG, "upload_ppf_table: the table was built for " + std::to_string(num_model_points) +
+                                     " model points, the uploaded model has " + std::to_string(ctx->M));
+  if (n >= (1ll << 31)) STOCS_FAIL(ctx, STOCS_E_ARG, "upload_ppf_table: too many entries");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  DevBuf dk, dp;
+  cudaError_t e = dk.ensure((size_t)(n ? n : 1) * 16);
+  if (e == cudaSuccess) e = dp.ensure((size_t)(n ? n : 1) * 8);
+  if (e == cudaSuccess && n) e = cudaMemcpyAsync(dk.p, keys4, (size_t)n * 16, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n) e = cudaMemcpyAsync(dp.p, pairs2, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+  int rc = STOCS_OK;
+  if (e != cudaSuccess) { ctx->err = std::string("upload_ppf_table: ") + cudaGetErrorString(e); rc = STOCS_E_CUDA; }
+  if (rc == STOCS_OK) rc = build_ppf_table(ctx, dk.as<int>(), dp.as<int>(), n);
+  cudaStreamSynchronize(st);
+  dk.release(); dp.release();
+  if (rc != STOCS_OK) { ctx->M = 0; ctx->ppf = PpfTableDesc{}; }
+  return rc;
+}
 
 int stocs_b200_ppf_num_pairs(stocs_b200_ctx* ctx, int64_t* own_bin_pairs, int64_t* own_bin_keys) {
   if (!ctx) return STOCS_E_ARG;

@@ -365,4 +365,15 @@ int stocs_b200_get_class_probability(stocs_b200_ctx* ctx, float* out) {
   return STOCS_OK;
 }
 
+// replica maintenance for multi-GPU runs: overwrite the per-point class probability (the w component
+// of the scene attribute records) with values read from another context
+int stocs_b200_set_class_probability(stocs_b200_ctx* ctx, const float* cls) {
+  if (!ctx || !cls) return STOCS_E_ARG;
+  if (ctx->S <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "no scene");
+  cudaSetDevice(ctx->device);
+  STOCS_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_sattr.as<char>() + 12, 16, cls, 4, 4, (size_t)ctx->S, cudaMemcpyHostToDevice, ctx->stream));
+  STOCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return STOCS_OK;
+}
+
 }  // extern "C"

@@ -68,6 +68,7 @@ struct ScoreArgs {
   GridDesc g;
   int M, Mpad;
   float sq_eps, dot_thr;
+  float to_block, to_cell;   // 2^-coarse_shift and 2^coarse_shift (exact scalings, see loop 1)
 };
 
 // kdtree.h:394-459 on the device (tie path only).
@@ -184,7 +185,12 @@ struct WarpQueue {   // one per warp, shared memory (single base register, const
   float G[12];           // the same map into grid-cell coordinates (FMA-evaluated, phase A only)
   uint32_t a0[kQueue];   // occupied-cell rank of the queued query
   uint32_t pi[kQueue];   // model point index of the queued query
+#ifdef SCORE_ATOM32
+  uint32_t best_d[32];   // drain: min over hits of the d^2 bit pattern (native 32-bit shared atomicMin)
+  uint32_t best_i[32];   //        scene index of a candidate that attains it
+#else
   unsigned long long best[32];  // drain: min over hits of (d^2 bit pattern << 32 | scene index), atomicMin
+#endif
   uint8_t plist[256];    // phase A: survivors of the coarse test within the current 256-point block
 };
 
@@ -235,7 +241,11 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
       qy = ((q.T[1] * mp.x + q.T[4] * mp.y) + q.T[7] * mp.z) + q.T[10];
       qz = ((q.T[2] * mp.x + q.T[5] * mp.y) + q.T[8] * mp.z) + q.T[11];
     }
+#ifdef SCORE_ATOM32
+    q.best_d[lane] = 0xffffffffu;
+#else
     q.best[lane] = ~0ull;
+#endif
     uint32_t pre = cnt;         // inclusive scan of the counts -> exclusive prefix
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -261,10 +271,27 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
       const float ox = __shfl_sync(0xffffffffu, qx, src), oy = __shfl_sync(0xffffffffu, qy, src),
                   oz = __shfl_sync(0xffffffffu, qz, src);
       const uint32_t os = __shfl_sync(0xffffffffu, s, src), op = __shfl_sync(0xffffffffu, pre, src);
+#ifdef SCORE_ATOM32
+      bool hit = false;
+      uint32_t hb = 0, hi = 0;
+#endif
       if (f < total) {
         const float4 c = LD_CAND(a.cand + os + (f - op));
         const float dx = ox - c.x, dy = oy - c.y, dz = oz - c.z;
         const float d = dx * dx + (dy * dy + dz * dz);
+#ifdef SCORE_ATOM32
+        // (d^2 >= 0, so its bit pattern orders like the value.)  The minimum is taken with the
+        // native 32-bit shared atomic; a candidate that meets its own d^2 already stored is an exact
+        // tie (flag); after the trip's atomics, whoever equals the minimum records its index.
+        hit = d <= sq_eps;
+        hb = __float_as_uint(d); hi = __float_as_uint(c.w);
+        if (hit && atomicMin(&q.best_d[src], hb) == hb) flag |= 1u << src;
+      }
+      __syncwarp();
+      if (hit && q.best_d[src] == hb) q.best_i[src] = hi;
+      __syncwarp();
+    }
+#else
         if (d <= sq_eps) {
           const uint32_t b = __float_as_uint(d), ci = __float_as_uint(c.w);
           const unsigned long long old = atomicMin(&q.best[src], ((unsigned long long)b << 32) | ci);
@@ -272,14 +299,22 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
         }
       }
     }
+#endif
     __syncwarp();
     flag = __reduce_or_sync(0xffffffffu, flag);
     // 3.
     bool match = false;
     float w = 0.f;
+#ifdef SCORE_ATOM32
+    const bool found = q.best_d[lane] != 0xffffffffu;
+    if (has && found) {
+      int res = (int)q.best_i[lane];
+#else
     const unsigned long long mine = q.best[lane];
-    if (has && mine != ~0ull) {
+    const bool found = mine != ~0ull;
+    if (has && found) {
       int res = (int)(uint32_t)mine;
+#endif
       if ((flag >> lane) & 1u) {
         res = kd_query_dev(a.kd_nodes, a.kd_pts, qx, qy, qz, sq_eps);
         r.ties++;
@@ -298,7 +333,7 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
       }
     }
     unsigned mm = __ballot_sync(0xffffffffu, match);
-    if (kCount) count<kCount>(a, lane, SC_HITS, __popc(__ballot_sync(0xffffffffu, has && mine != ~0ull)));
+    if (kCount) count<kCount>(a, lane, SC_HITS, __popc(__ballot_sync(0xffffffffu, has && found)));
     count<kCount>(a, lane, SC_INLIERS, __popc(mm));
     r.inl += __popc(mm);
     while (mm) {  // ordered fp32 accumulation == the reference's sequential loop
@@ -351,7 +386,11 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
       const float t = __ldg(a.T + 16 * (size_t)h + c * 4 + rr);
       const float o = (rr == 0) ? a.g.ox : (rr == 1 ? a.g.oy : a.g.oz);
       q.T[lane] = t;
-      q.G[lane] = (c == 3) ? (t - o) * a.g.inv_cell : t * a.g.inv_cell;
+      // G maps into BLOCK coordinates (cell coordinates * 2^-coarse_shift): loop 1 floors it straight
+      // to the coarse-map index; loop 2 multiplies by 2^coarse_shift first.  Scaling by a power of two
+      // commutes with every rounding of the FMA chain, so the cell found is bit-identical to mapping
+      // with the unscaled G.
+      q.G[lane] = ((c == 3) ? (t - o) * a.g.inv_cell : t * a.g.inv_cell) * a.to_block;
     }
     __syncwarp();
     float g0 = q.G[0], g1 = q.G[1], g2 = q.G[2], g3 = q.G[3], g4 = q.G[4], g5 = q.G[5];
@@ -376,10 +415,9 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
         const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
         const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy), iz = (unsigned)__float2int_rd(fz);
         // block coordinates clamped to the always-empty border block (index = number of real
-        // blocks): no bounds test, no branch; cells left of the grid are huge as unsigned
-        const unsigned k = (unsigned)a.coarse_shift;
-        const unsigned cx = min(ix >> k, (unsigned)a.coarse_nx), cy = min(iy >> k, (unsigned)a.coarse_ny),
-                       cz = min(iz >> k, (unsigned)a.coarse_nz);
+        // blocks): no bounds test, no branch; blocks left of the grid are huge as unsigned
+        const unsigned cx = min(ix, (unsigned)a.coarse_nx), cy = min(iy, (unsigned)a.coarse_ny),
+                       cz = min(iz, (unsigned)a.coarse_nz);
         const uint32_t cidx = (cz * (unsigned)a.coarse_sy + cy) * (unsigned)a.coarse_sx + cx;
         const bool pass = (s_coarse[cidx >> 5] >> (cidx & 31)) & 1u;
         const unsigned pm = __ballot_sync(0xffffffffu, pass);
@@ -395,7 +433,8 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
         const float fx = __fmaf_rn(g0, mp.x, __fmaf_rn(g3, mp.y, __fmaf_rn(g6, mp.z, g9)));
         const float fy = __fmaf_rn(g1, mp.x, __fmaf_rn(g4, mp.y, __fmaf_rn(g7, mp.z, g10)));
         const float fz = __fmaf_rn(g2, mp.x, __fmaf_rn(g5, mp.y, __fmaf_rn(g8, mp.z, g11)));
-        const unsigned ix = (unsigned)__float2int_rd(fx), iy = (unsigned)__float2int_rd(fy), iz = (unsigned)__float2int_rd(fz);
+        const unsigned ix = (unsigned)__float2int_rd(fx * a.to_cell), iy = (unsigned)__float2int_rd(fy * a.to_cell),
+                       iz = (unsigned)__float2int_rd(fz * a.to_cell);
         uint4 br = make_uint4(0u, 0u, 0u, 0u);
         const unsigned bidx = ((iz >> 2) * (unsigned)a.g.nby + (iy >> 2)) * (unsigned)a.g.nbx + (ix >> 2);
 #ifdef SCORE_BRICK_OCC
@@ -499,6 +538,8 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.Mpad = ctx->Mpad;
   a.sq_eps = ctx->eps * ctx->eps;
   a.dot_thr = ctx->dot_thr;
+  a.to_block = 1.0f / (float)(1u << ctx->coarse_shift);
+  a.to_cell = (float)(1u << ctx->coarse_shift);
   size_t smem = (size_t)4 * ctx->Mpad * 4 + (size_t)((a.coarse_words + 3) & ~3) * 4 + (size_t)kWarps * sizeof(WarpQueue);
   // static (per-warp queues) + dynamic (model, coarse bitmap) may exceed the 48 KB default
   // d_counters != NULL selects the counting variant (same code + one global atomic per warp event)

@@ -16,8 +16,22 @@
 
 namespace rgbd {
 
+std::string remap_path(const std::string& path) {
+  const char* e = std::getenv("STOCS_PATH_REMAP");
+  if (!e) return path;
+  std::stringstream rules(e);
+  for (std::string rule; std::getline(rules, rule, ';');) {
+    const size_t eq = rule.find('=');
+    if (eq == std::string::npos || eq == 0) continue;
+    const std::string from = rule.substr(0, eq), to = rule.substr(eq + 1);
+    if (path.compare(0, from.size(), from) == 0) return to + path.substr(from.size());
+  }
+  return path;
+}
+
 // ---- PLY -------------------------------------------------------------------------------------
-bool load_ply_file(const std::string& location, PCLPointCloud& cloud) {
+bool load_ply_file(const std::string& location_in, PCLPointCloud& cloud) {
+  const std::string location = remap_path(location_in);
   std::ifstream f(location);
   if (!f) return false;
   std::string line;
@@ -68,6 +82,7 @@ void load_ply_model(PCLPointCloud::Ptr cloud, std::vector<Point3D>& point3d, flo
 // reference src/rgbd.cpp:35-56; ASCII PointXYZRGBNormal layout as pcl::io::savePLYFile writes it.
 // Floats are printed with 9 significant digits so that a write/read round trip is exact.
 void save_as_ply(std::string location, std::vector<Point3D>& point3d, float scale) {
+  location = remap_path(location);
   FILE* f = fopen(location.c_str(), "w");
   if (!f) { std::cerr << "save_as_ply: cannot write " << location << std::endl; return; }
   fprintf(f, "ply\nformat ascii 1.0\ncomment PCL generated\nelement vertex %zu\n", point3d.size());
@@ -109,6 +124,7 @@ void ppf_compute(Point3D p1, Point3D p2, float tr, float rot, std::vector<int>& 
 // ---- compact PPF table file ("ppf_map"), replaces the Boost archive of src/rgbd.cpp:156-177 ----
 static const char kMagic[8] = {'S', 'T', 'O', 'C', 'S', 'P', 'F', '1'};
 void save_ppf_map(std::string location, PPFMapType& m) {
+  location = remap_path(location);
   std::ofstream f(location, std::ios::binary);
   if (f.fail()) return;
   int64_t n = (int64_t)(m.pairs2.size() / 2);
@@ -121,6 +137,7 @@ void save_ppf_map(std::string location, PPFMapType& m) {
   f.write((const char*)m.pairs2.data(), (std::streamsize)(n * 8));
 }
 void load_ppf_map(std::string location, PPFMapType& m) {
+  location = remap_path(location);
   std::ifstream f(location, std::ios::binary);
   m = PPFMapType();
   char magic[8];
@@ -267,6 +284,9 @@ void load_rgbd_data_sampled(std::string rgb_location, std::string depth_location
   std::vector<uint8_t> bgr;
   std::vector<uint16_t> depth, prob;
   int W = 0, H = 0, w2 = 0, h2 = 0;
+  rgb_location = remap_path(rgb_location);
+  depth_location = remap_path(depth_location);
+  class_probability_map_location = remap_path(class_probability_map_location);
   if (!imgio::load_bgr8(rgb_location, bgr, W, H) || !imgio::load_gray16(depth_location, depth, w2, h2) || w2 != W || h2 != H) {
     std::cerr << "load_rgbd_data_sampled: cannot read " << rgb_location << " / " << depth_location << std::endl;
     return;

@@ -7,8 +7,19 @@
 // the number of keys of the reference's expanded map, which is what the reference prints.
 #ifndef STOCS_B200_RGBD_HPP_
 #define STOCS_B200_RGBD_HPP_
+// Standard headers that the reference's header chain (point3d.hpp, PCL, OpenCV, Boost) exposes and
+// that its callers rely on without including them (src/stocs_match_one_object.cpp uses struct stat,
+// std::ofstream, std::cout, std::random_shuffle, system): kept so that those callers compile unchanged.
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
 #include <memory>
 #include <string>
 #include <utility>
@@ -46,6 +57,11 @@ void load_rgbd_data_sampled(std::string rgb_location, std::string depth_location
                             std::vector<float> camera_intrinsics, float depth_scale, float voxel_size,
                             float class_probability_threshold, std::vector<Point3D>& point3d,
                             stocs_b200_ctx* ctx);
+
+// STOCS_PATH_REMAP="from=to[;from2=to2]": every path the shim opens has a leading `from` replaced by
+// `to`.  Lets a caller with a compiled-in repository path (the reference's CLIs,
+// src/stocs_match_one_object.cpp:4) run against a tree that lives elsewhere, without editing it.
+std::string remap_path(const std::string& path);
 
 bool load_ply_file(const std::string& location, PCLPointCloud& cloud);
 void load_ply_model(PCLPointCloud::Ptr cloud, std::vector<Point3D>& point3d, float scale);

@@ -16,7 +16,9 @@
 namespace stocs {
 
 void stocs_estimator::fail(const char* where) {
-  std::cerr << "libstocs_b200: " << where << ": " << stocs_b200_last_error(ctx_) << std::endl;
+  std::cerr << "libstocs_b200: " << where << ": " << stocs_b200_last_error(ctx_);
+  if (group_ && *stocs_b200_group_last_error(group_)) std::cerr << " / " << stocs_b200_group_last_error(group_);
+  std::cerr << std::endl;
   std::exit(2);  // no CPU fallback: a GPU failure is fatal, loudly
 }
 
@@ -40,14 +42,34 @@ stocs_estimator::stocs_estimator(std::string model_location, PPFMapType& ppf_map
   best_lcp = 0;
   best_index = -1;
 
-  const char* dev = std::getenv("STOCS_DEVICE");
-  int rc = stocs_b200_create(&ctx_, dev ? std::atoi(dev) : 0);
+  // STOCS_DEVICES="0,1,2,3": several GPUs (hypothesis sharding at compute_best_transform);
+  // STOCS_DEVICE=k: one GPU; default device 0
+  std::vector<int> devices;
+  if (const char* list = std::getenv("STOCS_DEVICES")) {
+    std::string tok;
+    for (const char* p = list;; ++p) {
+      if (*p == ',' || *p == 0) { if (!tok.empty()) devices.push_back(std::atoi(tok.c_str())); tok.clear(); if (!*p) break; }
+      else tok.push_back(*p);
+    }
+  }
+  int rc;
+  if (devices.size() > 1) {
+    rc = stocs_b200_group_create(&group_, devices.data(), (int)devices.size());
+    if (rc == 0) ctx_ = stocs_b200_group_ctx(group_, 0);
+  } else {
+    const char* dev = std::getenv("STOCS_DEVICE");
+    rc = stocs_b200_create(&ctx_, devices.size() == 1 ? devices[0] : (dev ? std::atoi(dev) : 0));
+  }
   if (rc != 0) {
     std::cerr << "libstocs_b200: cannot create a GPU context (" << rc << "): " << stocs_b200_last_error(nullptr)
               << "\nThis build has no CPU path." << std::endl;
     std::exit(2);
   }
-  if (stocs_b200_set_params(ctx_, distance_threshold, ppf_tr_discretization, ppf_rot_discretization) != 0) fail("set_params");
+  if (group_) {
+    if (stocs_b200_group_set_params(group_, distance_threshold, ppf_tr_discretization, ppf_rot_discretization) != 0) fail("set_params");
+  } else if (stocs_b200_set_params(ctx_, distance_threshold, ppf_tr_discretization, ppf_rot_discretization) != 0) {
+    fail("set_params");
+  }
   const char* seed = std::getenv("STOCS_SEED");
   seed_ = seed ? std::strtoull(seed, nullptr, 10)
                : (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();  // src/stocs.cpp:135
@@ -62,7 +84,9 @@ stocs_estimator::stocs_estimator(std::string model_location, PPFMapType& ppf_map
 }
 
 stocs_estimator::~stocs_estimator() {
-  if (ctx_) stocs_b200_destroy(ctx_);  // PoseCandidate* are left to the caller, as in the reference
+  // PoseCandidate* are left to the caller, as in the reference
+  if (group_) stocs_b200_group_destroy(group_);
+  else if (ctx_) stocs_b200_destroy(ctx_);
 }
 
 void stocs_estimator::load_object_info(std::string model_location, PPFMapType& ppf_map_preloaded) {
@@ -119,8 +143,21 @@ void stocs_estimator::centroid_shift() {
       fclose(f);
     }
   }
-  if (stocs_b200_upload_model(ctx_, mp.data(), mn.data(), (int)M) != 0) fail("upload_model");
-  if (stocs_b200_upload_scene(ctx_, sp.data(), sn.data(), sc.data(), pix.data(), (int)S) != 0) fail("upload_scene");
+  if (group_) {  // every device holds a replica of the model tables and the scene index
+    if (stocs_b200_group_upload_model(group_, mp.data(), mn.data(), (int)M) != 0) fail("upload_model");
+    if (stocs_b200_group_upload_scene(group_, sp.data(), sn.data(), sc.data(), pix.data(), (int)S) != 0) fail("upload_scene");
+  } else {
+    if (stocs_b200_upload_model(ctx_, mp.data(), mn.data(), (int)M) != 0) fail("upload_model");
+    if (stocs_b200_upload_scene(ctx_, sp.data(), sn.data(), sc.data(), pix.data(), (int)S) != 0) fail("upload_scene");
+  }
+  // The preloaded map is THE table (reference: ppf_map = ppf_map_preloaded, src/stocs.cpp:94).  An
+  // empty one (no file) leaves the table upload_model derived from the points; one that does not
+  // fit the model or the discretisations stops the run.
+  if (!ppf_map.empty()) {
+    if (stocs_b200_upload_ppf_table(ctx_, ppf_map.keys4.data(), ppf_map.pairs2.data(), (int64_t)(ppf_map.pairs2.size() / 2),
+                                    ppf_map.tr_discretization, ppf_map.rot_discretization, ppf_map.num_model_points) != 0)
+      fail("upload_ppf_table (re-run model_preprocess for this model and these discretisations)");
+  }
   float cs[3], cm[3];
   if (stocs_b200_get_centroids(ctx_, cs, cm) != 0) fail("get_centroids");
   if (stocs_b200_get_centred(ctx_, sp.data(), mp.data()) != 0) fail("get_centred");
@@ -128,11 +165,6 @@ void stocs_estimator::centroid_shift() {
   centroid_model_ = VectorType(cm[0], cm[1], cm[2]);
   for (size_t i = 0; i < S; ++i) point3d_scene[i].pos() = VectorType(sp[3 * i], sp[3 * i + 1], sp[3 * i + 2]);
   for (size_t i = 0; i < M; ++i) point3d_model[i].pos() = VectorType(mp[3 * i], mp[3 * i + 1], mp[3 * i + 2]);
-  int64_t pairs = 0, bins = 0;
-  stocs_b200_ppf_num_pairs(ctx_, &pairs, &bins);
-  if (!ppf_map.empty() && (int64_t)(ppf_map.pairs2.size() / 2) != pairs)
-    std::cerr << "warning: ppf_map file holds " << ppf_map.pairs2.size() / 2 << " pairs, the model yields " << pairs
-              << " (stale ppf_map? re-run model_preprocess)" << std::endl;
 }
 
 void stocs_estimator::kdtree_initialize() {
@@ -281,12 +313,27 @@ void stocs_estimator::compute_best_transform() {
   if (H > 0) {
     std::vector<float> T((size_t)H * 16), lcp((size_t)H);
     for (int64_t i = 0; i < H; ++i) std::memcpy(&T[16 * i], all_transforms[i].data(), 64);
-    if (stocs_b200_score_lcp(ctx_, T.data(), H, lcp.data(), nullptr) != 0) fail("score_lcp");
-    for (int64_t i = 0; i < H; ++i) all_pose[i]->lcp = lcp[i];
     int64_t bi = -1;
     float bl = 0;
-    int64_t ti[1]; float tl[1];
-    if (stocs_b200_reduce_best(ctx_, nullptr, H, 1, &bi, &bl, ti, tl) != 0) fail("reduce_best");
+    if (group_) {
+      // instance sampling decays the class prior on device 0 only; LCP uses the decayed values
+      // (src/stocs.cpp:577,1033), so the other replicas are brought up to date first
+      if (class_prob_dirty_) {
+        std::vector<float> cls(point3d_scene.size());
+        if (stocs_b200_get_class_probability(ctx_, cls.data()) != 0) fail("get_class_probability");
+        for (int d = 1; d < stocs_b200_group_size(group_); ++d)
+          if (stocs_b200_set_class_probability(stocs_b200_group_ctx(group_, d), cls.data()) != 0) fail("set_class_probability");
+      }
+      stocs_b200_record top;
+      if (stocs_b200_group_score_best(group_, T.data(), H, 1, &top, lcp.data(), nullptr) != 0) fail("group_score_best");
+      bi = top.index;
+      bl = top.lcp;
+    } else {
+      if (stocs_b200_score_lcp(ctx_, T.data(), H, lcp.data(), nullptr) != 0) fail("score_lcp");
+      int64_t ti[1]; float tl[1];
+      if (stocs_b200_reduce_best(ctx_, nullptr, H, 1, &bi, &bl, ti, tl) != 0) fail("reduce_best");
+    }
+    for (int64_t i = 0; i < H; ++i) all_pose[i]->lcp = lcp[i];
     best_lcp = bl;
     best_index = (int)bi;
   }
@@ -302,18 +349,24 @@ void stocs_estimator::visualize_best_pose() {
   rgbd::save_as_ply(debug_location + "/scene.ply", point3d_scene, 1);
 }
 
+bool load_and_sample_model(std::string src_model_location, float normal_radius, float read_depth_scale, float voxel_size,
+                           std::vector<Point3D>& point3d_sampled) {
+  PCLPointCloud::Ptr cloud(new PCLPointCloud);
+  if (!rgbd::load_ply_file(src_model_location, *cloud)) { std::cerr << "cannot read " << src_model_location << std::endl; return false; }
+  rgbd::compute_normal_pcl(cloud, normal_radius);
+  for (auto& p : cloud->points) { p.nx = -p.nx; p.ny = -p.ny; p.nz = -p.nz; }  // normals face outside
+  rgbd::voxel_grid_filter(*cloud, voxel_size);
+  rgbd::load_ply_model(cloud, point3d_sampled, read_depth_scale);
+  return true;
+}
+
 // src/stocs.cpp:28-84.  Normal estimation and voxel-grid down-sampling are host restatements of
 // the PCL operators; the O(|M|^2) pair loop runs on the GPU (ppf_table.cu).
 void pre_process_model(std::string src_model_location, float normal_radius, float read_depth_scale,
                        float write_depth_scale, float voxel_size, float ppf_tr_discretization,
                        float ppf_rot_discretization, std::string dst_model_location, std::string dst_ppf_map_location) {
   std::vector<Point3D> point3d_sampled;
-  PCLPointCloud::Ptr cloud(new PCLPointCloud);
-  if (!rgbd::load_ply_file(src_model_location, *cloud)) { std::cerr << "cannot read " << src_model_location << std::endl; return; }
-  rgbd::compute_normal_pcl(cloud, normal_radius);
-  for (auto& p : cloud->points) { p.nx = -p.nx; p.ny = -p.ny; p.nz = -p.nz; }  // normals face outside
-  rgbd::voxel_grid_filter(*cloud, voxel_size);
-  rgbd::load_ply_model(cloud, point3d_sampled, read_depth_scale);
+  if (!load_and_sample_model(src_model_location, normal_radius, read_depth_scale, voxel_size, point3d_sampled)) return;
   std::cout << "After sampling |M|= " << point3d_sampled.size() << std::endl;
 
   stocs_b200_ctx* ctx = nullptr;

@@ -5,7 +5,11 @@
 // run_stocs_estimation in src/stocs_match_one_object.cpp:51-185 -- compile unchanged.
 //
 // Differences a caller can observe (all documented in DESIGN.md):
-//  * PPFMapType is the compact own-bin table, not a std::map (rgbd.hpp).
+//  * PPFMapType is the compact own-bin table, not a std::map (rgbd.hpp).  A non-empty
+//    ppf_map_preloaded IS the table used online (uploaded with stocs_b200_upload_ppf_table); one
+//    that does not belong to the model or the discretisations is a fatal error, never ignored.
+//  * STOCS_DEVICES="0,1,..": compute_best_transform() shards the hypotheses over those GPUs
+//    (stocs_b200_group_*: replicas of the scene index, one NCCL all-gather of the best records).
 //  * Sampling is keyed by (seed, base number) instead of the wall clock; the seed comes from the
 //    environment variable STOCS_SEED when set, else from the clock as in the reference.
 //  * sample_class_base draws bases 128 at a time in one launch and find_congruent_sets_on_model
@@ -23,6 +27,8 @@
 
 #include "image_io.hpp"
 #include "rgbd.hpp"
+
+struct stocs_b200_group;  // libstocs_b200 multi-GPU group (include/stocs_b200.h)
 
 using Scalar = typename Point3D::Scalar;
 using MatrixType = Eigen::Matrix<Scalar, 4, 4>;
@@ -99,7 +105,8 @@ class stocs_estimator {
   int image_width, image_height;
 
   // GPU state
-  struct stocs_b200_ctx* ctx_ = nullptr;
+  ::stocs_b200_ctx* ctx_ = nullptr;        // device 0 of group_ when there is one
+  ::stocs_b200_group* group_ = nullptr;    // STOCS_DEVICES with more than one entry
   uint64_t seed_ = 0;
   uint32_t next_base_no_ = 0;
   // class-mode prefetch: bases sampled kPrefetch at a time, congruent sets batched over them
@@ -119,6 +126,9 @@ class stocs_estimator {
   std::vector<int> pending_base_index_;
 };
 
+// host half of pre_process_model (src/stocs.cpp:41-60): load, normals, flip, voxel grid, point list
+bool load_and_sample_model(std::string src_model_location, float normal_radius, float read_depth_scale, float voxel_size,
+                           std::vector<Point3D>& point3d_sampled);
 void pre_process_model(std::string src_model_location, float normal_radius, float read_depth_scale,
                        float write_depth_scale, float voxel_size, float ppf_tr_discretization,
                        float ppf_rot_discretization, std::string dst_model_location,

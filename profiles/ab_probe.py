@@ -1,28 +1,36 @@
-"""A/B timing of score-kernel build variants on the S1 workload (development tool, not a test).
-Build each variant as gpurun_variants/lib_<name>.so (nvcc line of csrc/Makefile plus -D switches,
-e.g. -DSCORE_NO_L2_HINTS), then on the GPU box:
-    echo base nohints base@0.6 | python profiles/ab_probe.py
-Each variant runs in its own process (STOCS_B200_LIB selects the library, name@scale also sets
-STOCS_CELL_SCALE); prints ms per 10^6 hypotheses and a hash of the results, which must not change."""
-import sys, os, time, ctypes, subprocess, json
-if len(sys.argv)>1:
-    sys.path.insert(0,'.')
+"""A/B timing of score-kernel build variants on the S1 and S1-fit workloads (development tool).
+Build variants with profiles/build_variants.sh, then on the GPU box:
+    echo base atom32 w16b3 | python profiles/ab_probe.py
+Each variant runs in its own process (STOCS_B200_LIB selects the library); prints ms per 10^6
+hypotheses for both workloads and a hash of the results, which must not change between variants.
+The S1-fit hypotheses are generated once (first variant) and cached in /tmp."""
+import sys, os, time, ctypes, subprocess
+if len(sys.argv) > 1:
+    sys.path.insert(0, '.')
     import numpy as np, torch, bench, hashlib
     from model_matching_b200 import Context
-    sc,mpos,mnrm,T=bench.workload(0,1000000); H=len(T)
-    ctx=Context(0); ctx.upload_model(mpos,mnrm); ctx.upload_scene(sc['pos'],sc['nrm'],sc['cls'])
-    dT=torch.from_numpy(T).cuda(); dl=torch.empty(H,dtype=torch.float32,device='cuda'); di=torch.empty(H,dtype=torch.int32,device='cuda')
-    s=torch.cuda.Stream()
+    sc, mpos, mnrm, T = bench.workload(0, 1000000); H = len(T)
+    ctx = Context(0); ctx.upload_model(mpos, mnrm); ctx.upload_scene(sc['pos'], sc['nrm'], sc['cls'])
+    fitp = '/tmp/s1fit_T.npy'
+    if not os.path.exists(fitp):
+        Tf, info = bench.fitted_hypotheses(ctx, H)
+        np.save(fitp, Tf)
+    Tf = np.load(fitp)
+    s = torch.cuda.Stream()
+    out = '%-16s' % sys.argv[1]
     with torch.cuda.stream(s):
-        sp=ctypes.c_void_p(s.cuda_stream)
-        for _ in range(3): ctx.score_lcp_device(dT.data_ptr(),H,dl.data_ptr(),di.data_ptr(),sp)
-        torch.cuda.synchronize(); t=time.perf_counter()
-        for _ in range(20): ctx.score_lcp_device(dT.data_ptr(),H,dl.data_ptr(),di.data_ptr(),sp)
-        torch.cuda.synchronize(); ms=(time.perf_counter()-t)/20*1e3
-    print('%-14s %.3f ms  lcp sha %s inl sum %d'%(sys.argv[1],ms,hashlib.sha1(dl.cpu().numpy().tobytes()).hexdigest()[:10],int(di.sum())),flush=True)
+        sp = ctypes.c_void_p(s.cuda_stream)
+        for name, TT in (('S1', T), ('S1-fit', Tf)):
+            dT = torch.from_numpy(TT).cuda(); dl = torch.empty(H, dtype=torch.float32, device='cuda'); di = torch.empty(H, dtype=torch.int32, device='cuda')
+            for _ in range(3): ctx.score_lcp_device(dT.data_ptr(), H, dl.data_ptr(), di.data_ptr(), sp)
+            torch.cuda.synchronize(); ctx.kernel_ms_stats(reset=True)
+            for _ in range(20): ctx.score_lcp_device(dT.data_ptr(), H, dl.data_ptr(), di.data_ptr(), sp)
+            torch.cuda.synchronize(); n, ms, mx = ctx.kernel_ms_stats()
+            out += ' | %s %.3f ms (max %.3f) lcp %s inl %d' % (name, ms, mx, hashlib.sha1(dl.cpu().numpy().tobytes()).hexdigest()[:8], int(di.sum()))
+    print(out, flush=True)
 else:
     for v in sys.stdin.read().split():
-        lib,_,sc=v.partition('@')
-        env=dict(os.environ,STOCS_B200_LIB=os.path.abspath('gpurun_variants/lib_%s.so'%lib))
-        if sc: env['STOCS_CELL_SCALE']=sc
-        subprocess.run([sys.executable,'profiles/ab_probe.py',v],env=env)
+        lib, _, scale = v.partition('@')
+        env = dict(os.environ, STOCS_B200_LIB=os.path.abspath('gpurun_variants/lib_%s.so' % lib))
+        if scale: env['STOCS_CELL_SCALE'] = scale
+        subprocess.run([sys.executable, 'profiles/ab_probe.py', v], env=env)

@@ -1,0 +1,205 @@
+"""Numerical check of the drop-in C++ shim (model_matching_b200/host/stocs.cpp) -- the layer the
+reference's callers talk to.  stocs_single drives stocs::stocs_estimator through the reference's
+per-call sequence (src/stocs_match_one_object.cpp:79-165: sample_*_base per base,
+find_congruent_sets_on_model per base, get_rigid_transform_from_congruent_pair per picked quad,
+compute_best_transform) and, with STOCS_TRACE_FILE, dumps every intermediate.  The same sequence is
+then composed from the oracle's stages on the very point sets the shim uploaded (STOCS_DUMP_INPUTS)
+and everything is compared bit for bit: bases, invariants, quad lists, picks, centred and world
+transforms, LCP of every hypothesis, winner.  This covers the shim's prefetch of 128 bases, its
+batched congruent-set cache and its deferred fits, on the reference's three example scenes (class
+mode: ycb, linemod; instance mode: packed) and with the reference's own quad selection (quirk 5)."""
+import os
+import shutil
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "model_matching_b200", "host")
+SEED = 7
+
+SCENES = {
+    "ycb": ("024_bowl", {}),
+    "linemod": ("obj_06", {"STOCS_CAM_INTRINSICS": "572.4114,325.2611,573.57043,242.04899", "STOCS_DEPTH_SCALE": "0.001",
+                           "STOCS_MODEL_VOXEL_SIZE": "10", "STOCS_NORMAL_RADIUS": "5", "STOCS_MODEL_SCALE": "0.001"}),
+    "packed": ("dove", {"STOCS_CAM_INTRINSICS": "615.957763671875,308.1098937988281,615.9578247070312,246.33352661132812",
+                        "STOCS_DEPTH_SCALE": "0.000125", "STOCS_MODEL_VOXEL_SIZE": "0.005"}),
+}
+
+
+def make_tree(tmp, scene, obj):
+    repo = os.path.join(tmp, "repo")
+    shutil.copytree(os.path.join(ROOT, "tests", "golden", "examples", scene), os.path.join(repo, "examples", scene))
+    os.makedirs(os.path.join(repo, "models", obj))
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "models", obj, "textured_vertices.ply"), os.path.join(repo, "models", obj))
+    return repo, os.path.join(repo, "examples", scene)
+
+
+def read_trace(path):
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"STOCSTR1"
+    o = 8
+
+    def take(fmt):
+        nonlocal o
+        v = struct.unpack_from("<" + fmt, raw, o)
+        o += struct.calcsize("<" + fmt)
+        return v
+
+    def arr(n, dt):
+        nonlocal o
+        a = np.frombuffer(raw, dt, n, o).copy()
+        o += a.nbytes
+        return a
+
+    t = {}
+    n, = take("i")
+    t["attempts"] = [(bool(take("B")[0]), arr(4, np.int32), arr(2, np.float32)) for _ in range(n)]
+    nv, = take("i")
+    t["bases"] = []
+    for _ in range(nv):
+        nq, = take("q")
+        quads = arr(4 * nq, np.int32).reshape(nq, 4)
+        npk, = take("q")
+        t["bases"].append((quads, arr(npk, np.int32)))
+    nT, = take("q")
+    rec = np.dtype([("Tc", np.float32, (16,)), ("Tw", np.float32, (16,)), ("lcp", np.float32), ("base", np.int32)])
+    t["T"] = arr(nT, rec)
+    t["best_index"], t["best_lcp"] = take("if")
+    assert o == len(raw)
+    return t
+
+
+def read_inputs(path):
+    from golden.make_golden import read_inputs as r
+    return r(path)
+
+
+def run_cli(tmp, scene, extra_env=None, preprocess=True):
+    obj, env_scene = SCENES[scene]
+    repo, scene_dir = make_tree(tmp, scene, obj)
+    env = dict(os.environ, STOCS_REPO_PATH=repo, STOCS_SEED=str(SEED), STOCS_TRACE_FILE=os.path.join(tmp, "trace.bin"),
+               STOCS_DUMP_INPUTS=os.path.join(tmp, "inputs.bin"), **env_scene, **(extra_env or {}))
+    if preprocess:
+        p = subprocess.run([os.path.join(HOST, "model_preprocess"), obj], env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+    p = subprocess.run([os.path.join(HOST, "stocs_single"), scene_dir, obj], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return read_trace(env["STOCS_TRACE_FILE"]), read_inputs(env["STOCS_DUMP_INPUTS"]), p.stdout, scene_dir, env
+
+
+def same(a, b):
+    return np.array_equal(np.ascontiguousarray(a, np.float32).view(np.uint32), np.ascontiguousarray(b, np.float32).view(np.uint32))
+
+
+def compose_with_oracle(d, trace, scene_dir, instance, max_sets=200, picks_from_trace=False):
+    """the reference's driver sequence, stage by stage, on the oracle"""
+    omap = oracle.PPFMap(d["mpos"], d["mnrm"])
+    est = oracle.Estimator(d["spos"], d["snrm"], d["scls"], d["mpos"], d["mnrm"], ppfmap=omap, spix=d["spix"])
+    if instance:
+        import cv2
+        est.set_edge_map(cv2.imread(os.path.join(scene_dir, "probability_maps", "edge.png"), cv2.IMREAD_GRAYSCALE))
+    bases = []
+    for i, (ok, ids, inv) in enumerate(trace["attempts"]):
+        if instance:
+            ook, oids, oinv, _, _ = est.sample_instance_base(SEED, i + 1, 0.9)
+        else:
+            ook, oids, oinv, _ = est.sample_class_base(SEED, i)
+        assert ook == ok, i
+        if ok:
+            assert np.array_equal(oids, ids) and same(oinv, inv), i
+            bases.append((oids, oinv))
+    assert len(bases) == len(trace["bases"]) and len(bases) >= 5
+    Tc, Tw, base_of = [], [], []
+    for b, ((ids, inv), (quads, picked)) in enumerate(zip(bases, trace["bases"])):
+        oq, _, _ = est.find_congruent(ids, inv[0], inv[1])
+        assert oq.shape == quads.shape and np.array_equal(oq, quads), b
+        n = len(oq)
+        want = list(range(n)) if n < max_sets else [(k * n) // max_sets for k in range(max_sets)]
+        if picks_from_trace:      # the reference's shuffle: libc rand(), checked against the reference binary instead
+            assert len(picked) == min(n, max_sets) and (n == 0 or (picked.min() >= 0 and picked.max() < n))
+            want = list(picked)
+        else:
+            assert list(picked) == want, b
+        for k in want:
+            ok, tc, tw = est.fit(ids, oq[k])
+            if ok:
+                Tc.append(tc); Tw.append(tw); base_of.append(b)
+    T = trace["T"]
+    assert len(T) == len(Tc) and len(Tc) > 0
+    assert same(T["Tc"], np.array(Tc)) and same(T["Tw"], np.array(Tw))
+    assert np.array_equal(T["base"], np.array(base_of, np.int32))
+    lcp, _ = est.score(np.array(Tc, np.float32), threads=os.cpu_count() or 1)     # instance mode: decayed priors
+    assert same(T["lcp"], lcp)
+    assert (trace["best_index"], trace["best_lcp"]) == oracle.best(lcp)
+    return len(bases), len(Tc)
+
+
+@pytest.mark.parametrize("scene", ["ycb", "linemod", "packed"])
+def test_shim_call_sequence_matches_oracle(tmp_path, scene):
+    trace, d, out, scene_dir, _ = run_cli(str(tmp_path), scene)
+    nb, nT = compose_with_oracle(d, trace, scene_dir, instance=(scene == "packed"))
+    assert f"Transforms to verify: {nT}" in out
+    # the pose file is the un-centred transform of the winner, 12 numbers, default ostream precision
+    pose = np.loadtxt(os.path.join(scene_dir, f"best_pose_candidate_{SCENES[scene][0]}.txt"))
+    tw = trace["T"]["Tw"][trace["best_index"]].reshape(4, 4).T[:3].reshape(12)
+    assert np.allclose(pose, tw, rtol=1e-5, atol=1e-6)
+
+
+def test_reference_quad_selection_flag(tmp_path):
+    """STOCS_REF_SHUFFLE=1 (quirk 5): same bases and quads, the reference's shuffled picks"""
+    trace, d, out, scene_dir, _ = run_cli(str(tmp_path), "ycb", {"STOCS_REF_SHUFFLE": "1", "STOCS_MAX_SETS": "40"})
+    compose_with_oracle(d, trace, scene_dir, instance=False, max_sets=40, picks_from_trace=True)
+    big = [(q, p) for q, p in trace["bases"] if len(q) >= 40]
+    assert big, "the workload must contain a base with more quads than the limit"
+    # an index vector of n zeros followed by 0..n-1: about half of the picks are quad 0
+    zeros = sum(int((p == 0).sum()) for _, p in big)
+    assert zeros >= 0.3 * 40 * len(big)
+
+
+def test_preloaded_ppf_map_is_the_table_used(tmp_path):
+    """the map handed to the estimator is honoured: a map of another model / discretisation stops the
+    run with a message (reference: ppf_map = ppf_map_preloaded, src/stocs.cpp:94)"""
+    tmp = str(tmp_path)
+    trace, d, out, scene_dir, env = run_cli(tmp, "ycb")
+    repo = env["STOCS_REPO_PATH"]
+    mapf = os.path.join(repo, "models", "024_bowl", "ppf_map")
+    good = open(mapf, "rb").read()
+    # (a) a table built with another discretisation
+    env2 = dict(env, STOCS_PPF_ROT="10")
+    subprocess.run([os.path.join(HOST, "model_preprocess"), "024_bowl"], env=env2, capture_output=True, timeout=300, check=True)
+    p = subprocess.run([os.path.join(HOST, "stocs_single"), scene_dir, "024_bowl"], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0 and "discretisation" in p.stderr
+    # (b) a table whose pairs were thinned out is USED: fewer congruent sets than with the full table
+    n = struct.unpack_from("<q", good, 8 + 16 + 8)[0]
+    # STOCSPF1 layout (host/rgbd.cpp): magic 8 | int32 tr, rot, |M|, 0 | int64 expanded keys | int64 n | keys | pairs
+    keys = np.frombuffer(good, np.int32, 4 * n, 40).reshape(n, 4)
+    pairs = np.frombuffer(good, np.int32, 2 * n, 40 + 16 * n).reshape(n, 2)
+    keep = (pairs[:, 0] % 2 == 0)
+    thin = good[:32] + struct.pack("<q", int(keep.sum())) + keys[keep].tobytes() + pairs[keep].tobytes()
+    open(mapf, "wb").write(thin)
+    p = subprocess.run([os.path.join(HOST, "stocs_single"), scene_dir, "024_bowl"], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    t2 = read_trace(env["STOCS_TRACE_FILE"])
+    n_full = sum(len(q) for q, _ in trace["bases"])
+    n_thin = sum(len(q) for q, _ in t2["bases"])
+    assert 0 < n_thin < n_full
+    for q, _ in t2["bases"]:
+        assert (q[:, 0] % 2 == 0).all() and (q[:, 2] % 2 == 0).all()      # only pairs that are in the thinned table
+
+
+def test_multi_gpu_shim_matches_single(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    t1, _, _, _, _ = run_cli(str(tmp_path / "a"), "ycb")
+    t2, _, _, _, _ = run_cli(str(tmp_path / "b"), "ycb", {"STOCS_DEVICES": "0,1"})
+    assert t1["T"].tobytes() == t2["T"].tobytes() and t1["best_index"] == t2["best_index"]
+    t3, _, _, _, _ = run_cli(str(tmp_path / "c"), "packed")
+    t4, _, _, _, _ = run_cli(str(tmp_path / "d"), "packed", {"STOCS_DEVICES": "0,1"})
+    assert t3["T"].tobytes() == t4["T"].tobytes() and t3["best_index"] == t4["best_index"]
