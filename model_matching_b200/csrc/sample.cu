@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(1024) sample_bases_kernel(SampleArgs a) {
           bool zero = !ppf_key_exists(a.ppf, f) || i == bsel;
           if (stage == 2) {
             const V3 v_2 = normalized(sub(p, pb[0]));
-            float ang = (float)rad_to_deg_ref(acos_f(dot(v_1, v_2)));
+            float ang = deg_acos_unqualified_ref(dot(v_1, v_2));
             const float other = 180.0f - ang;
             ang = (other < ang) ? other : ang;
             zero = zero || (ang < internal_angle_threshold);

@@ -33,8 +33,16 @@ using namespace stocsm;
 
 namespace {
 
+// queued queries per warp: a larger queue means fewer, fuller drains (S1: 64 -> 2.15 ms, 96 -> 2.09 ms,
+// 128 -> 2.09 ms; shared memory per CTA grows by 8 KB per 32 entries)
 #ifndef SCORE_QUEUE
-#define SCORE_QUEUE 64
+#define SCORE_QUEUE 96
+#endif
+// shared-memory minimum over the candidates of a query: native 32-bit atomicMin on the d^2 bit
+// pattern + index write-back (default; S1 2.28 -> 2.15 ms, S1-fit 4.06 -> 3.76 ms) or the original
+// 64-bit (d^2, index) atomicMin, which compiles to a CAS loop (-DSCORE_ATOM64)
+#ifndef SCORE_ATOM64
+#define SCORE_ATOM32
 #endif
 #ifndef SCORE_MIN_BLOCKS
 #define SCORE_MIN_BLOCKS 2
@@ -181,8 +189,11 @@ __device__ __forceinline__ unsigned lanemask_lt() { unsigned r; asm("mov.u32 %0,
 __device__ __forceinline__ unsigned lanemask_le() { unsigned r; asm("mov.u32 %0, %%lanemask_le;" : "=r"(r)); return r; }
 
 struct WarpQueue {   // one per warp, shared memory (single base register, constant offsets)
-  float T[12];           // exact transform: columns 0..2 (rotation) and 3 (translation), 3 rows each
-  float G[12];           // the same map into grid-cell coordinates (FMA-evaluated, phase A only)
+  // exact transform and the same map into grid-block coordinates (FMA-evaluated, phase A only), as
+  // three rows {m_r0, m_r1, m_r2, t_r}: a row is ONE 16-byte broadcast load (12 scalar loads per use
+  // were a third of the kernel's shared-memory load wavefronts)
+  float4 T[3];
+  float4 G[3];
   uint32_t a0[kQueue];   // occupied-cell rank of the queued query
   uint32_t pi[kQueue];   // model point index of the queued query
 #ifdef SCORE_ATOM32
@@ -237,9 +248,10 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
       cnt = __ldg(a.starts + k + 1) - s;
       mi = q.pi[e];
       const float4 mp = mp4[mi];
-      qx = ((q.T[0] * mp.x + q.T[3] * mp.y) + q.T[6] * mp.z) + q.T[9];
-      qy = ((q.T[1] * mp.x + q.T[4] * mp.y) + q.T[7] * mp.z) + q.T[10];
-      qz = ((q.T[2] * mp.x + q.T[5] * mp.y) + q.T[8] * mp.z) + q.T[11];
+      const float4 t0 = q.T[0], t1 = q.T[1], t2 = q.T[2];
+      qx = ((t0.x * mp.x + t0.y * mp.y) + t0.z * mp.z) + t0.w;
+      qy = ((t1.x * mp.x + t1.y * mp.y) + t1.z * mp.z) + t1.w;
+      qz = ((t2.x * mp.x + t2.y * mp.y) + t2.z * mp.z) + t2.w;
     }
 #ifdef SCORE_ATOM32
     q.best_d[lane] = 0xffffffffu;
@@ -276,7 +288,7 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
       uint32_t hb = 0, hi = 0;
 #endif
       if (f < total) {
-        const float4 c = LD_CAND(a.cand + os + (f - op));
+        const float4 c = LD_CAND(a.cand + (uint32_t)(os + (f - op)));
         const float dx = ox - c.x, dy = oy - c.y, dz = oz - c.z;
         const float d = dx * dx + (dy * dy + dz * dz);
 #ifdef SCORE_ATOM32
@@ -323,9 +335,10 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
         const float4 sa = ld_stream(a.sattr + res);
         const float4 mn = __ldg(mn4 + mi);
         // mat.block<3,3>(0,0) * n  -- see stocs_math.h xform_dir
-        const float rx = q.T[0] * mn.x + (q.T[3] * mn.y + q.T[6] * mn.z);
-        const float ry = q.T[1] * mn.x + (q.T[4] * mn.y + q.T[7] * mn.z);
-        const float rz = q.T[2] * mn.x + (q.T[5] * mn.y + q.T[8] * mn.z);
+        const float4 t0 = q.T[0], t1 = q.T[1], t2 = q.T[2];
+        const float rx = t0.x * mn.x + (t0.y * mn.y + t0.z * mn.z);
+        const float ry = t1.x * mn.x + (t1.y * mn.y + t1.z * mn.z);
+        const float rz = t2.x * mn.x + (t2.y * mn.y + t2.z * mn.z);
         const float dt = sa.x * rx + (sa.y * ry + sa.z * rz);
         // acos(dt)*180/pi < 30  <=>  dot_thr <= dt <= 1   (threshold found by bisection on the host)
         match = (dt >= a.dot_thr) && (dt <= 1.0f);
@@ -385,16 +398,18 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
       const int c = lane / 3, rr = lane - 3 * c;
       const float t = __ldg(a.T + 16 * (size_t)h + c * 4 + rr);
       const float o = (rr == 0) ? a.g.ox : (rr == 1 ? a.g.oy : a.g.oz);
-      q.T[lane] = t;
+      reinterpret_cast<float*>(q.T)[rr * 4 + c] = t;
       // G maps into BLOCK coordinates (cell coordinates * 2^-coarse_shift): loop 1 floors it straight
       // to the coarse-map index; loop 2 multiplies by 2^coarse_shift first.  Scaling by a power of two
       // commutes with every rounding of the FMA chain, so the cell found is bit-identical to mapping
       // with the unscaled G.
-      q.G[lane] = ((c == 3) ? (t - o) * a.g.inv_cell : t * a.g.inv_cell) * a.to_block;
+      reinterpret_cast<float*>(q.G)[rr * 4 + c] = ((c == 3) ? (t - o) * a.g.inv_cell : t * a.g.inv_cell) * a.to_block;
     }
     __syncwarp();
-    float g0 = q.G[0], g1 = q.G[1], g2 = q.G[2], g3 = q.G[3], g4 = q.G[4], g5 = q.G[5];
-    float g6 = q.G[6], g7 = q.G[7], g8 = q.G[8], g9 = q.G[9], g10 = q.G[10], g11 = q.G[11];
+    // gK = element (row K % 3, column K / 3) of the grid map
+    float4 gr0 = q.G[0], gr1 = q.G[1], gr2 = q.G[2];
+    float g0 = gr0.x, g3 = gr0.y, g6 = gr0.z, g9 = gr0.w, g1 = gr1.x, g4 = gr1.y, g7 = gr1.z, g10 = gr1.w;
+    float g2 = gr2.x, g5 = gr2.y, g8 = gr2.z, g11 = gr2.w;
     r.acc = 0.f;
     r.inl = 0;
     int qn = 0;
@@ -470,8 +485,9 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
           drain_queue<kCount>(a, q, qn, lane, mp4, mn4, r);
           qn = 0;
           // the map is re-read after a drain so that it is not live (in registers) across it
-          g0 = q.G[0]; g1 = q.G[1]; g2 = q.G[2]; g3 = q.G[3]; g4 = q.G[4]; g5 = q.G[5];
-          g6 = q.G[6]; g7 = q.G[7]; g8 = q.G[8]; g9 = q.G[9]; g10 = q.G[10]; g11 = q.G[11];
+          gr0 = q.G[0]; gr1 = q.G[1]; gr2 = q.G[2];
+          g0 = gr0.x; g3 = gr0.y; g6 = gr0.z; g9 = gr0.w; g1 = gr1.x; g4 = gr1.y; g7 = gr1.z; g10 = gr1.w;
+          g2 = gr2.x; g5 = gr2.y; g8 = gr2.z; g11 = gr2.w;
         }
       }
       __syncwarp();

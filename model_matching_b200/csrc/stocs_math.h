@@ -36,10 +36,25 @@ static constexpr double kTwoOPi  = 0x1.45f306dc9c883p-1;
 static constexpr double kInvLn2  = 0x1.71547652b82fep+0;
 static constexpr double kSqrt2   = 0x1.6a09e667f3bcdp+0;
 
+// ---- arithmetic-model switches -------------------------------------------------------------------
+// For the sensitivity study of the unpinned leaf arithmetic ONLY (oracle/sensitivity.py builds oracle
+// variants with them; the product and the default oracle define none of them):
+//   STOCS_MODEL_SUM3_LEFT     3-term sums as (a + b) + c  (Eigen 3.2 coefficient-based products, and
+//                             SURVEY.md section 8c's reading) instead of a + (b + c)
+//   STOCS_MODEL_TRIG_DOUBLE   the reference's UNQUALIFIED atan2()/acos() calls (src/rgbd.cpp:113-115,
+//                             src/stocs.cpp:428) bound to the double overloads: the whole
+//                             "f(..)*180/M_PI" expression is then evaluated in binary64
+//   STOCS_MODEL_TRIG_ULP=+1/-1  every float atan2f/acosf result one ulp above / below the correctly
+//                             rounded value (what a libm that is not correctly rounded may return)
+
 struct V3 { float x, y, z; };
 
 STOCS_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+#ifdef STOCS_MODEL_SUM3_LEFT
+STOCS_HD float sum3(float a, float b, float c) { return (a + b) + c; }
+#else
 STOCS_HD float sum3(float a, float b, float c) { return a + (b + c); }
+#endif
 STOCS_HD V3 sub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 STOCS_HD V3 add(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 STOCS_HD V3 scale(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
@@ -132,8 +147,20 @@ STOCS_HD double atan2_d(double y, double x) {
   return yneg ? -a : a;
 }
 
+#if defined(STOCS_MODEL_TRIG_ULP)
+STOCS_HD float model_ulp(float r) {
+  uint32_t u; memcpy(&u, &r, 4);
+  if ((u & 0x7fffffffu) == 0u || (u & 0x7f800000u) == 0x7f800000u) return r;   // zero, inf, NaN unchanged
+  u = (uint32_t)((int32_t)u + ((STOCS_MODEL_TRIG_ULP) > 0 ? 1 : -1));           // magnitude +- 1 ulp (r >= 0 here)
+  memcpy(&r, &u, 4);
+  return r;
+}
+#else
+STOCS_HD float model_ulp(float r) { return r; }
+#endif
+
 // Float overloads (round the binary64 result once).
-STOCS_HD float atan2_f(float y, float x) { return (float)atan2_d((double)y, (double)x); }
+STOCS_HD float atan2_f(float y, float x) { return model_ulp((float)atan2_d((double)y, (double)x)); }
 STOCS_HD float atan_f(float x) { return (float)atan_d((double)x); }
 
 // acos(x) = atan2(sqrt((1-x)(1+x)), x); (1-x) and (1+x) are exact in binary64 for binary32 x.
@@ -141,7 +168,7 @@ STOCS_HD float acos_f(float x) {
   if (!(x >= -1.0f && x <= 1.0f)) return bitsf(0x7fc00000u);
   double xd = (double)x;
   double s = sqrt((1.0 - xd) * (1.0 + xd));
-  return (float)atan2_d(s, xd);
+  return model_ulp((float)atan2_d(s, xd));
 }
 
 // sin/cos for finite |x| < ~1e5: quadrant reduction with a two-part pi/2, Taylor to r^17 / r^18.
@@ -214,6 +241,28 @@ STOCS_HD float log2_f(float xf) {
 // in binary32, then divided by the double M_PI (src/rgbd.cpp:113, src/stocs.cpp:428,1028).
 STOCS_HD double rad_to_deg_ref(float rad) { return (double)(rad * 180.0f) / kPi; }
 
+// The two UNQUALIFIED call shapes of the reference.  With <cmath> in scope (it is: Eigen includes it)
+// float arguments select the float overloads, which is the model pinned here; see
+// STOCS_MODEL_TRIG_DOUBLE above for the other reading.
+//   int(atan2(y, x)*180/M_PI)              src/rgbd.cpp:113-115
+STOCS_HD double deg_atan2_ref(float y, float x) {
+#ifdef STOCS_MODEL_TRIG_DOUBLE
+  return atan2_d((double)y, (double)x) * 180.0 / kPi;
+#else
+  return rad_to_deg_ref(atan2_f(y, x));
+#endif
+}
+//   float int_angle = acos(d)*180/M_PI     src/stocs.cpp:428
+STOCS_HD float deg_acos_unqualified_ref(float d) {
+#ifdef STOCS_MODEL_TRIG_DOUBLE
+  if (!(d >= -1.0f && d <= 1.0f)) return bitsf(0x7fc00000u);
+  const double xd = (double)d;
+  return (float)(atan2_d(sqrt((1.0 - xd) * (1.0 + xd)), xd) * 180.0 / kPi);
+#else
+  return (float)rad_to_deg_ref(acos_f(d));
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Point-pair feature (reference src/rgbd.cpp:85-121).
 STOCS_HD int ppf_closest_bin(int value, int disc) {
@@ -227,9 +276,9 @@ struct Ppf4 { int f[4]; };
 STOCS_HD Ppf4 ppf_compute(V3 p1, V3 n1, V3 p2, V3 n2, int tr_disc, int rot_disc) {
   V3 u = sub(p1, p2);
   int a1 = (int)(norm(u) * 1000.0f);
-  int a2 = (int)rad_to_deg_ref(atan2_f(norm(cross(n1, u)), dot(n1, u)));
-  int a3 = (int)rad_to_deg_ref(atan2_f(norm(cross(n2, u)), dot(n2, u)));
-  int a4 = (int)rad_to_deg_ref(atan2_f(norm(cross(n1, n2)), dot(n1, n2)));
+  int a2 = (int)deg_atan2_ref(norm(cross(n1, u)), dot(n1, u));
+  int a3 = (int)deg_atan2_ref(norm(cross(n2, u)), dot(n2, u));
+  int a4 = (int)deg_atan2_ref(norm(cross(n1, n2)), dot(n1, n2));
   Ppf4 r;
   r.f[0] = ppf_closest_bin(a1, tr_disc);
   r.f[1] = ppf_closest_bin(a2, rot_disc);

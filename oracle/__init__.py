@@ -35,7 +35,8 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    L = C.CDLL(build())
+    # STOCS_ORACLE_LIB: an arithmetic-model variant built by oracle/sensitivity.py (never the default)
+    L = C.CDLL(os.environ.get("STOCS_ORACLE_LIB") or build())
     L.orc_backproject.argtypes = [u16p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_float, f32p, C.c_void_p]
     L.orc_build_scene_cloud.restype = C.c_longlong

@@ -439,7 +439,7 @@ struct Estimator {
     V3 v_1 = stocsm::normalized(stocsm::sub(spos[b2], spos[b1]));
     for (int i = 0; i < S; ++i) {
       V3 v_2 = stocsm::normalized(stocsm::sub(spos[i], spos[b1]));
-      float int_angle = (float)stocsm::rad_to_deg_ref(stocsm::acos_f(stocsm::dot(v_1, v_2)));
+      float int_angle = stocsm::deg_acos_unqualified_ref(stocsm::dot(v_1, v_2));
       float other = 180 - int_angle;
       int_angle = (other < int_angle) ? other : int_angle;  // std::min(int_angle, 180-int_angle)
       stocsm::Ppf4 f = scene_ppf(b2, i);
@@ -560,7 +560,7 @@ struct Estimator {
     V3 v_1 = stocsm::normalized(stocsm::sub(spos[b2], spos[b1]));
     for (int i = 0; i < S; ++i) {
       V3 v_2 = stocsm::normalized(stocsm::sub(spos[i], spos[b1]));
-      float int_angle = (float)stocsm::rad_to_deg_ref(stocsm::acos_f(stocsm::dot(v_1, v_2)));
+      float int_angle = stocsm::deg_acos_unqualified_ref(stocsm::dot(v_1, v_2));
       float other = 180 - int_angle;
       int_angle = (other < int_angle) ? other : int_angle;
       stocsm::Ppf4 f = scene_ppf(b2, i);
