@@ -150,13 +150,12 @@ int stocs_b200_upload_model(stocs_b200_ctx* ctx, const float* pos3, const float*
   STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)M * 12));
   STOCS_CUDA(ctx, ctx->d_mpos4.ensure((size_t)M * 16));
   STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp.p, pos3, (size_t)M * 12, cudaMemcpyHostToDevice, st));
-  int rc = stocs_centre_points(ctx, ctx->d_tmp.as<float>(), M, ctx->d_mpos4.as<float4>(), ctx->d_tmp2.as<float>(),
-                               ctx->cm, nullptr);
-  if (rc) return rc;
+  // centroid, centred copy and box on the host (see stocs_centre_points); the device centres its own copy
   ctx->h_mpos.resize((size_t)M * 3);
+  int rc = stocs_centre_points(ctx, ctx->d_tmp.as<float>(), M, ctx->d_mpos4.as<float4>(), nullptr, ctx->cm, nullptr, pos3,
+                               ctx->h_mpos.data());
+  if (rc) return rc;
   ctx->h_mnrm.assign(nrm3, nrm3 + (size_t)M * 3);
-  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_mpos.data(), ctx->d_tmp2.p, (size_t)M * 12, cudaMemcpyDeviceToHost, st));
-  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   const int Mpad = ((M + 63) / 64) * 64;  // the scoring kernel consumes 64 points per iteration
   // scoring-kernel layout: float4 centred positions (4*Mpad floats), then float4 normals
   std::vector<float> soa((size_t)8 * Mpad, 0.f);
@@ -198,7 +197,8 @@ int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float*
   STOCS_CUDA(ctx, cudaMemcpyAsync(d_c, class_probability, (size_t)S * 4, cudaMemcpyHostToDevice, st));
   int rc = stocs_pack_scene_attr(ctx, d_n, d_c, S);
   if (rc) { ctx->S_pending = 0; return rc; }
-  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  // (no synchronisation: the position upload below re-uses d_tmp in stream order, and the H2D copies
+  // of pageable host memory have consumed their source buffers when cudaMemcpyAsync returns)
   STOCS_CUDA(ctx, ctx->d_spix.ensure((size_t)S * 8));
   if (pixel_rc) STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_spix.p, pixel_rc, (size_t)S * 8, cudaMemcpyHostToDevice, st));
   else STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_spix.p, 0, (size_t)S * 8, st));
@@ -217,7 +217,9 @@ int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float*
     STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_inst_state.p, 0, (size_t)ctx->img_w * ctx->img_h * 3, st));
   // positions -> centre -> index
   STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp.p, pos3, (size_t)S * 12, cudaMemcpyHostToDevice, st));
+  ctx->h_pos_pending = getenv("STOCS_DEVICE_CENTROID") ? nullptr : pos3;
   rc = stocs_build_scene_index(ctx);
+  ctx->h_pos_pending = nullptr;
   ctx->S_pending = 0;
   if (rc) { ctx->S = 0; return rc; }
   ctx->S = S;

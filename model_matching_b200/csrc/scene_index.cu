@@ -266,13 +266,47 @@ struct KdBuild {
 
 // Centre n points with the reference's sequential fp32 centroid; optional float4 / float3 device
 // outputs, centroid and AABB (min xyz, max xyz of the centred points) returned to the host.
+// h_pos3 (optional): the same points in host memory.  The centroid is an ORDER-DEPENDENT serial fp32
+// sum (src/stocs.cpp:945-956), i.e. three dependent add chains of length n: one SM needs 5.5 ms for
+// 2^20 points, a host core ~1.3 ms, and the host runs it while the H2D copy of the points is still in
+// flight.  Without host data the single-CTA kernel does the same sum on the device.
 int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4* d_out4,
-                        float* d_out3, float* h_centroid3, float* h_aabb6) {
+                        float* d_out3, float* h_centroid3, float* h_aabb6, const float* h_pos3, float* h_centred3) {
   cudaStream_t st = ctx->stream;
   STOCS_CUDA(ctx, ctx->d_small.ensure(256));
   float* d_c = ctx->d_small.as<float>();
   int* d_aabb = (int*)(d_c + 4);
-  centroid_seq_kernel<<<1, 256, 0, st>>>(d_pos3, n, d_c);
+  if (h_pos3) {
+    float sx = 0.f, sy = 0.f, sz = 0.f;   // same order, same binary32 adds as the kernel (no contraction: no multiply)
+    for (int i = 0; i < n; ++i) { sx += h_pos3[3 * (size_t)i]; sy += h_pos3[3 * (size_t)i + 1]; sz += h_pos3[3 * (size_t)i + 2]; }
+    ctx->h_centroid_stage[0] = sx / (float)n; ctx->h_centroid_stage[1] = sy / (float)n; ctx->h_centroid_stage[2] = sz / (float)n;
+    STOCS_CUDA(ctx, cudaMemcpyAsync(d_c, ctx->h_centroid_stage, 12, cudaMemcpyHostToDevice, st));
+    if (h_centred3) {
+      // The host has everything the callers wait for: centroid, centred copy (one binary32
+      // subtraction per coordinate, the same operation as centre_pack_kernel) and bounding box.
+      // The device centres its own copy concurrently; nothing is read back, no synchronisation.
+      const float cx = ctx->h_centroid_stage[0], cy = ctx->h_centroid_stage[1], cz = ctx->h_centroid_stage[2];
+      float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+      bool finite = true;
+      for (int i = 0; i < n; ++i) {
+        const float v[3] = {h_pos3[3 * (size_t)i] - cx, h_pos3[3 * (size_t)i + 1] - cy, h_pos3[3 * (size_t)i + 2] - cz};
+        for (int k = 0; k < 3; ++k) {
+          h_centred3[3 * (size_t)i + k] = v[k];
+          if (v[k] < mn[k]) mn[k] = v[k];
+          if (v[k] > mx[k]) mx[k] = v[k];
+          finite = finite && std::isfinite(v[k]);
+        }
+      }
+      if (!finite) mn[0] = NAN;   // callers test the box
+      centre_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_pos3, n, d_c, d_out4, d_out3, nullptr);
+      STOCS_CUDA(ctx, cudaGetLastError());
+      for (int k = 0; k < 3; ++k) h_centroid3[k] = ctx->h_centroid_stage[k];
+      if (h_aabb6) for (int k = 0; k < 3; ++k) { h_aabb6[k] = mn[k]; h_aabb6[3 + k] = mx[k]; }
+      return STOCS_OK;
+    }
+  } else {
+    centroid_seq_kernel<<<1, 256, 0, st>>>(d_pos3, n, d_c);
+  }
   int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
   STOCS_CUDA(ctx, cudaMemcpyAsync(d_aabb, init, sizeof(init), cudaMemcpyHostToDevice, st));
   centre_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_pos3, n, d_c, d_out4, d_out3, d_aabb);
@@ -295,12 +329,15 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)S * 12));
   int nb = (S + 255) / 256;
   float aabb[6];
-  int rc = stocs_centre_points(ctx, ctx->d_tmp.as<float>(), S, ctx->d_spos4.as<float4>(),
-                               ctx->d_tmp2.as<float>(), ctx->cs, aabb);
-  if (rc) return rc;
   ctx->h_spos.resize((size_t)S * 3);
-  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_spos.data(), ctx->d_tmp2.p, (size_t)S * 12, cudaMemcpyDeviceToHost, st));
-  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  int rc = stocs_centre_points(ctx, ctx->d_tmp.as<float>(), S, ctx->d_spos4.as<float4>(),
+                               ctx->h_pos_pending ? nullptr : ctx->d_tmp2.as<float>(), ctx->cs, aabb, ctx->h_pos_pending,
+                               ctx->h_pos_pending ? ctx->h_spos.data() : nullptr);
+  if (rc) return rc;
+  if (!ctx->h_pos_pending) {   // device-only path: centred points and box come back from the kernels
+    STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_spos.data(), ctx->d_tmp2.p, (size_t)S * 12, cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  }
   tr.mark("centre + copy back");
   float mn[3] = {aabb[0], aabb[1], aabb[2]}, mx[3] = {aabb[3], aabb[4], aabb[5]};
   for (int k = 0; k < 3; ++k)

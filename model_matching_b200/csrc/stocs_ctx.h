@@ -114,6 +114,8 @@ struct stocs_b200_ctx {
   // scene (centred)
   int S = 0;
   int S_pending = 0;                   // size of the scene being uploaded (S is committed on success)
+  const float* h_pos_pending = nullptr;  // its positions in the caller's host buffer (valid during upload_scene only)
+  float h_centroid_stage[4] = {0, 0, 0, 0};  // source of the 12-byte centroid upload (must outlive the async copy)
   float cs[3] = {0, 0, 0};
   std::vector<float> h_spos;           // centred positions (S*3)
   DevBuf d_spos4;                      // float4 (x,y,z,bits(idx))
@@ -181,7 +183,8 @@ struct stocs_b200_ctx {
 // kernels / stages implemented in the other translation units
 int stocs_build_scene_index(stocs_b200_ctx* ctx);                         // scene_index.cu
 int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4* d_out4,
-                        float* d_out3, float* h_centroid3, float* h_aabb6);
+                        float* d_out3, float* h_centroid3, float* h_aabb6, const float* h_pos3 = nullptr,
+                        float* h_centred3 = nullptr);
 int stocs_pack_scene_attr(stocs_b200_ctx* ctx, const float* d_nrm3, const float* d_cls, int S);
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp,
                        int32_t* d_inl, cudaStream_t st, bool time_it, int slot = 0,

@@ -1,6 +1,7 @@
 """Golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py with the oracle).
 CPU: the oracle still reproduces them.  GPU: the CUDA path reproduces them bit for bit, on the
-seeded synthetic workload AND on the reference's YCB / LINEMOD example scenes (configs[0..1])."""
+seeded synthetic workload AND on the reference's YCB / LINEMOD / packed example scenes
+(configs[0..2]; packed = instance mode: stateful sampling with the edge map, decayed priors)."""
 import os
 
 import numpy as np
@@ -73,3 +74,54 @@ def test_gpu_reproduces_golden(gpu_ctx, name):
     keys, pairs = ctx.ppf_export()
     assert len(pairs) == len(mpos) * (len(mpos) - 1)
     assert np.all(np.diff(np.ascontiguousarray(keys).view([("", np.int32)] * 4).ravel().argsort(kind="stable")) >= 0) or True
+
+
+def _edge():
+    import cv2
+    return cv2.imread(os.path.join(G, "examples", "packed", "probability_maps", "edge.png"), cv2.IMREAD_GRAYSCALE)
+
+
+def _mask_sha(mask):
+    import hashlib
+    return np.frombuffer(hashlib.sha1(np.ascontiguousarray(mask).tobytes()).digest()[:8], np.uint64)[0]
+
+
+def test_oracle_reproduces_packed_golden():
+    g, spos, snrm, scls, mpos, mnrm = _inputs("packed")
+    omap = oracle.PPFMap(mpos, mnrm)
+    assert omap.num_keys == int(g["map_keys"])
+    est = oracle.Estimator(spos, snrm, scls, mpos, mnrm, ppfmap=omap, spix=g["spix"])
+    est.set_edge_map(_edge())
+    for b in range(10):
+        ok, ids, inv, _, mask = est.sample_instance_base(SEED, b + 1, 0.9)
+        assert ok == bool(g["base_ok"][b]) and _mask_sha(mask) == g["mask_sha"][b]
+        if ok:
+            assert np.array_equal(ids, g["base_ids"][b]) and np.array_equal(inv, g["base_inv"][b])
+    b = int(np.flatnonzero(g["base_ok"])[0])
+    q, _, _ = est.find_congruent(g["base_ids"][b], g["base_inv"][b][0], g["base_inv"][b][1])
+    assert np.array_equal(q, g["quads"][g["quad_offsets"][b]:g["quad_offsets"][b + 1]])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_packed_golden_instance_mode(gpu_ctx):
+    g, spos, snrm, scls, mpos, mnrm = _inputs("packed")
+    ctx = gpu_ctx
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(spos, snrm, scls, g["spix"])
+    ctx.upload_edge_map(_edge())
+    assert ctx.ppf_num_expanded_keys() == int(g["map_keys"])
+    nb = len(g["base_ok"])
+    bases, invs = [], []
+    for b in range(nb):
+        ok, ids, inv, mask = ctx.sample_instance_base(SEED, b + 1, 0.9)
+        assert ok == bool(g["base_ok"][b]), b
+        assert _mask_sha(mask) == g["mask_sha"][b], b
+        if ok:
+            assert np.array_equal(ids, g["base_ids"][b]) and np.array_equal(inv.view(np.uint32), g["base_inv"][b].view(np.uint32)), b
+            bases.append(ids.copy()); invs.append(inv.copy())
+    assert np.array_equal(ctx.class_probability().view(np.uint32), g["class_prob_after"].view(np.uint32))
+    quads, offs = ctx.find_congruent(np.array(bases), np.array(invs))
+    assert np.array_equal(quads, g["quads"])
+    lcp, inl = ctx.score_lcp(g["T"])                      # scored with the decayed priors (src/stocs.cpp:577,1033)
+    assert np.array_equal(inl, g["inliers"]) and np.array_equal(lcp.view(np.uint32), g["lcp"].view(np.uint32))
+    assert ctx.reduce_best(lcp, K=1)[:2] == (int(g["best_index"]), float(g["best_lcp"]))

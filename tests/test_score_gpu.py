@@ -231,3 +231,28 @@ def test_index_geometry_knobs_do_not_change_results(small_scene, scale, coarse_b
         _check(ctx, sc, mpos, mnrm, T)
     finally:
         ctx.close()
+
+
+def test_centroid_host_and_device_paths_agree(small_scene):
+    """the order-dependent fp32 centroid (src/stocs.cpp:945-956) is summed on the host while the
+    points are in flight; the single-CTA device kernel (STOCS_DEVICE_CENTROID=1) must give the same bits"""
+    import os
+    from model_matching_b200 import Context
+    sc, mpos, mnrm = small_scene
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+    want_cs, want_cm = est.centroids()
+    want_s, want_m = est.centred()
+    for dev_path in (False, True):
+        if dev_path:
+            os.environ["STOCS_DEVICE_CENTROID"] = "1"
+        try:
+            ctx = Context(0)
+            ctx.upload_model(mpos, mnrm)
+            ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+        finally:
+            os.environ.pop("STOCS_DEVICE_CENTROID", None)
+        cs, cm = ctx.centroids()
+        s, m = ctx.centred()
+        assert np.array_equal(cs.view(np.uint32), want_cs.view(np.uint32)) and np.array_equal(cm.view(np.uint32), want_cm.view(np.uint32))
+        assert np.array_equal(s.view(np.uint32), want_s.view(np.uint32)) and np.array_equal(m.view(np.uint32), want_m.view(np.uint32))
+        ctx.close()
