@@ -65,9 +65,23 @@ def worker(name):
     i, j = i.ravel()[keep], j.ravel()[keep]
     ppf = oracle.ppf_compute(g["mpos"][i], g["mnrm"][i], g["mpos"][j], g["mnrm"][j])
     omap = oracle.PPFMap(g["mpos"], g["mnrm"])
-    est = oracle.Estimator(g["spos"], g["snrm"], g["scls"], g["mpos"], g["mnrm"], ppfmap=omap)
+    est = oracle.Estimator(g["spos"], g["snrm"], g["scls"], g["mpos"], g["mnrm"], ppfmap=omap,
+                           spix=g["spix"] if "spix" in g else None)
     nb = len(g["base_ok"])
-    bases = [est.sample_class_base(SEED, b) for b in range(nb)]
+    # scene-side PPFs: first point of every golden base against every scene point (the input of the
+    # first sampling predicate, src/stocs.cpp:395-407)
+    firsts = [int(g["base_ids"][b][0]) for b in range(nb) if g["base_ok"][b]][:8]
+    S = len(g["spos"])
+    sppf = np.concatenate([oracle.ppf_compute(np.repeat(g["spos"][f][None], S, 0), np.repeat(g["snrm"][f][None], S, 0),
+                                               g["spos"], g["snrm"]) for f in firsts])
+    if "mask_sha" in g:      # instance mode (packed): the stateful sequence
+        import cv2
+        est.set_edge_map(cv2.imread(os.path.join(ROOT, "tests", "golden", "examples", name, "probability_maps", "edge.png"),
+                                    cv2.IMREAD_GRAYSCALE))
+        bases = [est.sample_instance_base(SEED, b + 1, 0.9)[:4] for b in range(nb)]
+        est = oracle.Estimator(g["spos"], g["snrm"], g["scls"], g["mpos"], g["mnrm"], ppfmap=omap, spix=g["spix"])
+    else:
+        bases = [est.sample_class_base(SEED, b) for b in range(nb)]
     # congruent sets on the GOLDEN bases, so that a change in sampling does not hide behind them
     quads = []
     for b in range(nb):
@@ -76,7 +90,7 @@ def worker(name):
             quads.append(q.tolist())
     lcp, inl = est.score(g["T"], threads=os.cpu_count() or 1)
     bi, bl = oracle.best(lcp)
-    print(json.dumps({"ppf": ppf.tolist(), "map_keys": int(omap.num_keys), "map_entries": int(omap.num_entries),
+    print(json.dumps({"ppf": ppf.tolist(), "scene_ppf": sppf.tolist(), "map_keys": int(omap.num_keys), "map_entries": int(omap.num_entries),
                       "base_ok": [bool(b[0]) for b in bases], "base_ids": [b[1].tolist() for b in bases],
                       "quads": quads, "inl": inl.tolist(), "lcp": lcp.view(np.uint32).tolist(), "best": int(bi)}))
 
@@ -97,7 +111,9 @@ def compare(a, b):
     qb = [set(map(tuple, q)) for q in b["quads"]]
     ia, ib = np.array(a["inl"]), np.array(b["inl"])
     okb = [x and y and i == j for x, y, i, j in zip(a["base_ok"], b["base_ok"], a["base_ids"], b["base_ids"])]
+    sa, sb = np.array(a["scene_ppf"]), np.array(b["scene_ppf"])
     return {"ppf_pairs": int(len(pa)), "ppf_pairs_changed": int((pa != pb).any(1).sum()),
+            "scene_ppf_pairs": int(len(sa)), "scene_ppf_pairs_changed": int((sa != sb).any(1).sum()),
             "map_keys": [a["map_keys"], b["map_keys"]], "map_entries": [a["map_entries"], b["map_entries"]],
             "bases": len(a["base_ok"]), "bases_changed": int(sum(1 for x, y, k in zip(a["base_ok"], b["base_ok"], okb) if (x or y) and not k)),
             "quad_lists": len(qa), "quad_lists_changed": int(sum(x != y for x, y in zip(qa, qb))),
@@ -120,14 +136,14 @@ def main():
         report[gname] = {v: compare(base, run(gname, lib)) for v, lib in libs.items()}
     out = os.path.join(ROOT, "profiles", "r02_arithmetic_sensitivity.json")
     json.dump(report, open(out, "w"), indent=1)
-    cols = ("ppf_pairs_changed", "bases_changed", "quad_lists_changed", "quads_added_or_removed", "inlier_counts_changed",
+    cols = ("ppf_pairs_changed", "scene_ppf_pairs_changed", "bases_changed", "quad_lists_changed", "quads_added_or_removed", "inlier_counts_changed",
             "max_inlier_delta", "lcp_bits_changed", "winner_changed")
     print("%-8s %-22s " % ("golden", "model") + " ".join("%22s" % c for c in cols))
     for gname, rows in report.items():
         for v, r in rows.items():
-            print("%-8s %-22s " % (gname, v) + " ".join("%22s" % (("%d / %d" % (r[c], r[{"ppf_pairs_changed": "ppf_pairs", "bases_changed": "bases",
+            print("%-8s %-22s " % (gname, v) + " ".join("%22s" % (("%d / %d" % (r[c], r[{"ppf_pairs_changed": "ppf_pairs", "scene_ppf_pairs_changed": "scene_ppf_pairs", "bases_changed": "bases",
                   "quad_lists_changed": "quad_lists", "quads_added_or_removed": "quads", "inlier_counts_changed": "hypotheses",
-                  "lcp_bits_changed": "hypotheses"}[c]])) if c in ("ppf_pairs_changed", "bases_changed", "quad_lists_changed",
+                  "lcp_bits_changed": "hypotheses"}[c]])) if c in ("ppf_pairs_changed", "scene_ppf_pairs_changed", "bases_changed", "quad_lists_changed",
                   "quads_added_or_removed", "inlier_counts_changed", "lcp_bits_changed") else str(r[c])) for c in cols))
     print("written:", out)
 
