@@ -72,6 +72,7 @@ struct ScoreArgs {
   unsigned long long* work_counter;
   unsigned long long* tie_counter;
   unsigned long long* cnt;   // counting variant only (stocs_b200_score_counters): see ScoreCounter
+  const int* __restrict__ order;   // claim number -> hypothesis (heavy-first schedule, see probe_order_kernel) or NULL
   long long H;
   GridDesc g;
   int M, Mpad;
@@ -358,6 +359,14 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
   }
 }
 
+// next unit of work (lane 0 only): a claim number from the global counter, mapped through the
+// heavy-first order when there is one; any value >= H ends the warp
+__device__ __forceinline__ int claim_hypothesis(const ScoreArgs& a) {
+  const unsigned long long c = atomicAdd(a.work_counter, 1ull);
+  if (c >= (unsigned long long)a.H) return 0x7fffffff;
+  return a.order ? __ldg(a.order + c) : (int)c;
+}
+
 template <bool kCount>
 __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kernel(ScoreArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   // than it saves: 2.63 / 2.76 ms against 2.58 ms.)
   // (claimed index broadcast by redux for the same reason: h stays in a uniform register)
   int h = 0;
-  if (lane == 0) h = (int)atomicAdd(a.work_counter, 1ull);
+  if (lane == 0) h = claim_hypothesis(a);
   h = (int)__reduce_max_sync(0xffffffffu, (unsigned)h);
   while (h < a.H) {
     // lanes 0..11 fetch the 3x4 transform (column-major 4x4: element (r,c) at c*4+r) and publish
@@ -498,11 +507,73 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
       if (a.inl) a.inl[h] = r.inl;
     }
     h = 0;
-    if (lane == 0) h = (int)atomicAdd(a.work_counter, 1ull);
+    if (lane == 0) h = claim_hypothesis(a);
     h = (int)__reduce_max_sync(0xffffffffu, (unsigned)h);
     __syncwarp();
   }
   if (r.ties) atomicAdd(a.tie_counter, (unsigned long long)r.ties);
+}
+
+// Heavy-first schedule.  The cost of a hypothesis varies by an order of magnitude (a pose that lands
+// the model on scene surface queues hundreds of queries, a pose in free space none), and with one
+// warp per hypothesis the launch ends when the last HEAVY hypothesis claimed does: a straggler tail
+// of ~0.09 ms, a quarter of the launch when 10^6 hypotheses are sharded over 8 GPUs.  This kernel
+// estimates the cost of every hypothesis from 32 sample points of the model (coarse-map test only:
+// 1/16 of loop 1, about 1 % of the scoring work) and writes a claim order with the predicted-heavy
+// hypotheses first and the light ones last.  The order only changes WHO scores a hypothesis WHEN;
+// every result is computed exactly as before.
+__global__ void __launch_bounds__(256) probe_order_kernel(ScoreArgs a, int* __restrict__ order, unsigned* __restrict__ fill,
+                                                          int heavy_threshold) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_pts = reinterpret_cast<float4*>(smem_raw);                 // 32 sample points
+  uint32_t* s_coarse = reinterpret_cast<uint32_t*>(s_pts + 32);
+  if (threadIdx.x < 32) s_pts[threadIdx.x] = reinterpret_cast<const float4*>(a.model)[(int)(((long long)threadIdx.x * a.M) / 32)];
+  for (int i = threadIdx.x; i < a.coarse_words; i += blockDim.x) s_coarse[i] = a.coarse[i];
+  __syncthreads();
+  const long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = lane_id();
+  bool heavy = false;
+  if (h < a.H) {
+    float g[12];
+    const float* t = a.T + 16 * (size_t)h;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const float v = __ldg(t + c * 4 + rr);
+        const float o = (rr == 0) ? a.g.ox : (rr == 1 ? a.g.oy : a.g.oz);
+        g[rr * 4 + c] = ((c == 3) ? (v - o) * a.g.inv_cell : v * a.g.inv_cell) * a.to_block;
+      }
+    int cnt = 0;
+#pragma unroll 4
+    for (int s = 0; s < 32; ++s) {
+      const float4 mp = s_pts[s];
+      const float fx = __fmaf_rn(g[0], mp.x, __fmaf_rn(g[1], mp.y, __fmaf_rn(g[2], mp.z, g[3])));
+      const float fy = __fmaf_rn(g[4], mp.x, __fmaf_rn(g[5], mp.y, __fmaf_rn(g[6], mp.z, g[7])));
+      const float fz = __fmaf_rn(g[8], mp.x, __fmaf_rn(g[9], mp.y, __fmaf_rn(g[10], mp.z, g[11])));
+      const unsigned cx = min((unsigned)__float2int_rd(fx), (unsigned)a.coarse_nx), cy = min((unsigned)__float2int_rd(fy), (unsigned)a.coarse_ny),
+                     cz = min((unsigned)__float2int_rd(fz), (unsigned)a.coarse_nz);
+      const uint32_t cidx = (cz * (unsigned)a.coarse_sy + cy) * (unsigned)a.coarse_sx + cx;
+      cnt += (s_coarse[cidx >> 5] >> (cidx & 31)) & 1u;
+    }
+    heavy = cnt >= heavy_threshold;
+  }
+  // warp-aggregated append: heavy hypotheses fill the order from the front, light ones from the back
+  const unsigned valid = __ballot_sync(0xffffffffu, h < a.H);
+  const unsigned hm = __ballot_sync(0xffffffffu, heavy);
+  const unsigned lm = valid & ~hm;
+  unsigned base_h = 0, base_l = 0;
+  if (lane == 0) {
+    if (hm) base_h = atomicAdd(&fill[0], (unsigned)__popc(hm));
+    if (lm) base_l = atomicAdd(&fill[1], (unsigned)__popc(lm));
+  }
+  base_h = __shfl_sync(0xffffffffu, base_h, 0);
+  base_l = __shfl_sync(0xffffffffu, base_l, 0);
+  if (h < a.H) {
+    const unsigned below = lanemask_lt();
+    if (heavy) order[base_h + __popc(hm & below)] = (int)h;
+    else order[(unsigned)a.H - 1u - (base_l + __popc(lm & below))] = (int)h;
+  }
 }
 
 __global__ void fmad_selftest_kernel(float a, float b, float c, float* out) { out[0] = a * b + c; }
@@ -548,6 +619,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.work_counter = wctr;
   a.tie_counter = ctr + 1;
   a.cnt = d_counters;
+  a.order = nullptr;
   a.H = H;
   a.g = ctx->grid;
   a.M = ctx->M;
@@ -568,6 +640,23 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   long long grid = (long long)ctx->num_sms * per_sm;
   if (grid > want) grid = want;
   STOCS_CUDA(ctx, cudaMemsetAsync(wctr, 0, 8, st));  // work counter only; tie counter accumulates
+  // Heavy-first schedule for MID-SIZE launches only.  Measured on B200 (S1 hypotheses, kernel + probe):
+  // 125 000 hypotheses (the per-GPU share of the named config on 8 GPUs) 0.347 -> 0.312 ms; 10^6
+  // hypotheses 2.100 -> 2.139 ms (the probe costs 64 us per 10^6, the tail it removes is ~0.09 ms
+  // whatever the size), and on the all-fitted S1-fit list the heavy-first order itself slows the
+  // kernel by 2 % (3.622 -> 3.692 ms).  Small launches (the online pipeline's ~1 000 hypotheses)
+  // cannot spare one more launch.  STOCS_NO_LPT=1 switches it off, STOCS_LPT_MAX overrides the bound.
+  const bool no_lpt = getenv("STOCS_NO_LPT") != nullptr;
+  const long long lpt_max = getenv("STOCS_LPT_MAX") ? atoll(getenv("STOCS_LPT_MAX")) : 300000;
+  if (!no_lpt && !d_counters && H >= 32768 && H <= lpt_max && slot == 0) {
+    DevBuf& b_order = ctx->pool[POOL_SCORE_ORDER];
+    STOCS_CUDA(ctx, b_order.ensure((size_t)H * 4));
+    unsigned* fill = (unsigned*)(ctx->d_small.as<char>() + 3328);
+    STOCS_CUDA(ctx, cudaMemsetAsync(fill, 0, 8, st));
+    const size_t psm = 32 * 16 + (size_t)((a.coarse_words + 3) & ~3) * 4;
+    probe_order_kernel<<<(unsigned)((H + 255) / 256), 256, psm, st>>>(a, b_order.as<int>(), fill, 16);
+    a.order = b_order.as<int>();
+  }
   if (time_it) {  // next pair of the ring (events are created on first use)
     const int k = (int)(ctx->ev_count % stocs_b200_ctx::kEvRing);
     for (int j = 0; j < 2; ++j)

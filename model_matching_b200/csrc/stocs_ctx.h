@@ -79,6 +79,8 @@ enum PoolSlot : int {
   POOL_COMM_SEND = 38, POOL_COMM_RECV, POOL_COMM_OUT, POOL_COMM_TOPK,
   // sharded scoring scratch (transforms / lcp / inliers of the local shard)
   POOL_SHARD_T = 42, POOL_SHARD_LCP, POOL_SHARD_INL,
+  // score.cu: claim order of the heavy-first schedule (one int per hypothesis of the launch)
+  POOL_SCORE_ORDER = 45,
   POOL_COUNT = 48
 };
 

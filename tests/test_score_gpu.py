@@ -256,3 +256,25 @@ def test_centroid_host_and_device_paths_agree(small_scene):
         assert np.array_equal(cs.view(np.uint32), want_cs.view(np.uint32)) and np.array_equal(cm.view(np.uint32), want_cm.view(np.uint32))
         assert np.array_equal(s.view(np.uint32), want_s.view(np.uint32)) and np.array_equal(m.view(np.uint32), want_m.view(np.uint32))
         ctx.close()
+
+
+def test_heavy_first_schedule_changes_no_result(small_scene, monkeypatch):
+    """launches of 32 768..300 000 hypotheses are claimed in a heavy-first order (probe_order_kernel);
+    the order only decides which warp scores a hypothesis when"""
+    sc, mpos, mnrm = small_scene
+    T, _ = synth.make_hypotheses(40000, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=21, near_fraction=0.02)
+    ctx = Context(0)
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    lcp1, inl1 = ctx.score_lcp(T)
+    monkeypatch.setenv("STOCS_NO_LPT", "1")
+    lcp0, inl0 = ctx.score_lcp(T)
+    monkeypatch.delenv("STOCS_NO_LPT")
+    monkeypatch.setenv("STOCS_LPT_MAX", "10000000")       # also on the largest size
+    lcp2, inl2 = ctx.score_lcp(np.concatenate([T] * 9))
+    assert np.array_equal(inl1, inl0) and np.array_equal(lcp1.view(np.uint32), lcp0.view(np.uint32))
+    assert np.array_equal(inl2, np.tile(inl0, 9)) and np.array_equal(lcp2.view(np.uint32), np.tile(lcp0, 9).view(np.uint32))
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm)
+    olcp, oinl = est.score(T[:3000], threads=4)
+    assert np.array_equal(inl1[:3000], oinl) and np.array_equal(lcp1[:3000].view(np.uint32), olcp.view(np.uint32))
+    ctx.close()
