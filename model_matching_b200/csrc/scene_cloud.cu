@@ -124,7 +124,7 @@ __global__ void outlier_kernel(const float4* __restrict__ cent, const unsigned l
 
 struct FilterArgs {
   const float4* cent; const int* keep; int nvox;
-  const float* xyz; const uint8_t* bgr; const uint16_t* prob; const uint8_t* edge;
+  const float* xyz; const uint16_t* depth; const uint8_t* bgr; const uint16_t* prob; const uint8_t* edge;
   int W, H; float fx, cx, fy, cy; float class_threshold;
   int* flags;      // out: 1 = emitted
   float* nrm;      // nvox * 3 (scratch)
@@ -145,7 +145,7 @@ __global__ void final_filter_kernel(FilterArgs a) {
         const float class_probability = (float)((double)(float)a.prob[(size_t)row * a.W + col] * (1.0 / 10000));
         if (!(class_probability < a.class_threshold)) {
           float n[3];
-          depth_normal_at(a.xyz, a.W, a.H, row, col, n);
+          linemod_normal_at(a.depth, a.W, a.H, row, col, a.fx, a.cx, a.fy, a.cy, n);
           const bool bad = (n[0] != n[0]) || (n[1] != n[1]) || (n[2] != n[2]) || (n[0] == 0 && n[1] == 0 && n[2] == 0);
           if (!bad) {
             ok = 1;
@@ -271,7 +271,7 @@ extern "C" int stocs_b200_build_scene_cloud(stocs_b200_ctx* ctx, const uint16_t*
   outlier_kernel<<<nxb, 128, 0, st>>>(d_cent.as<float4>(), d_ukeys.as<unsigned long long>(), nvox, r2, reach, 10, d_keep.as<int>());
   // flags / scan buffers are reused for the emit compaction (nvox <= n_valid)
   FilterArgs fa;
-  fa.cent = d_cent.as<float4>(); fa.keep = d_keep.as<int>(); fa.nvox = nvox; fa.xyz = d_xyz.as<float>();
+  fa.cent = d_cent.as<float4>(); fa.keep = d_keep.as<int>(); fa.nvox = nvox; fa.xyz = d_xyz.as<float>(); fa.depth = d_depth.as<uint16_t>();
   fa.bgr = bgr ? d_bgr.as<uint8_t>() : nullptr; fa.prob = d_prob.as<uint16_t>(); fa.edge = edge ? d_edge.as<uint8_t>() : nullptr;
   fa.W = W; fa.H = H; fa.fx = fx; fa.cx = cx; fa.fy = fy; fa.cy = cy; fa.class_threshold = class_threshold;
   fa.flags = d_flags.as<int>(); fa.nrm = d_nrm.as<float>(); fa.rc = d_rc.as<int>();

@@ -413,10 +413,15 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   g.nbricks = (uint32_t)((size_t)g.nbx * g.nby * g.nbz);
   g.ncells = g.nbricks * 64u;
   ctx->grid = g;
-  // dilation radius: eps plus a margin that absorbs the rounding of both cell-index computations
-  // (the scoring kernel locates cells through an FMA-evaluated affine map whose error is a few
-  // 1e-5 cells at these grid sizes; the margin is cell/256 + eps/256)
-  const float r = (float)(eps * (1.0 + 1.0 / 256.0) + cell / 256.0);
+  // dilation radius: eps plus a margin that absorbs the rounding of both cell-index computations.
+  // The scoring kernel locates cells through an FMA-evaluated affine map; its absolute error grows
+  // with the magnitude of the cell coordinate (three chained binary32 FMAs: <= ~4 ulp of the largest
+  // coordinate, i.e. 4 * n * 2^-24 cells on an axis of n cells): a few 1e-4 cells at S1 (830 cells),
+  // but 0.02 cells on a long thin scene of 10^5 cells.  The margin is therefore
+  // max(cell/256, 2 * that bound) + eps/256 -- cell/256 for every grid up to 32 768 cells per axis.
+  const double nmax = (double)std::max(g.nx, std::max(g.ny, g.nz));
+  const double margin_cells = std::max(1.0 / 256.0, 2.0 * 4.0 * nmax * 5.9604644775390625e-8);
+  const float r = (float)(eps * (1.0 + 1.0 / 256.0) + cell * margin_cells);
 
   size_t nc1 = (size_t)g.ncells + 1;
   DevBuf& d_dense = ctx->pool[POOL_INDEX_DENSE];  // dense per-cell starts (scratch)

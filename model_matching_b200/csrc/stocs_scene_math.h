@@ -30,42 +30,56 @@ STOCS_HD void smallest_eigenvector3(double a[3][3], double v[3]) {
   for (int k = 0; k < 3; ++k) v[k] = V[k][m];
 }
 
-// Depth-image normal at one pixel: stand-in for cv::rgbd::RgbdNormals(rows, cols, CV_32F, K, 5,
-// RGBD_NORMALS_METHOD_LINEMOD) (reference src/rgbd.cpp:202-206; opencv_contrib's source is not in
-// the reference tree).  Least-squares plane through the back-projected points of a 9x9 window
-// (stride 2) that lie on the same surface as the centre pixel (depth within 2 % + 5 mm), oriented
-// towards the camera.  Zero vector = invalid, which the caller treats as the reference treats an
-// all-zero normal (src/rgbd.cpp:266).  xyz: organised H*W*3 cloud of the back-projection.
-STOCS_HD void depth_normal_at(const float* xyz, int W, int H, int row, int col, float n_out[3]) {
-  n_out[0] = n_out[1] = n_out[2] = 0.f;
-  const float* c = xyz + 3 * ((size_t)row * W + col);
-  if (!(c[2] > 0)) return;
-  const float tol = 0.02f * c[2] + 0.005f;
-  double m[3] = {0, 0, 0};
-  float pts[25][3];
-  int n = 0;
-  for (int di = -4; di <= 4; di += 2)
-    for (int dj = -4; dj <= 4; dj += 2) {
-      const int i = row + di, j = col + dj;
-      if (i < 0 || i >= H || j < 0 || j >= W) continue;
-      const float* p = xyz + 3 * ((size_t)i * W + j);
-      if (!(p[2] > 0) || fabsf(p[2] - c[2]) > tol) continue;
-      pts[n][0] = p[0]; pts[n][1] = p[1]; pts[n][2] = p[2];
-      m[0] += p[0]; m[1] += p[1]; m[2] += p[2];
-      ++n;
+// Depth-image normal at one pixel: cv::rgbd::RgbdNormals(rows, cols, CV_32F, K, 5,
+// RGBD_NORMALS_METHOD_LINEMOD) applied to the raw CV_16U depth image (reference src/rgbd.cpp:202-206).
+// opencv_contrib is NOT in the reference tree (nor in this image), so this restates its published
+// algorithm -- modules/rgbd/src/normal.cpp, LINEMOD<float>::computeImpl<unsigned short, long>, after
+// Hinterstoisser et al., "Gradient Response Maps", PAMI 2012, eq. (8) -- and is UNVERIFIED against the
+// library ("parity unpinned"):
+//   * pixels with row in [5, rows-6) and col in [5, cols-6) only; every other pixel keeps NaN;
+//   * least-squares depth gradient over the 11x11 window: a neighbour takes part when its RAW depth
+//     differs from the centre's by at most 50 units ("difference_threshold", integer arithmetic):
+//       A0 += i*i, A1 += i*j, A3 += j*j, b0 += i*delta, b1 += j*delta   (i = column, j = row offset)
+//       det = A0*A3 - A1*A1,  dx = A3*b0 - A1*b1,  dy = -A1*b0 + A0*b1   (gradient * det, no division)
+//   * tangents (X1 - X)*det = K^-1 [d*det + (x+1)*dx, y*dx, dx],  (X2 - X)*det = K^-1 [x*dy, d*det + (y+1)*dy, dy]
+//     with K^-1 written out in binary32 (K converted to float first), products and sums left to right;
+//   * normal = cross product, scaled by 1.f / sqrt(n0*n0 + n1*n1 + n2*n2) and negated when n2 > 0
+//     (towards the camera).  A window with no usable neighbour gives 0 * inf = NaN, as in OpenCV.
+// The caller rejects NaN and all-zero normals (src/rgbd.cpp:262-266).
+STOCS_HD void linemod_normal_at(const uint16_t* depth, int W, int H, int row, int col, float fx, float cx, float fy,
+                                float cy, float n_out[3]) {
+  const float qnan = bitsf(0x7fc00000u);
+  n_out[0] = n_out[1] = n_out[2] = qnan;
+  const int r = 5;
+  if (row < r || row >= H - r - 1 || col < r || col >= W - r - 1) return;
+  const long long d = (long long)depth[(size_t)row * W + col];
+  long long A0 = 0, A1 = 0, A3 = 0, b0 = 0, b1 = 0;
+  for (int j = -r; j <= r; ++j) {
+    const uint16_t* line = depth + (size_t)(row + j) * W + col;
+    for (int i = -r; i <= r; ++i) {
+      const long long delta = (long long)line[i] - d;
+      if ((delta < 0 ? -delta : delta) > 50) continue;
+      A0 += (long long)(i * i); A1 += (long long)(i * j); A3 += (long long)(j * j);
+      b0 += (long long)i * delta; b1 += (long long)j * delta;
     }
-  if (n < 8) return;
-  for (int k = 0; k < 3; ++k) m[k] /= n;
-  double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  for (int t = 0; t < n; ++t) {
-    const double d[3] = {pts[t][0] - m[0], pts[t][1] - m[1], pts[t][2] - m[2]};
-    for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < 3; ++b) cov[a][b] += d[a] * d[b];
   }
-  double v[3];
-  smallest_eigenvector3(cov, v);
-  if (v[0] * c[0] + v[1] * c[1] + v[2] * c[2] > 0) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
-  n_out[0] = (float)v[0]; n_out[1] = (float)v[1]; n_out[2] = (float)v[2];
+  const long long det = A0 * A3 - A1 * A1;
+  const long long dx = A3 * b0 - A1 * b1;
+  const long long dy = -A1 * b0 + A0 * b1;
+  // K^-1 "by hand, just for higher accuracy" (skew K(0,1) = 0)
+  const float k00 = 1.0f / fx;
+  const float k01 = -0.0f / (fx * fy);
+  const float k02 = (0.0f * cy - cx * fy) / (fx * fy);
+  const float k11 = 1.0f / fy;
+  const float k12 = -cy / fy;
+  const float a1 = (float)(d * det + (long long)(col + 1) * dx), b1f = (float)((long long)row * dx), c1 = (float)dx;
+  const float a2 = (float)((long long)col * dy), b2f = (float)(d * det + (long long)(row + 1) * dy), c2 = (float)dy;
+  const float u0 = (k00 * a1 + k01 * b1f) + k02 * c1, u1 = k11 * b1f + k12 * c1, u2 = c1;
+  const float v0 = (k00 * a2 + k01 * b2f) + k02 * c2, v1 = k11 * b2f + k12 * c2, v2 = c2;
+  const float n0 = u1 * v2 - u2 * v1, n1 = u2 * v0 - u0 * v2, n2 = u0 * v1 - u1 * v0;
+  const float inv = 1.0f / sqrtf((n0 * n0 + n1 * n1) + n2 * n2);
+  if (n2 > 0) { n_out[0] = (-n0) * inv; n_out[1] = (-n1) * inv; n_out[2] = (-n2) * inv; }
+  else { n_out[0] = n0 * inv; n_out[1] = n1 * inv; n_out[2] = n2 * inv; }
 }
 
 // pcl::VoxelGrid leaf coordinates of a point (floor(p * inverse_leaf_size))

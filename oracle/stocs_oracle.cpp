@@ -835,7 +835,7 @@ long long orc_build_scene_cloud(const uint16_t* depth, const uint8_t* bgr, const
     const float edge_probability = (float)(255.0 - (edge ? edge[px] : 0)) / 255.0;
     if (class_probability < class_threshold) continue;
     float nr[3];
-    stocsm::depth_normal_at(xyz.data(), W, H, row, col, nr);
+    stocsm::linemod_normal_at(depth, W, H, row, col, fx, cx, fy, cy, nr);
     if (std::isnan(nr[0]) || std::isnan(nr[1]) || std::isnan(nr[2])) continue;
     if (nr[0] == 0 && nr[1] == 0 && nr[2] == 0) continue;
     if (nout < cap) {

@@ -278,3 +278,30 @@ def test_heavy_first_schedule_changes_no_result(small_scene, monkeypatch):
     olcp, oinl = est.score(T[:3000], threads=4)
     assert np.array_equal(inl1[:3000], oinl) and np.array_equal(lcp1[:3000].view(np.uint32), olcp.view(np.uint32))
     ctx.close()
+
+
+def test_long_thin_scene_cell_location_margin():
+    """a 60 m strip at 2.5 mm cells is 24 000 cells long: the FMA-evaluated cell map is off by more
+    than cell/256 at the far end, so the candidate-list margin scales with the grid extent"""
+    rng = np.random.default_rng(5)
+    n = 60000
+    pos = np.stack([rng.uniform(0, 60.0, n), rng.uniform(0, 0.04, n), rng.uniform(0, 0.04, n)], -1).astype(np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (n, 1))
+    cls = rng.uniform(0.1, 1, n).astype(np.float32)
+    mpos = rng.uniform(-0.02, 0.02, (128, 3)).astype(np.float32)
+    mnrm = np.tile(np.array([0, 0, 1], np.float32), (128, 1))
+    ctx = Context(0)
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(pos, nrm, cls)
+    cs, cm = ctx.centroids()
+    H = 4000
+    R = synth.axis_angle(rng.normal(size=(H, 3)), rng.uniform(0, 0.3, H))
+    t = np.stack([rng.uniform(0, 60.0, H), rng.uniform(0, 0.04, H), rng.uniform(0, 0.04, H)], -1)
+    t[:H // 2, 0] = rng.uniform(59.0, 60.0, H // 2)          # half of them at the far end of the grid
+    T = synth.to_colmajor16(R, t - cs.astype(np.float64))
+    lcp, inl = ctx.score_lcp(T)
+    est = oracle.Estimator(pos, nrm, cls, mpos, mnrm)
+    olcp, oinl = est.score(T, threads=8)
+    assert oinl.sum() > 1000
+    assert np.array_equal(inl, oinl) and np.array_equal(lcp.view(np.uint32), olcp.view(np.uint32))
+    ctx.close()
