@@ -1,5 +1,9 @@
-mkdir -p gpurun_out/r2g
-nvidia-smi -L > gpurun_out/r2g/gpus.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 200 --warmup 3 > gpurun_out/r2g/bench_n8.json 2> gpurun_out/r2g/bench_n8.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --workload s2 --steps 3 --warmup 3 > gpurun_out/r2g/bench_s2_n8.json 2> gpurun_out/r2g/bench_s2_n8.err
-tail -3 gpurun_out/r2g/bench_n8.err; head -c 300 gpurun_out/r2g/bench_n8.json; echo; tail -3 gpurun_out/r2g/bench_s2_n8.err; head -c 300 gpurun_out/r2g/bench_s2_n8.json
+mkdir -p gpurun_out/r2k
+nvidia-smi -L > gpurun_out/r2k/gpus.txt
+timeout 400 python bench.py --steps 200 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2k/bench_n1.json 2> gpurun_out/r2k/bench_n1.err
+for N in 2 4 8; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29530+N)) bench.py --gpus $N --steps 200 --warmup 3 > gpurun_out/r2k/bench_n$N.json 2> gpurun_out/r2k/bench_n$N.err
+done
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29549 bench.py --gpus 8 --workload s2 --steps 3 --warmup 3 > gpurun_out/r2k/bench_s2_n8.json 2> gpurun_out/r2k/bench_s2_n8.err
+for f in gpurun_out/r2k/bench_n1.json gpurun_out/r2k/bench_n2.json gpurun_out/r2k/bench_n4.json gpurun_out/r2k/bench_n8.json gpurun_out/r2k/bench_s2_n8.json; do head -c 220 $f; echo; done
+tail -2 gpurun_out/r2k/*.err | tail -20

@@ -45,3 +45,39 @@ def test_ppf_table_matches_expanded_map(gpu_ctx):
     assert n_absent > 100
     for q in ([5, 0, 0, 0], [0, 0, 0, 0], [-5, 10, 10, 10], [10, -5, 0, 0], [100000, 0, 0, 0]):
         assert gpu_ctx.ppf_lookup(np.array(q, np.int32)) is None
+
+
+def test_preloaded_table_round_trip_and_rejection(gpu_ctx):
+    """stocs_b200_upload_ppf_table (reference: ppf_map = ppf_map_preloaded, src/stocs.cpp:94): the
+    exported table uploaded again gives the same lookups; a thinned table is what gets used; a table
+    of another discretisation, another model size or with entries off the lattice is refused"""
+    from model_matching_b200 import StocsError
+    pos, nrm = _model(120)
+    gpu_ctx.upload_model(pos, nrm)
+    keys, pairs = gpu_ctx.ppf_export()
+    n_keys = gpu_ctx.ppf_num_expanded_keys()
+    probe = keys[:: max(1, len(keys) // 60)]
+    before = [gpu_ctx.ppf_lookup(k) for k in probe]
+    perm = np.random.default_rng(3).permutation(len(keys))          # any entry order is accepted
+    gpu_ctx.upload_ppf_table(keys[perm], pairs[perm], 5, 5, 120)
+    assert gpu_ctx.ppf_num_expanded_keys() == n_keys and gpu_ctx.ppf_num_pairs()[0] == len(pairs)
+    for k, want in zip(probe, before):
+        assert np.array_equal(gpu_ctx.ppf_lookup(k), want)
+    keep = pairs[:, 0] % 3 == 0
+    gpu_ctx.upload_ppf_table(keys[keep], pairs[keep], 5, 5, 120)
+    assert gpu_ctx.ppf_num_pairs()[0] == int(keep.sum())
+    for k, want in zip(probe, before):
+        got = gpu_ctx.ppf_lookup(k)
+        w = want[want[:, 0] % 3 == 0]
+        assert (got is None and len(w) == 0) or np.array_equal(got, w)
+    for bad_args in ((keys, pairs, 10, 5, 120), (keys, pairs, 5, 5, 121)):
+        with pytest.raises(StocsError):
+            gpu_ctx.upload_ppf_table(*bad_args)
+        gpu_ctx.upload_model(pos, nrm)          # a refused table leaves the context without a model
+    off = keys.copy(); off[0, 1] += 1           # not a multiple of the rotation bin
+    with pytest.raises(StocsError):
+        gpu_ctx.upload_ppf_table(off, pairs, 5, 5, 120)
+    gpu_ctx.upload_model(pos, nrm)
+    big = pairs.copy(); big[0, 1] = 120         # id out of range
+    with pytest.raises(StocsError):
+        gpu_ctx.upload_ppf_table(keys, big, 5, 5, 120)
