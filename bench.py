@@ -217,12 +217,26 @@ def pose_latency_packed(ctx):
     runs = [once(s) for s in range(2, 7)]
     out = {"workload": "packed/dove example scene, instance mode (|S|=%d, |M|=%d), 100 bases, <=200 sets/base" % (len(g["spos"]), len(g["mpos"]))}
     for k in ("upload_index_ms", "sampling_ms", "congruent_ms", "fit_score_best_ms"):
-        out["gpu_" + k] = 1e3 * float(np.median([r.get(k, 0.0) for r in runs]))
-    out["gpu_ms_per_pose"] = out["gpu_sampling_ms"] + out["gpu_congruent_ms"] + out["gpu_fit_score_best_ms"]
+        out["per_stage_driver_" + k] = 1e3 * float(np.median([r.get(k, 0.0) for r in runs]))
+    out["per_stage_driver_ms_per_pose"] = out["per_stage_driver_sampling_ms"] + out["per_stage_driver_congruent_ms"] + out["per_stage_driver_fit_score_best_ms"]
     for k in ("valid_bases", "congruent_sets", "transforms_scored", "best_lcp"):
         out[k] = runs[-1][k]
-    out["note"] = ("instance mode is serial across bases by definition (prior decay + cached masks): 100 launches with a host round "
-                   "trip each; the congruent-set stage returns every quad to the host in this per-stage driver")
+    # the fused device pipeline: the 100 coupled bases enqueued back to back, quads stay on the device
+    tf, tu, res = [], [], None
+    for s in range(2, 9):
+        t0 = time.perf_counter()
+        ctx.upload_scene(g["spos"], g["snrm"], g["scls"], g["spix"]); ctx.upload_edge_map(edge)
+        tu.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        res = ctx.run_pipeline_instance(s, 100, 200, 0.9)
+        tf.append(time.perf_counter() - t0)
+    out["gpu_ms_per_pose"] = 1e3 * float(np.median(tf[1:]))
+    out["gpu_upload_index_ms"] = 1e3 * float(np.median(tu[1:]))
+    out["fused"] = {"valid_bases": int(res.n_valid_bases), "congruent_sets": int(res.n_congruent_sets),
+                    "transforms_scored": int(res.n_transforms), "best_lcp": float(res.best_lcp)}
+    out["note"] = ("gpu_ms_per_pose: stocs_b200_run_pipeline_instance (bases are sequentially coupled -- prior decay + cached masks -- "
+                   "so sampling is 100 dependent launches, enqueued back to back); per_stage_driver_*: the same work through the "
+                   "per-call ABI the class shim uses (a host round trip per base, every quad returned to the host)")
     return out
 
 

@@ -208,6 +208,12 @@ typedef struct stocs_b200_pipeline_result {
 } stocs_b200_pipeline_result;
 int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets,
                             stocs_b200_pipeline_result* result);
+/* The same with the instance-mode sampler (edge map uploaded; src/stocs_match_one_object.cpp:89-92):
+ * bases 1..n_bases (n_bases <= 255) are sampled in sequence -- each launch sees the prior decay and
+ * the cached masks of its predecessors -- but enqueued back to back, without a host round trip per
+ * base.  Like n_bases calls of sample_instance_base, it advances the context's instance state. */
+int stocs_b200_run_pipeline_instance(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets,
+                                     float dispersion, stocs_b200_pipeline_result* result);
 
 /* ---- e: multi-GPU, hypothesis sharding -------------------------------
  * The reference scores its hypotheses in one sequential loop (src/stocs.cpp:990-998); they are

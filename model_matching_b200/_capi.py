@@ -25,7 +25,7 @@ SYMBOLS = [
     "stocs_b200_find_congruent", "stocs_b200_fit_transforms", "stocs_b200_score_lcp",
     "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device", "stocs_b200_select_above",
     "stocs_b200_icp_point_to_plane",
-    "stocs_b200_run_pipeline", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
+    "stocs_b200_run_pipeline", "stocs_b200_run_pipeline_instance", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
     "stocs_b200_score_counters", "stocs_b200_kernel_ms_stats",
     "stocs_b200_comm_unique_id", "stocs_b200_comm_init", "stocs_b200_comm_destroy", "stocs_b200_shard_range",
     "stocs_b200_score_sharded_device", "stocs_b200_score_sharded",
@@ -90,6 +90,7 @@ def lib():
     L.stocs_b200_select_above.argtypes = [vp, vp, i64, f32, vp, vp, i64, C.POINTER(i64)]
     L.stocs_b200_icp_point_to_plane.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.stocs_b200_run_pipeline.argtypes = [vp, u64, i32, i32, C.POINTER(PipelineResult)]
+    L.stocs_b200_run_pipeline_instance.argtypes = [vp, u64, i32, i32, f32, C.POINTER(PipelineResult)]
     L.stocs_b200_get_counters.argtypes = [vp, vp, i32]
     L.stocs_b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
     L.stocs_b200_score_counters.argtypes = [vp, vp, i64, vp, i32]
@@ -419,6 +420,11 @@ class Context:
     def run_pipeline(self, seed, n_bases=100, max_sets=200):
         r = PipelineResult()
         self._check(self._L.stocs_b200_run_pipeline(self.h, int(seed), n_bases, max_sets, C.byref(r)))
+        return r
+
+    def run_pipeline_instance(self, seed, n_bases=100, max_sets=200, dispersion=0.9):
+        r = PipelineResult()
+        self._check(self._L.stocs_b200_run_pipeline_instance(self.h, int(seed), n_bases, max_sets, dispersion, C.byref(r)))
         return r
 
     def counters(self):

@@ -25,6 +25,14 @@ float stocs_angle_threshold_dot() {
 
 static thread_local std::string g_create_err;
 
+// a "device pointer" handed to the *_device entry points may be page-locked host memory mapped into
+// the device address space (the zero-copy path): such transforms must not be read twice
+bool stocs_is_host_memory(const void* p) {
+  cudaPointerAttributes pa{};
+  if (cudaPointerGetAttributes(&pa, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return pa.type == cudaMemoryTypeHost;
+}
+
 extern "C" {
 
 int stocs_b200_abi_version(void) { return STOCS_B200_ABI_VERSION; }
@@ -253,7 +261,7 @@ int stocs_b200_score_lcp_device(stocs_b200_ctx* ctx, const float* d_T16, int64_t
   if (H < 0 || (H > 0 && (!d_T16 || !d_lcp))) STOCS_FAIL(ctx, STOCS_E_ARG, "score_lcp: bad argument");
   cudaSetDevice(ctx->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  return stocs_launch_score(ctx, d_T16, H, d_lcp, d_inliers, st, true);
+  return stocs_launch_score(ctx, d_T16, H, d_lcp, d_inliers, st, true, 0, nullptr, H > 0 && stocs_is_host_memory(d_T16));
 }
 
 // Top-32 of the resident lcp array into the page-locked cache, on stream st (no synchronize).
@@ -293,7 +301,7 @@ int stocs_b200_score_lcp(stocs_b200_ctx* ctx, const float* T16, int64_t H, float
     if (!mapped) cudaGetLastError();
     if (mapped && !getenv("STOCS_NO_ZERO_COPY")) {
       int rc = stocs_launch_score(ctx, (const float*)pa.devicePointer, H, ctx->d_lcp.as<float>(),
-                                  ctx->d_inl.as<int32_t>(), ctx->stream, true);
+                                  ctx->d_inl.as<int32_t>(), ctx->stream, true, 0, nullptr, /*T_in_host_memory=*/true);
       if (rc != STOCS_OK) return rc;
       ctx->last_T_dev = (const float*)pa.devicePointer;
       // the top-32 reduction (what stocs_b200_reduce_best returns for the resident array) runs on

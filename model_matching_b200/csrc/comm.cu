@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(1024) merge_records_kernel(const stocs_b200_re
 int enqueue_local_topk(stocs_b200_ctx* ctx, const float* d_T, int64_t H_local, int64_t index_offset, int K,
                        float* d_lcp, int32_t* d_inl, stocs_b200_record* d_send, cudaStream_t st, bool time_it) {
   if (H_local > 0) {
-    int rc = stocs_launch_score(ctx, d_T, H_local, d_lcp, d_inl, st, time_it);
+    int rc = stocs_launch_score(ctx, d_T, H_local, d_lcp, d_inl, st, time_it, 0, nullptr, stocs_is_host_memory(d_T));
     if (rc) return rc;
   }
   // H_local == 0: the top-K kernels run over an empty array and emit K empty records

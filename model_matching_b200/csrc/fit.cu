@@ -161,11 +161,17 @@ extern "C" int stocs_b200_fit_transforms(stocs_b200_ctx* ctx, int64_t n, const i
   return STOCS_OK;
 }
 
-extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets,
-                                       stocs_b200_pipeline_result* result) {
+int stocs_launch_sample_instance(stocs_b200_ctx* ctx, uint64_t seed, int base_num, float dispersion, int* d_ids,
+                                 float* d_inv, uint8_t* d_valid, cudaStream_t st);  // sample_instance.cu
+
+// mode 0: class-mode bases (independent, one launch for all); mode 1: instance-mode bases (sequentially
+// coupled: one launch per base, base numbers 1..n_bases, enqueued back to back without host round trips)
+static int run_pipeline_impl(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets, int mode, float dispersion,
+                             stocs_b200_pipeline_result* result) {
   if (!ctx) return STOCS_E_ARG;
   if (ctx->S <= 0 || ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "run_pipeline: upload_model and upload_scene first");
   if (n_bases <= 0 || max_sets <= 0 || !result) STOCS_FAIL(ctx, STOCS_E_ARG, "run_pipeline: bad argument");
+  if (mode == 1 && n_bases > 255) STOCS_FAIL(ctx, STOCS_E_ARG, "run_pipeline: instance mode numbers its bases 1..255");
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   StageTrace tr(st);
@@ -178,7 +184,14 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
   int* d_ids = d_bases.as<int>();
   float* d_inv = (float*)(d_ids + 4 * (size_t)n_bases);
   uint8_t* d_valid = (uint8_t*)(d_inv + 2 * (size_t)n_bases);
-  int rc = stocs_launch_sample(ctx, seed, 0, n_bases, d_ids, d_inv, d_valid, st);
+  int rc = STOCS_OK;
+  if (mode == 0) {
+    rc = stocs_launch_sample(ctx, seed, 0, n_bases, d_ids, d_inv, d_valid, st);
+  } else {
+    STOCS_CUDA(ctx, cudaMemsetAsync(d_valid, 0, (size_t)n_bases, st));
+    for (int b = 0; b < n_bases && rc == STOCS_OK; ++b)
+      rc = stocs_launch_sample_instance(ctx, seed, b + 1, dispersion, d_ids + 4 * (size_t)b, d_inv + 2 * (size_t)b, d_valid + b, st);
+  }
   if (rc) return rc;
   std::vector<int> h_ids((size_t)4 * n_bases);
   std::vector<float> h_inv((size_t)2 * n_bases);
@@ -269,4 +282,14 @@ extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n
 #undef PL
   cleanup();
   return STOCS_OK;
+}
+
+extern "C" int stocs_b200_run_pipeline(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets,
+                                       stocs_b200_pipeline_result* result) {
+  return run_pipeline_impl(ctx, seed, n_bases, max_sets, 0, 0.f, result);
+}
+
+extern "C" int stocs_b200_run_pipeline_instance(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets,
+                                                float dispersion, stocs_b200_pipeline_result* result) {
+  return run_pipeline_impl(ctx, seed, n_bases, max_sets, 1, dispersion, result);
 }

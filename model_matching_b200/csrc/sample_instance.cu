@@ -307,18 +307,20 @@ int stocs_b200_upload_edge_map(stocs_b200_ctx* ctx, const uint8_t* edge, int W, 
   return STOCS_OK;
 }
 
-int stocs_b200_sample_instance_base(stocs_b200_ctx* ctx, uint64_t seed, int base_num, float dispersion,
-                                    int32_t* base_idx4, float* inv2, uint8_t* valid, uint8_t* mask_out,
-                                    uint32_t* segment_bits) {
-  if (!ctx) return STOCS_E_ARG;
+}  // extern "C"
+
+// One base of the stateful instance-mode sequence, enqueued on st: outputs go to DEVICE memory
+// (d_ids 4 ints, d_inv 2 floats, d_valid 1 byte); mask and segment bits stay in ctx buffers.  No
+// synchronisation: the sequential coupling between bases (prior decay, cached masks) lives in device
+// state and is ordered by the stream, so a whole sequence can be enqueued back to back.
+int stocs_launch_sample_instance(stocs_b200_ctx* ctx, uint64_t seed, int base_num, float dispersion, int* d_ids,
+                                 float* d_inv, uint8_t* d_valid, cudaStream_t st) {
   if (ctx->S <= 0 || ctx->M <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "sample_instance_base: upload_model and upload_scene first");
   if (ctx->img_w <= 0) STOCS_FAIL(ctx, STOCS_E_STATE, "sample_instance_base: upload_edge_map first");
   if (!ctx->has_pixels) STOCS_FAIL(ctx, STOCS_E_STATE, "sample_instance_base: upload_scene was called without pixel coordinates");
   if (ctx->pix_min[0] < 0 || ctx->pix_min[1] < 0 || ctx->pix_max[0] >= ctx->img_h || ctx->pix_max[1] >= ctx->img_w)
     STOCS_FAIL(ctx, STOCS_E_ARG, "sample_instance_base: scene pixel coordinates fall outside the edge map");
-  if (base_num < 1 || base_num > 255 || !base_idx4 || !inv2 || !valid) STOCS_FAIL(ctx, STOCS_E_ARG, "sample_instance_base: base_num must be 1..255");
-  cudaSetDevice(ctx->device);
-  cudaStream_t st = ctx->stream;
+  if (base_num < 1 || base_num > 255) STOCS_FAIL(ctx, STOCS_E_ARG, "sample_instance_base: base_num must be 1..255");
   const size_t n = (size_t)ctx->img_w * ctx->img_h;
   InstArgs a;
   a.spos4 = ctx->d_spos4.as<float4>();
@@ -339,17 +341,35 @@ int stocs_b200_sample_instance_base(stocs_b200_ctx* ctx, uint64_t seed, int base
   a.alive = ctx->d_work.as<uint32_t>();
   a.seg_alive = a.alive + a.words;
   STOCS_CUDA(ctx, cudaMemsetAsync(a.seg_alive, 0, (size_t)a.words * 4, st));
-  int* d_ids = (int*)(ctx->d_small.as<char>() + 1024);
-  float* d_inv = (float*)(d_ids + 4);
-  uint8_t* d_valid = (uint8_t*)(d_inv + 2);
   a.out_ids = d_ids; a.out_inv = d_inv; a.out_valid = d_valid;
   sample_instance_kernel<<<1, 1024, 0, st>>>(a);
   STOCS_CUDA(ctx, cudaGetLastError());
+  return STOCS_OK;
+}
+
+extern "C" {
+
+int stocs_b200_sample_instance_base(stocs_b200_ctx* ctx, uint64_t seed, int base_num, float dispersion,
+                                    int32_t* base_idx4, float* inv2, uint8_t* valid, uint8_t* mask_out,
+                                    uint32_t* segment_bits) {
+  if (!ctx) return STOCS_E_ARG;
+  if (!base_idx4 || !inv2 || !valid) STOCS_FAIL(ctx, STOCS_E_ARG, "sample_instance_base: bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  int* d_ids = (int*)(ctx->d_small.as<char>() + 1024);
+  float* d_inv = (float*)(d_ids + 4);
+  uint8_t* d_valid = (uint8_t*)(d_inv + 2);
+  int rc = stocs_launch_sample_instance(ctx, seed, base_num, dispersion, d_ids, d_inv, d_valid, st);
+  if (rc) return rc;
+  const size_t n = (size_t)ctx->img_w * ctx->img_h;
+  const int words = (ctx->S + 31) / 32;
+  const uint8_t* cur_mask = ctx->d_inst_state.as<uint8_t>() + 2 * n;
+  const uint32_t* seg_alive = ctx->d_work.as<uint32_t>() + words;
   STOCS_CUDA(ctx, cudaMemcpyAsync(base_idx4, d_ids, 16, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaMemcpyAsync(inv2, d_inv, 8, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaMemcpyAsync(valid, d_valid, 1, cudaMemcpyDeviceToHost, st));
-  if (mask_out) STOCS_CUDA(ctx, cudaMemcpyAsync(mask_out, a.cur_mask, n, cudaMemcpyDeviceToHost, st));
-  if (segment_bits) STOCS_CUDA(ctx, cudaMemcpyAsync(segment_bits, a.seg_alive, (size_t)a.words * 4, cudaMemcpyDeviceToHost, st));
+  if (mask_out) STOCS_CUDA(ctx, cudaMemcpyAsync(mask_out, cur_mask, n, cudaMemcpyDeviceToHost, st));
+  if (segment_bits) STOCS_CUDA(ctx, cudaMemcpyAsync(segment_bits, seg_alive, (size_t)words * 4, cudaMemcpyDeviceToHost, st));
   STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   return STOCS_OK;
 }

@@ -190,11 +190,12 @@ int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4*
 int stocs_pack_scene_attr(stocs_b200_ctx* ctx, const float* d_nrm3, const float* d_cls, int S);
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp,
                        int32_t* d_inl, cudaStream_t st, bool time_it, int slot = 0,
-                       unsigned long long* d_counters = nullptr);  // score.cu
+                       unsigned long long* d_counters = nullptr, bool T_in_host_memory = false);  // score.cu
 int stocs_launch_backproject(stocs_b200_ctx* ctx, const uint16_t* d_depth, const uint8_t* d_bgr,
                              int W, int H, float fx, float cx, float fy, float cy, float scale,
                              float* d_xyz, uint32_t* d_rgb, cudaStream_t st);  // backproject.cu
 bool stocs_fmad_selftest(stocs_b200_ctx* ctx);                             // score.cu
+bool stocs_is_host_memory(const void* p);                                  // capi.cu
 // top-K of a device lcp array (reduce.cu); d_idx/d_val may be NULL when only records are wanted
 int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
                       int64_t* d_idx, float* d_val, cudaStream_t st, const float* d_T16 = nullptr,

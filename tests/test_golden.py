@@ -125,3 +125,44 @@ def test_gpu_reproduces_packed_golden_instance_mode(gpu_ctx):
     lcp, inl = ctx.score_lcp(g["T"])                      # scored with the decayed priors (src/stocs.cpp:577,1033)
     assert np.array_equal(inl, g["inliers"]) and np.array_equal(lcp.view(np.uint32), g["lcp"].view(np.uint32))
     assert ctx.reduce_best(lcp, K=1)[:2] == (int(g["best_index"]), float(g["best_lcp"]))
+
+
+@pytest.mark.gpu
+def test_fused_instance_pipeline_matches_oracle_composition(gpu_ctx):
+    """stocs_b200_run_pipeline_instance on the reference's packed frame: n sequentially coupled bases
+    enqueued back to back, congruent sets, <= max_sets fits per base (even spread), scoring with the
+    decayed priors, winner -- against the same sequence composed from the oracle's stages"""
+    g, spos, snrm, scls, mpos, mnrm = _inputs("packed")
+    nb, max_sets = 12, 60
+    ctx = gpu_ctx
+    ctx.upload_model(mpos, mnrm)
+    ctx.upload_scene(spos, snrm, scls, g["spix"])
+    ctx.upload_edge_map(_edge())
+    r = ctx.run_pipeline_instance(SEED, nb, max_sets, 0.9)
+    omap = oracle.PPFMap(mpos, mnrm)
+    est = oracle.Estimator(spos, snrm, scls, mpos, mnrm, ppfmap=omap, spix=g["spix"])
+    est.set_edge_map(_edge())
+    bases = []
+    for b in range(nb):
+        ok, ids, inv, _, _ = est.sample_instance_base(SEED, b + 1, 0.9)
+        assert ok == bool(g["base_ok"][b])
+        if ok:
+            bases.append((ids, inv))
+    assert r.n_valid_bases == len(bases) >= 4
+    Ts, Tws, base_of, n_sets = [], [], [], 0
+    for b, (ids, inv) in enumerate(bases):
+        quads, _, _ = est.find_congruent(ids, inv[0], inv[1])
+        cnt = len(quads)
+        n_sets += cnt
+        for k in (range(cnt) if cnt < max_sets else [(j * cnt) // max_sets for j in range(max_sets)]):
+            ok, Tc, Tw = est.fit(ids, quads[k])
+            if ok:
+                Ts.append(Tc); Tws.append(Tw); base_of.append(b)
+    assert r.n_congruent_sets == n_sets and r.n_transforms == len(Ts) > 100
+    lcp, _ = est.score(np.array(Ts, np.float32), threads=os.cpu_count() or 1)
+    bi, bl = oracle.best(lcp)
+    assert (r.best_index, r.best_lcp) == (bi, bl) and r.best_base == base_of[bi]
+    assert np.array_equal(np.array(r.best_T_centred[:], np.float32), Ts[bi])
+    assert np.array_equal(np.array(r.best_T_world[:], np.float32), Tws[bi])
+    # the context's instance state advanced exactly as nb single calls would have advanced it
+    assert np.array_equal(ctx.class_probability().view(np.uint32), est.class_prob().view(np.uint32))
