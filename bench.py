@@ -152,7 +152,10 @@ def pose_latency_fixture(ctx, name, label):
     ctx.run_pipeline(1, 100, 200)
     tp, res = [], None
     for seed in range(2, 12):
-        t0 = time.perf_counter(); res = ctx.run_pipeline(seed, 100, 200); tp.append(time.perf_counter() - t0)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter(); res = ctx.run_pipeline(seed, 100, 200); best = min(best, time.perf_counter() - t0)
+        tp.append(best)
     T = np.ascontiguousarray(g["T"], np.float32)
     lcp, inl = ctx.score_lcp(T)
     ts = []
@@ -264,10 +267,13 @@ def pose_latency(ctx_factory, with_cpu):
     t_model, t_upload = float(np.median(tm)), float(np.median(tu))
     ctx.run_pipeline(1, 100, 200)
     times, res = [], None
-    for seed in range(2, 12):
-        t0 = time.perf_counter()
-        res = ctx.run_pipeline(seed, 100, 200)
-        times.append(time.perf_counter() - t0)
+    for seed in range(2, 12):      # per seed: best of 3 (host jitter); reported: median over the 10 seeds
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res = ctx.run_pipeline(seed, 100, 200)
+            best = min(best, time.perf_counter() - t0)
+        times.append(best)
     out = {"workload": "YCB 024_bowl example scene (|S|=%d, |M|=%d), 100 bases, <=200 sets/base" % (len(g["spos"]), len(g["mpos"])),
            "gpu_ms_per_pose": 1e3 * float(np.median(times)), "gpu_upload_index_ms": 1e3 * t_upload, "gpu_model_table_ms": 1e3 * t_model,
            "transforms_scored": int(res.n_transforms), "congruent_sets": int(res.n_congruent_sets)}
