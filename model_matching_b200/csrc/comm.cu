@@ -234,18 +234,59 @@ int stocs_b200_score_sharded(stocs_b200_ctx* ctx, const float* T16_local, int64_
     }
     lcp_local = (float*)ctx->h_pinned;
   }
-  if (H_local > 0) {
-    int rc = stocs_b200_score_lcp(ctx, T16_local, H_local, lcp_local, inliers_local);
-    if (rc) return rc;
-  }
-  // 2. K best of the resident results as records, 3. ONE all-gather, 4. merge
   const int nranks = ctx->comm ? ctx->comm_nranks : 1;
   DevBuf &b_send = ctx->pool[POOL_COMM_SEND], &b_recv = ctx->pool[POOL_COMM_RECV], &b_out = ctx->pool[POOL_COMM_OUT];
   STOCS_CUDA(ctx, b_send.ensure((size_t)K * sizeof(stocs_b200_record)));
   STOCS_CUDA(ctx, b_recv.ensure((size_t)K * nranks * sizeof(stocs_b200_record)));
   STOCS_CUDA(ctx, b_out.ensure((size_t)K * sizeof(stocs_b200_record)));
-  STOCS_CUDA(ctx, ctx->d_lcp.ensure(4));
   stocs_b200_record* d_local = nranks > 1 ? b_send.as<stocs_b200_record>() : b_out.as<stocs_b200_record>();
+  // Page-locked, device-mapped transforms: ONE pass with ONE synchronisation.  The kernel reads the
+  // transforms in place over PCIe; then the per-hypothesis results go back on the context stream
+  // while, on the second stream, the K best are packed, all-gathered and merged.  (Going through
+  // stocs_b200_score_lcp first costs its own top-32 reduction and a second synchronisation:
+  // 0.58 -> 0.50 ms per step at 125 000 hypotheses per rank on 8 GPUs.)
+  if (H_local > 0 && !getenv("STOCS_NO_ZERO_COPY")) {
+    cudaPointerAttributes pa{};
+    const bool mapped = cudaPointerGetAttributes(&pa, T16_local) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                        pa.devicePointer != nullptr;
+    if (!mapped) cudaGetLastError();
+    if (mapped) {
+      const float* d_T = (const float*)pa.devicePointer;
+      STOCS_CUDA(ctx, ctx->d_lcp.ensure((size_t)H_local * 4));
+      STOCS_CUDA(ctx, ctx->d_inl.ensure((size_t)H_local * 4));
+      ctx->top_valid = false;
+      int rc = stocs_launch_score(ctx, d_T, H_local, ctx->d_lcp.as<float>(), ctx->d_inl.as<int32_t>(), st, true, 0, nullptr, true);
+      if (rc) return rc;
+      ctx->last_H = H_local;
+      ctx->last_T_dev = d_T;
+      cudaStream_t aux = ctx->aux_stream;
+      STOCS_CUDA(ctx, cudaEventRecord(ctx->join_ev[0], st));
+      STOCS_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->join_ev[0], 0));
+      STOCS_CUDA(ctx, cudaMemcpyAsync(lcp_local, ctx->d_lcp.p, (size_t)H_local * 4, cudaMemcpyDeviceToHost, st));
+      if (inliers_local)
+        STOCS_CUDA(ctx, cudaMemcpyAsync(inliers_local, ctx->d_inl.p, (size_t)H_local * 4, cudaMemcpyDeviceToHost, st));
+      rc = stocs_launch_topk(ctx, ctx->d_lcp.as<float>(), H_local, K, index_offset, nullptr, nullptr, aux, d_T,
+                             ctx->d_inl.as<int32_t>(), d_local);
+      if (rc) return rc;
+      if (nranks > 1) {
+        STOCS_NCCL(ctx, g_nccl.AllGather(b_send.p, b_recv.p, (size_t)K * sizeof(stocs_b200_record), ncclInt8,
+                                         (ncclComm_t)ctx->comm, aux));
+        merge_records_kernel<<<1, 1024, 0, aux>>>(b_recv.as<stocs_b200_record>(), K * nranks, K, b_out.as<stocs_b200_record>());
+        STOCS_CUDA(ctx, cudaGetLastError());
+      }
+      STOCS_CUDA(ctx, cudaMemcpyAsync(topk_out, b_out.p, (size_t)K * sizeof(stocs_b200_record), cudaMemcpyDeviceToHost, aux));
+      STOCS_CUDA(ctx, cudaEventRecord(ctx->join_ev[1], aux));
+      STOCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->join_ev[1], 0));
+      STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+      return STOCS_OK;
+    }
+  }
+  if (H_local > 0) {
+    int rc = stocs_b200_score_lcp(ctx, T16_local, H_local, lcp_local, inliers_local);
+    if (rc) return rc;
+  }
+  // 2. K best of the resident results as records, 3. ONE all-gather, 4. merge
+  STOCS_CUDA(ctx, ctx->d_lcp.ensure(4));
   int rc = stocs_launch_topk(ctx, ctx->d_lcp.as<float>(), H_local, K, index_offset, nullptr, nullptr, st,
                              H_local > 0 ? ctx->last_T_dev : nullptr, H_local > 0 ? ctx->d_inl.as<int32_t>() : nullptr, d_local);
   if (rc) return rc;
