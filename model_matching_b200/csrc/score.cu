@@ -208,6 +208,24 @@ struct WarpQueue {   // one per warp, shared memory (single base register, const
 
 struct Acc { float acc; int inl; unsigned ties; };
 
+// Model positions in shared memory as three float arrays x[Mpad] y[Mpad] z[Mpad]: a warp load is three
+// LDS.32 = 3 wavefronts of the L1 data pipe -- the kernel's binding resource -- where a float4 record
+// (LDS.128) takes 4, and a gather of 32 arbitrary points conflicts less (S1 2.074 -> 2.058 ms,
+// S1-fit 3.582 -> 3.481 ms; -DSCORE_AOS restores the float4 records).
+#ifndef SCORE_AOS
+struct ModelPts {
+  const float* x; int Mpad;
+  __device__ __forceinline__ float4 operator[](int i) const { return make_float4(x[i], x[Mpad + i], x[2 * Mpad + i], 0.f); }
+};
+#else
+typedef const float4* ModelPts;
+#endif
+#ifndef SCORE_AOS
+constexpr int kModelFloats = 3;   // floats of shared memory per (padded) model point
+#else
+constexpr int kModelFloats = 4;
+#endif
+
 // Work counters of the counting variant (template parameter kCount; the timed kernel carries none
 // of this).  One global atomic per warp-level event, issued by lane 0.
 enum ScoreCounter { SC_SURVIVORS = 0, SC_BRICK_RECORDS, SC_QUEUED, SC_CANDIDATES, SC_HITS, SC_INLIERS, SC_DRAINS, SC_N };
@@ -233,7 +251,7 @@ __device__ __forceinline__ void count(const ScoreArgs& a, int lane, int slot, un
 //      the LCP bit-identical to the reference's sequential fp32 sum.
 template <bool kCount>
 __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, int qn, int lane,
-                                            const float4* __restrict__ mp4, const float4* __restrict__ mn4, Acc& r) {
+                                            const ModelPts mp4, const float4* __restrict__ mn4, Acc& r) {
   __syncwarp();
   const float sq_eps = a.sq_eps;
   const unsigned le_mask = lanemask_le();
@@ -378,16 +396,27 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
   // tid >> 5 the queue address was spilled and re-loaded at 18 sites (37 local loads per hypothesis)
   const int warp = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
   // dynamic shared memory: [model positions float4 x Mpad][coarse bitmap][one WarpQueue per warp]
+#ifndef SCORE_AOS
+  for (int i = threadIdx.x; i < 4 * Mpad; i += blockDim.x) { const int c = i & 3; if (c < 3) s_model[c * Mpad + (i >> 2)] = a.model[i]; }
+#else
   for (int i = threadIdx.x; i < 4 * Mpad; i += blockDim.x) s_model[i] = a.model[i];
-  uint32_t* s_coarse = reinterpret_cast<uint32_t*>(s_model + 4 * Mpad);
+#endif
+  uint32_t* s_coarse = reinterpret_cast<uint32_t*>(s_model + kModelFloats * Mpad);   // Mpad % 64 == 0: 16-byte aligned
   for (int i = threadIdx.x; i < a.coarse_words; i += blockDim.x) s_coarse[i] = a.coarse[i];
   WarpQueue& q = reinterpret_cast<WarpQueue*>(s_coarse + ((a.coarse_words + 3) & ~3))[warp];
   __syncthreads();
+#ifndef SCORE_AOS
+  ModelPts mp4; mp4.x = s_model; mp4.Mpad = Mpad;                // positions as x[] y[] z[] (NaN beyond M)
+#else
   const float4* mp4 = reinterpret_cast<const float4*>(s_model);  // positions as float4 (NaN beyond M)
+#endif
   const float4* mn4 = reinterpret_cast<const float4*>(a.model) + Mpad;  // normals stay in global (hits only)
 
   const unsigned lt_mask = lanemask_lt();
   const int M = a.M;
+  // shared-window address of the coarse bitmap, made warp-uniform through redux so that it lives in a
+  // uniform register for the whole kernel
+  const unsigned coarse_sa = __reduce_max_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared(s_coarse));
   Acc r;
   r.ties = 0;
 
@@ -443,8 +472,16 @@ __global__ void __launch_bounds__(kWarps * 32, SCORE_MIN_BLOCKS) score_lcp_kerne
         const unsigned cx = min(ix, (unsigned)a.coarse_nx), cy = min(iy, (unsigned)a.coarse_ny),
                        cz = min(iz, (unsigned)a.coarse_nz);
         const uint32_t cidx = (cz * (unsigned)a.coarse_sy + cy) * (unsigned)a.coarse_sx + cx;
-        const bool pass = (s_coarse[cidx >> 5] >> (cidx & 31)) & 1u;
-        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+        // The bitmap word is loaded through its shared-window address held in a uniform register, and
+        // the ballot is written in PTX on ONE predicate: as plain C++ the compiler re-derived the
+        // address (S2UR + UMOV + 2 ULEA) and a second predicate (ISETP) in every iteration -- 40 -> 35
+        // SASS instructions per 32 points (profiles/r02_score_loop1_sass.txt).
+        unsigned cw;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(coarse_sa + ((cidx >> 5) << 2)));
+        const unsigned bitv = (cw >> (cidx & 31)) & 1u;
+        unsigned pm;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}" : "=r"(pm) : "r"(bitv));
+        const bool pass = bitv != 0u;
         if (pass) q.plist[nl + __popc(pm & lt_mask)] = (uint8_t)(rr * 32 + lane);
         nl += __popc(pm);
       }
@@ -638,7 +675,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.dot_thr = ctx->dot_thr;
   a.to_block = 1.0f / (float)(1u << ctx->coarse_shift);
   a.to_cell = (float)(1u << ctx->coarse_shift);
-  size_t smem = (size_t)4 * ctx->Mpad * 4 + (size_t)((a.coarse_words + 3) & ~3) * 4 + (size_t)kWarps * sizeof(WarpQueue);
+  size_t smem = (size_t)kModelFloats * ctx->Mpad * 4 + (size_t)((a.coarse_words + 3) & ~3) * 4 + (size_t)kWarps * sizeof(WarpQueue);
   // static (per-warp queues) + dynamic (model, coarse bitmap) may exceed the 48 KB default
   // d_counters != NULL selects the counting variant (same code + one global atomic per warp event)
   void (*kernel)(ScoreArgs) = d_counters ? score_lcp_kernel<true> : score_lcp_kernel<false>;
