@@ -750,8 +750,8 @@ def main():
                                      "lcp + inlier counts and the merged top-K records copied back",
                        "staged_copy_value": e2e_staged, "numa_cpus": numa, "h2d_probe": h2d},
                # per step: [probe_order_kernel for 32 768..300 000 hypotheses per launch] + score_lcp_kernel +
-               # topk_partial_kernel + topk_merge_kernel [+ merge_records_kernel after the all-gather]
-               "gpu_launches": args.steps * (3 + (1 if world > 1 else 0) + (1 if 32768 <= Hl <= 300000 and not os.environ.get("STOCS_NO_LPT") else 0)),
+               # topk_kernel [+ merge_records_kernel after the all-gather]
+               "gpu_launches": args.steps * (2 + (1 if world > 1 else 0) + (1 if 32768 <= Hl <= 300000 and not os.environ.get("STOCS_NO_LPT") else 0)),
                "collectives_per_step": 1 if world > 1 else 0,
                "merge_check": {"merged_topk_equals_single_gpu_topk_of_whole_list": merge_ok, "ranks_agree": True, "K": TOPK},
                "roofline": roof, "clocks": clocks, "ties_resolved_by_kdtree": int(ctx.counters()[1]), "extra": extra}

@@ -3,7 +3,7 @@
 // The reference scores every hypothesis in one sequential loop and keeps the first strict maximum
 // (src/stocs.cpp:990-998).  Hypotheses are independent, so each GPU scores a contiguous block of
 // the list against its own replica of the scene index; the per-GPU K best are packed as 64-byte
-// records {lcp, inliers, global index, 3x4 transform} (reduce.cu: topk_merge_kernel), ONE
+// records {lcp, inliers, global index, 3x4 transform} (reduce.cu: topk_kernel), ONE
 // ncclAllGather moves nranks*K records (16 KB at 8 GPUs, K = 32) over NVLink, and a single-CTA
 // kernel ranks them by (lcp descending, global index ascending): record 0 is the reference's
 // winner over the whole list.  The collective is latency-bound; nothing here is worth fusing into

@@ -40,10 +40,40 @@ __device__ __forceinline__ void warp_offer(unsigned long long& mine, unsigned lo
   }
 }
 
-// one sorted top-32 list per CTA: per-warp lists, merged through shared memory by warp 0
-__global__ void __launch_bounds__(256) topk_partial_kernel(const float* __restrict__ lcp, long long H,
-                                                           unsigned long long* __restrict__ out) {
+// Merge two lists that are BOTH sorted descending across the lanes (lane j = j-th best) into the top 32
+// of their union, sorted: max(a[j], b[31-j]) is a bitonic sequence that holds exactly those 32 keys,
+// and five compare-exchange stages sort it.  ~60 instructions, against up to 32 dependent insertions
+// with warp_offer (the final merge kernel took 40 us per step with those: it sits on the critical
+// path of every step, 10 % of a step when 10^6 hypotheses are sharded over 8 GPUs).
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ void warp_merge_sorted(unsigned long long& mine, unsigned long long other, int lane) {
+  const unsigned long long rev = shfl64(other, 31 - lane);
+  unsigned long long m = mine > rev ? mine : rev;
+#pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) {
+    const unsigned long long p = shfl64(m, lane ^ k);
+    const bool keep_max = (lane & k) == 0;      // descending: the lower lane of a pair keeps the larger key
+    m = keep_max ? (m > p ? m : p) : (m < p ? m : p);
+  }
+  mine = m;
+}
+
+// ONE launch: every CTA reduces its strided share of the LCP array to a sorted top-32 list (per-warp
+// lists with ballot insertion, merged by warp 0); the CTA that finishes LAST (threadfence + atomic
+// ticket) merges the per-CTA lists -- each of its 8 warps folds a strided share with the bitonic merge,
+// then a 3-round tournament -- and writes the K winners, also packed as 64-byte records {lcp, inliers,
+// global index, rows 0..2 of the transform} when rec_out != NULL (the unit of the multi-GPU all-gather,
+// comm.cu).  Two launches with insertion merges took 55 us per step at 10^6 hypotheses, this one 13 us.
+__global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ lcp, long long H, unsigned long long* __restrict__ lists,
+                                                   unsigned* __restrict__ ticket, int K, long long index_offset,
+                                                   long long* __restrict__ out_idx, float* __restrict__ out_lcp,
+                                                   const float* __restrict__ T16, const int* __restrict__ inl,
+                                                   stocs_b200_record* __restrict__ rec_out) {
   __shared__ unsigned long long s_keys[8 * 32];
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * 8 + w;
   const long long nwarps = (long long)gridDim.x * 8;
@@ -56,35 +86,29 @@ __global__ void __launch_bounds__(256) topk_partial_kernel(const float* __restri
   s_keys[w * 32 + lane] = mine;
   __syncthreads();
   if (w == 0) {
-    for (int k = 1; k < 8; ++k) warp_offer(mine, s_keys[k * 32 + lane], lane);
-    out[(long long)blockIdx.x * 32 + lane] = mine;
+    for (int k = 1; k < 8; ++k) warp_merge_sorted(mine, s_keys[k * 32 + lane], lane);
+    lists[(long long)blockIdx.x * 32 + lane] = mine;
+    __threadfence();
+    if (lane == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
-}
-
-// final merge of nlists sorted lists: 32 warps take a strided share each, warp 0 merges the rest
-// With rec_out != NULL the K winners are also packed as 64-byte records {lcp, inliers, global
-// index, rows 0..2 of the transform} -- the unit of the multi-GPU all-gather (comm.cu).
-__global__ void __launch_bounds__(1024) topk_merge_kernel(const unsigned long long* __restrict__ keys, long long nlists,
-                                                          int K, long long index_offset, long long* __restrict__ out_idx,
-                                                          float* __restrict__ out_lcp, const float* __restrict__ T16,
-                                                          const int* __restrict__ inl, stocs_b200_record* __restrict__ rec_out) {
-  __shared__ unsigned long long s_keys[32 * 32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned long long mine = 0ull;
-  for (long long l = w; l < nlists; l += 32) warp_offer(mine, keys[l * 32 + lane], lane);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last CTA: merge the gridDim.x sorted lists
+  mine = 0ull;
+  for (long long l = w; l < (long long)gridDim.x; l += 8)
+    warp_merge_sorted(mine, __ldcg(lists + l * 32 + lane), lane);   // written by other CTAs: bypass L1
   s_keys[w * 32 + lane] = mine;
   __syncthreads();
-  // tournament over the 32 per-warp lists: in round r the warps whose index is a multiple of 2^(r+1)
-  // absorb the list of warp + 2^r -- 5 dependent merges instead of 31 by one warp (the launch sits
-  // on the critical path of every step: 33 -> 14 us cold)
-  for (int stride = 1; stride < 32; stride <<= 1) {
+  for (int stride = 1; stride < 8; stride <<= 1) {
     if ((w & (2 * stride - 1)) == 0) {
-      warp_offer(mine, s_keys[(w + stride) * 32 + lane], lane);
+      warp_merge_sorted(mine, s_keys[(w + stride) * 32 + lane], lane);
       s_keys[w * 32 + lane] = mine;
     }
     __syncthreads();
   }
   if (w != 0) return;
+  if (lane == 0) *ticket = 0u;      // ready for the next launch (launches on one context are stream-ordered)
   if (lane < K) {
     const long long local = (long long)(0xffffffffull - (mine & 0xffffffffull));
     if (out_idx) {
@@ -189,10 +213,14 @@ int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K,
   long long need = (H + 2047) / 2048;   // at least 256 keys per warp: fewer, longer lists for the merge
   if (need < 1) need = 1;
   if (blocks > need) blocks = (int)need;
-  STOCS_CUDA(ctx, ctx->d_work.ensure((size_t)blocks * 32 * 8));
-  topk_partial_kernel<<<blocks, 256, 0, st>>>(d_lcp, H, ctx->d_work.as<unsigned long long>());
-  topk_merge_kernel<<<1, 1024, 0, st>>>(ctx->d_work.as<unsigned long long>(), blocks, K, index_offset,
-                                        (long long*)d_idx, d_val, d_T16, d_inl, d_rec);
+  // per-stream scratch: launches on the context stream and on its second stream (the host-buffer
+  // calls overlap their result copies with the reduction) must not share lists or ticket
+  const int which = (st == ctx->aux_stream) ? 1 : 0;
+  DevBuf& lists = which ? ctx->pool[POOL_TOPK_LISTS_AUX] : ctx->d_work;
+  STOCS_CUDA(ctx, lists.ensure((size_t)blocks * 32 * 8));
+  unsigned* ticket = (unsigned*)(ctx->d_small.as<char>() + 3344) + which;   // zero at creation, reset by the last CTA
+  topk_kernel<<<blocks, 256, 0, st>>>(d_lcp, H, lists.as<unsigned long long>(), ticket, K, index_offset,
+                                      (long long*)d_idx, d_val, d_T16, d_inl, d_rec);
   STOCS_CUDA(ctx, cudaGetLastError());
   return STOCS_OK;
 }

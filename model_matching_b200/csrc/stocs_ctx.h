@@ -81,6 +81,8 @@ enum PoolSlot : int {
   POOL_SHARD_T = 42, POOL_SHARD_LCP, POOL_SHARD_INL,
   // score.cu: claim order of the heavy-first schedule (one int per hypothesis of the launch)
   POOL_SCORE_ORDER = 45,
+  // reduce.cu: per-CTA top-32 lists of reductions launched on the context's second stream
+  POOL_TOPK_LISTS_AUX = 46,
   POOL_COUNT = 48
 };
 

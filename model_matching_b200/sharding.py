@@ -33,7 +33,7 @@ def empty_records(K):
 
 
 def local_records(lcp, inliers, T16, lo, K):
-    """K best of one block as records (what reduce.cu's topk_merge_kernel packs): lcp > 0 only,
+    """K best of one block as records (what reduce.cu's topk_kernel packs): lcp > 0 only,
     ordered by (lcp descending, index ascending), global index = lo + local index."""
     lcp = np.asarray(lcp, np.float32)
     order = np.lexsort((np.arange(lcp.size), -lcp.astype(np.float64)))

@@ -168,14 +168,14 @@ def main():
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:20]:
         out.append(f"{k:54s} n={v[0]:4d} total_ms={v[1] / 1e6:10.3f} share={v[1] / tot:.4f}")
     big = [num(r[mv]) for r in rows[hi + 1:] if len(r) > mv and "score_lcp_kernel" in r[kn] and num(r[mv]) > 1.5e6]
-    tp = [num(r[mv]) for r in rows[hi + 1:] if len(r) > mv and "topk_partial_kernel" in r[kn]]
-    tm = [num(r[mv]) for r in rows[hi + 1:] if len(r) > mv and "topk_merge_kernel" in r[kn]]
-    if big and tp and tm:
+    tp = [num(r[mv]) for r in rows[hi + 1:] if len(r) > mv and "topk_kernel" in r[kn]]
+    tm = [0.0]
+    if big and tp:
         mean = lambda v: sum(v) / len(v)
-        step = mean(big) + mean(tp) + mean(tm)
+        step = mean(big) + mean(tp)
         bj = json.load(open(bench))
-        out.append("# one bench step at N=1 = score_lcp_kernel (10^6 hypotheses) + topk_partial + topk_merge (packs the 64-byte records):")
-        out.append(f"#   ncu: {mean(big) / 1e6:.3f} + {mean(tp) / 1e6:.3f} + {mean(tm) / 1e6:.3f} ms -> score share {mean(big) / step:.3f}")
+        out.append("# one bench step at N=1 = score_lcp_kernel (10^6 hypotheses) + topk_kernel (top-32, packs the 64-byte records):")
+        out.append(f"#   ncu: {mean(big) / 1e6:.3f} + {mean(tp) / 1e6:.3f} ms -> score share {mean(big) / step:.3f}")
         out.append(f"#   bench.py (CUDA events): kernel_ms {bj['roofline']['kernel_ms']:.3f} of ms_per_step {bj['ms_per_step']:.3f}"
                    f" -> share {bj['roofline']['kernel_ms'] / bj['ms_per_step']:.3f}")
     open(os.path.join(ROOT, f"profiles/{tag}_launch_shares.txt"), "w").write("\n".join(out) + "\n")
