@@ -65,10 +65,15 @@ int stocs_b200_create(stocs_b200_ctx** out, int device) {
             cudaEventCreateWithFlags(&ctx->join_ev[0], cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->join_ev[1], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaHostAlloc((void**)&ctx->h_top, sizeof(stocs_b200_ctx::TopCache), cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&ctx->h_pipe_state, sizeof(StocsPipeState), cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&ctx->h_index_counts, 64, cudaHostAllocDefault) == cudaSuccess;
   for (int i = 0; ok && i < stocs_b200_ctx::kMaxChunks; ++i)
     ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { g_create_err = "stream/event creation failed"; delete ctx; return STOCS_E_CUDA; }
   ctx->dot_thr = stocs_angle_threshold_dot();
+  // initial capacities of the online stages (tests shrink them to exercise the grow-and-retry path)
+  if (const char* e = getenv("STOCS_CONG_CAP_CODES")) { const long long v = atoll(e); if (v >= 1 && v < (1ll << 31)) ctx->cong_cap_codes = v; }
+  if (const char* e = getenv("STOCS_CONG_CAP_QUADS")) { const long long v = atoll(e); if (v >= 1 && v < (1ll << 31)) ctx->cong_cap_quads = v; }
   if (ctx->d_small.ensure(4096) != cudaSuccess || cudaMemset(ctx->d_small.p, 0, 4096) != cudaSuccess) {
     g_create_err = "device allocation failed";
     stocs_b200_destroy(ctx);
@@ -101,6 +106,8 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   for (int i = 0; i < 2; ++i) if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->h_top) cudaFreeHost(ctx->h_top);
+  if (ctx->h_pipe_state) cudaFreeHost(ctx->h_pipe_state);
+  if (ctx->h_index_counts) cudaFreeHost(ctx->h_index_counts);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;

@@ -14,6 +14,14 @@
 // computes (cell, 343-bit cone mask, queryQ) per Q entry, and one warp per P entry sweeps its
 // base's Q list (cheap 4-byte cell compare first), counting, then writing in ballot order, which
 // is exactly the std::set order of the reference.
+//
+// The whole search is ENQUEUED without a host round trip (stocs_congruent_enqueue): list lengths,
+// segment offsets and quad counts stay on the device in a StocsPipeState record, the buffers are
+// sized by capacities kept in the context, every kernel takes its bounds from the record (grid-stride
+// loops), and a search that does not fit raises `overflow` there, which empties its later stages;
+// the caller reads the record once, grows the capacities and enqueues the search again.  (Round 1 read
+// the list lengths, the quad total and the per-base offsets back one after the other: three
+// synchronisations, ~0.2 ms of a 0.45 ms stage on the YCB frame.)
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 
@@ -47,12 +55,16 @@ __device__ __forceinline__ V3 ld3(const float4* p, int i) { const float4 v = p[i
 
 // per base: PPF keys of the two base segments, alpha, list lengths
 __global__ void cong_count_kernel(const float4* __restrict__ spos4, const float4* __restrict__ sattr, PpfView v,
-                                  const int* __restrict__ base_idx4, const float* __restrict__ inv2, int n_bases,
-                                  BaseInfo* __restrict__ info) {
+                                  const int* __restrict__ base_idx4, const float* __restrict__ inv2,
+                                  const uint8_t* __restrict__ valid, int n_bases, BaseInfo* __restrict__ info) {
   const int b = blockIdx.x;
   const int j = threadIdx.x;  // 256 threads: 0..127 -> P bins, 128..255 -> Q bins
   __shared__ BaseInfo s;
   __shared__ uint32_t s_cnt[256];
+  if (valid && !valid[b]) {   // a base the sampler rejected keeps its slot with empty lists
+    if (j == 0) { BaseInfo z; memset(&z, 0, sizeof(z)); info[b] = z; }
+    return;
+  }
   if (j == 0) {
     const int* id = base_idx4 + 4 * b;
     const V3 p0 = ld3(spos4, id[0]), p1 = ld3(spos4, id[1]), p2 = ld3(spos4, id[2]), p3 = ld3(spos4, id[3]);
@@ -80,12 +92,65 @@ __global__ void cong_count_kernel(const float4* __restrict__ spos4, const float4
   }
 }
 
+// exclusive scan of one value per thread over a 256-thread block; *total = the block's sum
+__device__ __forceinline__ unsigned long long block_excl_scan_256(unsigned long long v, unsigned long long* s_buf,
+                                                                  unsigned long long* total) {
+  const int j = threadIdx.x;
+  s_buf[j] = v;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const unsigned long long up = (j >= o) ? s_buf[j - o] : 0ull;
+    __syncthreads();
+    s_buf[j] += up;
+    __syncthreads();
+  }
+  const unsigned long long incl = s_buf[j];
+  *total = s_buf[255];
+  __syncthreads();
+  return incl - v;
+}
+
+// segment offsets of the flat code buffer, [P_0..P_{n-1} | Q_0..Q_{n-1} | total], from the list lengths
+// (index bookkeeping only; one block).  Lists that do not fit the code buffers leave every segment
+// empty and raise the overflow flag.
+__global__ void __launch_bounds__(256) cong_seg_kernel(const BaseInfo* __restrict__ info, int n_bases, uint32_t* __restrict__ seg,
+                                                        unsigned long long cap_codes, StocsPipeState* __restrict__ stt) {
+  __shared__ unsigned long long s_buf[256];
+  const int j = threadIdx.x;
+  const int per = (n_bases + 255) / 256;
+  const int b0 = min(n_bases, j * per), b1 = min(n_bases, b0 + per);
+  unsigned long long locP = 0, locQ = 0;
+  for (int b = b0; b < b1; ++b) { locP += info[b].nP; locQ += info[b].nQ; }
+  unsigned long long totalP, totalQ;
+  unsigned long long offP = block_excl_scan_256(locP, s_buf, &totalP);
+  unsigned long long offQ = block_excl_scan_256(locQ, s_buf, &totalQ);
+  const unsigned long long total = totalP + totalQ;
+  const uint32_t ovf = (total >= (1ull << 31)) ? 4u : (total > cap_codes ? 1u : 0u);
+  if (ovf) {
+    for (int b = b0; b < b1; ++b) { seg[b] = 0u; seg[n_bases + b] = 0u; }
+  } else {
+    offQ += totalP;
+    for (int b = b0; b < b1; ++b) {
+      seg[b] = (uint32_t)offP; offP += info[b].nP;
+      seg[n_bases + b] = (uint32_t)offQ; offQ += info[b].nQ;
+    }
+  }
+  if (j == 0) {
+    seg[2 * n_bases] = ovf ? 0u : (uint32_t)total;
+    stt->need_codes = total;
+    stt->totalP = ovf ? 0u : (uint32_t)totalP;
+    stt->total = ovf ? 0u : (uint32_t)total;
+    stt->overflow |= ovf;
+  }
+}
+
 // copy the source-bin ranges of both lists into the flat code buffer (unsorted)
 __global__ void cong_gather_kernel(PpfView v, const BaseInfo* __restrict__ info, const uint32_t* __restrict__ seg_off,
-                                   int n_bases, uint32_t* __restrict__ codes) {
+                                   int n_bases, uint32_t* __restrict__ codes, const StocsPipeState* __restrict__ stt) {
   const int b = blockIdx.x;
   const int j = threadIdx.x;
   __shared__ uint32_t s_start[256], s_cnt[256], s_off[256];
+  if (stt->overflow) return;
   const BaseInfo bi = info[b];
   if (bi.nP == 0) return;
   const Ppf4 f = (j < 128) ? bi.f1 : bi.f2;
@@ -122,11 +187,11 @@ struct QEntry { float qx, qy, qz; uint32_t mask[11]; };          // queryQ (mode
 
 // entry e of the flat (sorted) code buffer: P entries first, then Q entries
 __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
-                                    const BaseInfo* __restrict__ info, int n_bases, uint32_t totalP, uint32_t total,
+                                    const BaseInfo* __restrict__ info, int n_bases, const StocsPipeState* __restrict__ stt,
                                     const float4* __restrict__ mpos4, ModelNorm mn, PEntry* __restrict__ pe,
                                     QEntry* __restrict__ qe, int* __restrict__ qcell) {
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
+  const uint32_t totalP = stt->totalP, total = stt->total;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
   const bool isP = e < totalP;
   // find the base (segment) by binary search in seg_off (2*n_bases+1 entries)
   int lo = isP ? 0 : n_bases, hi = isP ? n_bases : 2 * n_bases;
@@ -196,18 +261,21 @@ __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const ui
     qe[e - totalP] = o;
     qcell[e - totalP] = index_pos(mn, query);
   }
+  }
 }
 
 // one warp per P entry; WRITE=false counts, WRITE=true emits quads
 template <bool WRITE>
 __global__ void cong_match_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
-                                  int n_bases, uint32_t totalP, const PEntry* __restrict__ pe,
+                                  int n_bases, const StocsPipeState* __restrict__ stt, const PEntry* __restrict__ pe,
                                   const QEntry* __restrict__ qe, const int* __restrict__ qcell, float thr,
                                   uint32_t* __restrict__ counts, const uint32_t* __restrict__ out_off,
                                   int* __restrict__ quads) {
-  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (wid >= totalP) return;
+  const uint32_t totalP = stt->totalP;
+  if (WRITE && stt->overflow) return;   // the quads would not fit: the caller grows the buffer and searches again
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < totalP; wid += nwarps) {
   int lo = 0, hi = n_bases;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -246,15 +314,25 @@ __global__ void cong_match_kernel(const uint32_t* __restrict__ codes, const uint
     }
   }
   if (!WRITE && lane == 0) counts[wid] = cnt;
+  }
 }
 
-__global__ void cong_base_offsets_kernel(const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ pscan,
-                                         int n_bases, uint32_t totalP, uint32_t total_quads,
-                                         long long* __restrict__ quad_off) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > n_bases) return;
-  const uint32_t e = (b < n_bases) ? seg_off[b] : totalP;
-  quad_off[b] = (e < totalP) ? (long long)pscan[e] : (long long)total_quads;
+// quad total and per-base quad offsets from the scanned per-P counts (one block)
+__global__ void __launch_bounds__(256) cong_base_offsets_kernel(const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ pscan,
+                                                                 int n_bases, unsigned long long cap_quads,
+                                                                 StocsPipeState* __restrict__ stt, long long* __restrict__ quad_off) {
+  const uint32_t totalP = stt->totalP;
+  const uint32_t total_quads = pscan[totalP];
+  const bool ovf = (unsigned long long)total_quads > cap_quads;
+  for (int b = threadIdx.x; b <= n_bases; b += blockDim.x) {
+    const uint32_t e = (b < n_bases) ? seg_off[b] : totalP;
+    quad_off[b] = ovf ? 0ll : ((e < totalP) ? (long long)pscan[e] : (long long)total_quads);
+  }
+  if (threadIdx.x == 0) {
+    stt->need_quads = total_quads;
+    stt->total_quads = ovf ? 0u : total_quads;
+    if (ovf) stt->overflow |= 2u;
+  }
 }
 
 }  // namespace
@@ -283,84 +361,80 @@ static ModelNorm model_norm(const stocs_b200_ctx* ctx) {
   return m;
 }
 
-// Device-resident congruent-set search.  d_base_idx4 / d_inv2: n_bases entries on the device.
-// On return *d_quads_out points to ctx-owned device memory holding total quads (int4 each) and
-// h_quad_off (n_bases+1) is filled on the host.
-int stocs_congruent_device(stocs_b200_ctx* ctx, int n_bases, const int* d_base_idx4, const float* d_inv2,
-                           DevBuf& quads_buf, std::vector<long long>& h_quad_off, cudaStream_t st) {
-  h_quad_off.assign((size_t)n_bases + 1, 0);
-  if (n_bases == 0) return STOCS_OK;
+// Enqueues the congruent-set search of n_bases bases on `st`; nothing is read back.
+//   d_base_idx4 / d_inv2 / d_valid (may be NULL: all valid): per base, on the device
+//   d_state: the run's StocsPipeState (the CALLER zeroes it); this search fills need_codes, need_quads,
+//            totalP, total, total_quads and may raise overflow bits 1 / 2 / 4
+//   d_quad_off: n_bases + 1 offsets into the quad buffer ctx->pool[POOL_CONG_QUADS]
+// Buffers are sized by ctx->cong_cap_codes / cong_cap_quads; stocs_congruent_grow() raises them from a
+// state record that came back with overflow set.
+int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_idx4, const float* d_inv2,
+                            const uint8_t* d_valid, StocsPipeState* d_state, long long* d_quad_off, cudaStream_t st) {
+  if (n_bases <= 0) return STOCS_OK;
   const PpfView v = stocs_ppf_view(ctx);
   DevBuf &d_info = ctx->pool[POOL_CONG_INFO], &d_seg = ctx->pool[POOL_CONG_SEG], &d_codes_a = ctx->pool[POOL_CONG_CODES_A], &d_codes_b = ctx->pool[POOL_CONG_CODES_B], &d_tmp = ctx->pool[POOL_CONG_TMP],
          &d_pe = ctx->pool[POOL_CONG_PE], &d_qe = ctx->pool[POOL_CONG_QE], &d_qcell = ctx->pool[POOL_CONG_QCELL], &d_cnt = ctx->pool[POOL_CONG_CNT], &d_scan = ctx->pool[POOL_CONG_SCAN],
-         &d_qoff = ctx->pool[POOL_CONG_QOFF];
-  auto cleanup = [&]() {};  // pool slots persist
-#define CG(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
+         &quads_buf = ctx->pool[POOL_CONG_QUADS];
+#define CG(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return STOCS_E_CUDA; } } while (0)
+  const size_t cap = (size_t)ctx->cong_cap_codes, capq = (size_t)ctx->cong_cap_quads;
   CG(d_info.ensure((size_t)n_bases * sizeof(BaseInfo)));
+  CG(d_seg.ensure(((size_t)2 * n_bases + 1) * 4));
+  CG(d_codes_a.ensure(cap * 4));
+  CG(d_codes_b.ensure(cap * 4));
+  CG(d_pe.ensure(cap * sizeof(PEntry)));
+  CG(d_qe.ensure(cap * sizeof(QEntry)));
+  CG(d_qcell.ensure(cap * 4));
+  CG(d_cnt.ensure((cap + 1) * 4));
+  CG(d_scan.ensure((cap + 1) * 4));
+  CG(quads_buf.ensure(capq * 16));
+  // (id1 << 16) | id2 with ids < M: the bits above 16 + ceil(log2 M) are zero
+  int end_bit = 17;
+  while (end_bit < 32 && (1 << (end_bit - 16)) < ctx->M) ++end_bit;
+  size_t tb = 0, tb2 = 0;
+  cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, d_codes_a.as<uint32_t>(), d_codes_b.as<uint32_t>(), (int)cap,
+                                          2 * n_bases, d_seg.as<uint32_t>(), d_seg.as<uint32_t>() + 1, 0, end_bit, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(cap + 1), st);
+  CG(d_tmp.ensure(tb > tb2 ? tb : tb2));
+
   cong_count_kernel<<<n_bases, 256, 0, st>>>(ctx->d_spos4.as<float4>(), ctx->d_sattr.as<float4>(), v, d_base_idx4, d_inv2,
-                                             n_bases, d_info.as<BaseInfo>());
-  std::vector<BaseInfo> h_info((size_t)n_bases);
-  CG(cudaMemcpyAsync(h_info.data(), d_info.p, (size_t)n_bases * sizeof(BaseInfo), cudaMemcpyDeviceToHost, st));
-  CG(cudaStreamSynchronize(st));
-  // segment offsets: [P_0..P_{n-1} | Q_0..Q_{n-1}] (index bookkeeping only)
-  std::vector<uint32_t> seg((size_t)2 * n_bases + 1, 0);
-  uint64_t acc = 0;
-  for (int b = 0; b < n_bases; ++b) { seg[b] = (uint32_t)acc; acc += h_info[b].nP; }
-  const uint32_t totalP = (uint32_t)acc;
-  for (int b = 0; b < n_bases; ++b) { seg[n_bases + b] = (uint32_t)acc; acc += h_info[b].nQ; }
-  seg[2 * n_bases] = (uint32_t)acc;
-  if (acc >= (1ull << 31)) { ctx->err = "find_congruent: pair lists too long"; cleanup(); return STOCS_E_ARG; }
-  const uint32_t total = (uint32_t)acc;
-  if (totalP == 0) { cleanup(); return STOCS_OK; }
-  const uint32_t totalQ = total - totalP;
-  CG(d_seg.ensure(seg.size() * 4));
-  CG(cudaMemcpyAsync(d_seg.p, seg.data(), seg.size() * 4, cudaMemcpyHostToDevice, st));
-  CG(d_codes_a.ensure((size_t)total * 4));
-  CG(d_codes_b.ensure((size_t)total * 4));
-  cong_gather_kernel<<<n_bases, 256, 0, st>>>(v, d_info.as<BaseInfo>(), d_seg.as<uint32_t>(), n_bases, d_codes_a.as<uint32_t>());
-  // per-list sort by (id1, id2): the reference's list order (insertion order of the pair loop)
-  size_t tb = 0;
-  cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, d_codes_a.as<uint32_t>(), d_codes_b.as<uint32_t>(), (int)total,
-                                          2 * n_bases, d_seg.as<uint32_t>(), d_seg.as<uint32_t>() + 1, 0, 32, st);
-  CG(d_tmp.ensure(tb));
-  cub::DeviceSegmentedRadixSort::SortKeys(d_tmp.p, tb, d_codes_a.as<uint32_t>(), d_codes_b.as<uint32_t>(), (int)total,
-                                          2 * n_bases, d_seg.as<uint32_t>(), d_seg.as<uint32_t>() + 1, 0, 32, st);
+                                             d_valid, n_bases, d_info.as<BaseInfo>());
+  cong_seg_kernel<<<1, 256, 0, st>>>(d_info.as<BaseInfo>(), n_bases, d_seg.as<uint32_t>(), (unsigned long long)cap, d_state);
+  cong_gather_kernel<<<n_bases, 256, 0, st>>>(v, d_info.as<BaseInfo>(), d_seg.as<uint32_t>(), n_bases, d_codes_a.as<uint32_t>(), d_state);
+  // per-list sort by (id1, id2): the reference's list order (insertion order of the pair loop).
+  // num_items only sizes the library's scratch; the segments come from d_seg on the device.
+  cub::DeviceSegmentedRadixSort::SortKeys(d_tmp.p, tb, d_codes_a.as<uint32_t>(), d_codes_b.as<uint32_t>(), (int)cap,
+                                          2 * n_bases, d_seg.as<uint32_t>(), d_seg.as<uint32_t>() + 1, 0, end_bit, st);
   const uint32_t* codes = d_codes_b.as<uint32_t>();
-  CG(d_pe.ensure((size_t)totalP * sizeof(PEntry)));
-  CG(d_qe.ensure((size_t)totalQ * sizeof(QEntry)));
-  CG(d_qcell.ensure((size_t)totalQ * 4));
   const ModelNorm mn = model_norm(ctx);
-  cong_prepare_kernel<<<(total + 127) / 128, 128, 0, st>>>(codes, d_seg.as<uint32_t>(), d_info.as<BaseInfo>(), n_bases, totalP,
-                                                           total, ctx->d_mpos4.as<float4>(), mn, d_pe.as<PEntry>(),
-                                                           d_qe.as<QEntry>(), d_qcell.as<int>());
-  CG(d_cnt.ensure((size_t)(totalP + 1) * 4));
-  CG(d_scan.ensure((size_t)(totalP + 1) * 4));
-  CG(cudaMemsetAsync(d_cnt.p, 0, (size_t)(totalP + 1) * 4, st));
-  const unsigned mblocks = (unsigned)(((size_t)totalP * 32 + 255) / 256);
-  cong_match_kernel<false><<<mblocks, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, totalP, d_pe.as<PEntry>(),
-                                                    d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, d_cnt.as<uint32_t>(),
-                                                    nullptr, nullptr);
-  size_t tb2 = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(totalP + 1), st);
-  CG(d_tmp.ensure(tb2));
-  cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(totalP + 1), st);
-  uint32_t total_quads = 0;
-  CG(cudaMemcpyAsync(&total_quads, d_scan.as<uint32_t>() + totalP, 4, cudaMemcpyDeviceToHost, st));
-  CG(cudaStreamSynchronize(st));
-  CG(quads_buf.ensure((size_t)(total_quads ? total_quads : 1) * 16));
-  if (total_quads)
-    cong_match_kernel<true><<<mblocks, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, totalP, d_pe.as<PEntry>(),
-                                                     d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, nullptr,
-                                                     d_scan.as<uint32_t>(), quads_buf.as<int>());
-  CG(d_qoff.ensure((size_t)(n_bases + 1) * 8));
-  cong_base_offsets_kernel<<<(n_bases + 1 + 127) / 128, 128, 0, st>>>(d_seg.as<uint32_t>(), d_scan.as<uint32_t>(), n_bases,
-                                                                      totalP, total_quads, d_qoff.as<long long>());
-  CG(cudaMemcpyAsync(h_quad_off.data(), d_qoff.p, (size_t)(n_bases + 1) * 8, cudaMemcpyDeviceToHost, st));
-  CG(cudaStreamSynchronize(st));
+  const unsigned wide = (unsigned)ctx->num_sms * 8;
+  cong_prepare_kernel<<<wide, 128, 0, st>>>(codes, d_seg.as<uint32_t>(), d_info.as<BaseInfo>(), n_bases, d_state,
+                                            ctx->d_mpos4.as<float4>(), mn, d_pe.as<PEntry>(), d_qe.as<QEntry>(), d_qcell.as<int>());
+  CG(cudaMemsetAsync(d_cnt.p, 0, (cap + 1) * 4, st));
+  cong_match_kernel<false><<<wide, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
+                                                 d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, d_cnt.as<uint32_t>(), nullptr, nullptr);
+  cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(cap + 1), st);
+  cong_base_offsets_kernel<<<1, 256, 0, st>>>(d_seg.as<uint32_t>(), d_scan.as<uint32_t>(), n_bases, (unsigned long long)capq,
+                                              d_state, d_quad_off);
+  cong_match_kernel<true><<<wide, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
+                                                d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, nullptr, d_scan.as<uint32_t>(),
+                                                quads_buf.as<int>());
   CG(cudaGetLastError());
 #undef CG
-  cleanup();
   return STOCS_OK;
+}
+
+// After a state record came back with overflow bits 1 or 2: raise the capacities to what the search
+// needs (+25 %).  Returns false when the search can never fit (bit 4: pair lists of 2^31 entries or more).
+bool stocs_congruent_grow(stocs_b200_ctx* ctx, const StocsPipeState& s) {
+  if (s.overflow & 4u) return false;
+  if ((s.overflow & 1u) && (long long)s.need_codes > ctx->cong_cap_codes) {
+    long long want = (long long)(s.need_codes + s.need_codes / 4 + 1024);
+    if (want >= (1ll << 31)) want = (1ll << 31) - 1;
+    ctx->cong_cap_codes = want;
+  }
+  if ((s.overflow & 2u) && (long long)s.need_quads > ctx->cong_cap_quads)
+    ctx->cong_cap_quads = (long long)(s.need_quads + s.need_quads / 4 + 1024);
+  return true;
 }
 
 extern "C" int stocs_b200_find_congruent(stocs_b200_ctx* ctx, int n_bases, const int32_t* base_idx4, const float* inv2,
@@ -371,25 +445,35 @@ extern "C" int stocs_b200_find_congruent(stocs_b200_ctx* ctx, int n_bases, const
     STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: bad argument");
   for (int i = 0; i < 4 * n_bases; ++i)
     if (base_idx4[i] < 0 || base_idx4[i] >= ctx->S) STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: base index out of range");
+  quad_offsets[0] = 0;
+  if (n_bases == 0) return STOCS_OK;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)(n_bases ? n_bases : 1) * 24));
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure((size_t)n_bases * 24));
   int* d_ids = ctx->d_tmp2.as<int>();
   float* d_inv = (float*)(d_ids + 4 * (size_t)n_bases);
-  if (n_bases) {
-    STOCS_CUDA(ctx, cudaMemcpyAsync(d_ids, base_idx4, (size_t)n_bases * 16, cudaMemcpyHostToDevice, st));
-    STOCS_CUDA(ctx, cudaMemcpyAsync(d_inv, inv2, (size_t)n_bases * 8, cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(d_ids, base_idx4, (size_t)n_bases * 16, cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(d_inv, inv2, (size_t)n_bases * 8, cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, ctx->pool[POOL_PIPE_STATE].ensure(sizeof(StocsPipeState)));
+  STOCS_CUDA(ctx, ctx->pool[POOL_CONG_QOFF].ensure((size_t)(n_bases + 1) * 8));
+  StocsPipeState* d_state = ctx->pool[POOL_PIPE_STATE].as<StocsPipeState>();
+  long long* d_qoff = ctx->pool[POOL_CONG_QOFF].as<long long>();
+  StocsPipeState& hs = *ctx->h_pipe_state;
+  for (int attempt = 0;; ++attempt) {
+    STOCS_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(StocsPipeState), st));
+    const int rc = stocs_congruent_enqueue(ctx, n_bases, d_ids, d_inv, nullptr, d_state, d_qoff, st);
+    if (rc) return rc;
+    STOCS_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(StocsPipeState), cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaMemcpyAsync(quad_offsets, d_qoff, (size_t)(n_bases + 1) * 8, cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (!hs.overflow) break;
+    if (!stocs_congruent_grow(ctx, hs) || attempt >= 2) STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: pair lists too long");
   }
-  DevBuf& quads = ctx->pool[POOL_CONG_QUADS];
-  std::vector<long long> off;
-  int rc = stocs_congruent_device(ctx, n_bases, d_ids, d_inv, quads, off, st);
-  if (rc) return rc;
-  for (int b = 0; b <= n_bases; ++b) quad_offsets[b] = off[b];
-  const long long total = off[n_bases];
+  const long long total = (long long)hs.total_quads;
   if (total > cap) STOCS_FAIL(ctx, STOCS_E_CAPACITY, "find_congruent: quads4 capacity too small");
   if (total > 0) {
     if (!quads4) STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: quads4 is NULL");
-    STOCS_CUDA(ctx, cudaMemcpyAsync(quads4, quads.p, (size_t)total * 16, cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaMemcpyAsync(quads4, ctx->pool[POOL_CONG_QUADS].p, (size_t)total * 16, cudaMemcpyDeviceToHost, st));
     STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   }
   return STOCS_OK;

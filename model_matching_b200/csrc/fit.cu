@@ -17,8 +17,9 @@ using namespace stocsm;
 
 int stocs_launch_sample(stocs_b200_ctx* ctx, uint64_t seed, uint32_t first_base_no, int n_bases, int* d_ids,
                         float* d_inv, uint8_t* d_valid, cudaStream_t st);
-int stocs_congruent_device(stocs_b200_ctx* ctx, int n_bases, const int* d_base_idx4, const float* d_inv2,
-                           DevBuf& quads_buf, std::vector<long long>& h_quad_off, cudaStream_t st);
+int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_idx4, const float* d_inv2,
+                            const uint8_t* d_valid, StocsPipeState* d_state, long long* d_quad_off, cudaStream_t st);  // congruent.cu
+bool stocs_congruent_grow(stocs_b200_ctx* ctx, const StocsPipeState& s);
 
 namespace {
 
@@ -49,13 +50,14 @@ struct FitArgs {
   float* __restrict__ Tw;
   uint8_t* __restrict__ ok;
   long long n;
+  const long long* __restrict__ n_dev;  // optional: the item count lives on the device (n is then ignored)
   float cs[3], cm[3];
   int S, M;
 };
 
 __global__ void fit_kernel(FitArgs a) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.n) return;
+  const long long n = a.n_dev ? *a.n_dev : a.n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
   const int* bid = a.base_idx4 + 4 * (size_t)(a.item_base ? a.item_base[t] : t);
   const int* qd = a.quads4 + 4 * (size_t)(a.item_quad ? a.item_quad[t] : t);
   float* Tc = a.Tc + 16 * (size_t)t;
@@ -87,7 +89,7 @@ __global__ void fit_kernel(FitArgs a) {
     const float qnan = __int_as_float(0x7fc00000);
     for (int k = 0; k < 16; ++k) { Tc[k] = qnan; if (Tw) Tw[k] = qnan; }
     a.ok[t] = 0;
-    return;
+    continue;
   }
   const V3 nc2 = v3(-c2.x, -c2.y, -c2.z);
   const float c1a[3] = {c1.x, c1.y, c1.z};
@@ -104,6 +106,71 @@ __global__ void fit_kernel(FitArgs a) {
     Tw[3] = Tw[7] = Tw[11] = 0.f; Tw[15] = 1.f;
   }
   a.ok[t] = 1;
+  }
+}
+
+// item offsets of the pipeline from the per-base quad offsets: min(cnt, max_sets) transforms per base
+// (one block; the total goes to the state record)
+__global__ void __launch_bounds__(256) pipe_item_offsets_kernel(const long long* __restrict__ quad_off, int n_bases, int max_sets,
+                                                                 long long* __restrict__ item_off, StocsPipeState* __restrict__ stt) {
+  __shared__ unsigned long long s_buf[256];
+  const int j = threadIdx.x;
+  const int per = (n_bases + 255) / 256;
+  const int b0 = min(n_bases, j * per), b1 = min(n_bases, b0 + per);
+  unsigned long long loc = 0;
+  for (int b = b0; b < b1; ++b) { const long long c = quad_off[b + 1] - quad_off[b]; loc += (unsigned long long)(c < max_sets ? c : max_sets); }
+  // exclusive scan of the 256 partial sums
+  s_buf[j] = loc;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const unsigned long long up = (j >= o) ? s_buf[j - o] : 0ull;
+    __syncthreads();
+    s_buf[j] += up;
+    __syncthreads();
+  }
+  unsigned long long off = s_buf[j] - loc;
+  for (int b = b0; b < b1; ++b) {
+    item_off[b] = (long long)off;
+    const long long c = quad_off[b + 1] - quad_off[b];
+    off += (unsigned long long)(c < max_sets ? c : max_sets);
+  }
+  if (j == 255) { item_off[n_bases] = (long long)s_buf[255]; stt->n_items = (long long)s_buf[255]; }
+}
+
+// closes a pipeline run (one block): transforms that passed the fit, the winner's rank among them (the
+// index the reference's transform list gives it), its base's rank among the valid bases, its two poses
+__global__ void __launch_bounds__(256) pipe_finalize_kernel(const uint8_t* __restrict__ ok, const uint8_t* __restrict__ valid, int n_bases,
+                                                             const int* __restrict__ item_base, const long long* __restrict__ best_idx,
+                                                             const float* __restrict__ best_val, const float* __restrict__ Tc,
+                                                             const float* __restrict__ Tw, StocsPipeState* __restrict__ stt) {
+  __shared__ long long s_a[256], s_b[256];
+  __shared__ int s_c[256], s_d[256];
+  const int j = threadIdx.x;
+  const long long n = stt->n_items;
+  const long long bi = best_idx[0];
+  long long n_ok = 0, before = 0;
+  for (long long i = j; i < n; i += 256) { const int o = ok[i] ? 1 : 0; n_ok += o; if (i < bi) before += o; }
+  const int bb = (bi >= 0) ? item_base[bi] : -1;
+  int n_valid = 0, valid_before = 0;
+  for (int b = j; b < n_bases; b += 256) { const int o = valid[b] ? 1 : 0; n_valid += o; if (b < bb) valid_before += o; }
+  s_a[j] = n_ok; s_b[j] = before; s_c[j] = n_valid; s_d[j] = valid_before;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (j < o) { s_a[j] += s_a[j + o]; s_b[j] += s_b[j + o]; s_c[j] += s_c[j + o]; s_d[j] += s_d[j + o]; }
+    __syncthreads();
+  }
+  if (j == 0) {
+    stt->n_ok = s_a[0];
+    stt->n_valid = s_c[0];
+    stt->best_item = bi;
+    stt->rank_of_best = (bi >= 0) ? s_b[0] : -1;
+    stt->best_base = (bi >= 0) ? s_d[0] : -1;
+    stt->best_lcp = best_val[0];
+  }
+  if (j < 16) {
+    stt->best_Tc[j] = (bi >= 0) ? Tc[16 * bi + j] : 0.f;
+    stt->best_Tw[j] = (bi >= 0) ? Tw[16 * bi + j] : 0.f;
+  }
 }
 
 // item list of the pipeline: for base b with cnt quads, take all when cnt < max_sets, else
@@ -129,7 +196,7 @@ static void fill_fit_args(stocs_b200_ctx* ctx, FitArgs& a) {
   a.mpos4 = ctx->d_mpos4.as<float4>();
   for (int k = 0; k < 3; ++k) { a.cs[k] = ctx->cs[k]; a.cm[k] = ctx->cm[k]; }
   a.S = ctx->S; a.M = ctx->M;
-  a.item_base = nullptr; a.item_quad = nullptr;
+  a.item_base = nullptr; a.item_quad = nullptr; a.n_dev = nullptr;
 }
 
 extern "C" int stocs_b200_fit_transforms(stocs_b200_ctx* ctx, int64_t n, const int32_t* base_idx4, const int32_t* quads4,
@@ -165,7 +232,9 @@ int stocs_launch_sample_instance(stocs_b200_ctx* ctx, uint64_t seed, int base_nu
                                  float* d_inv, uint8_t* d_valid, cudaStream_t st);  // sample_instance.cu
 
 // mode 0: class-mode bases (independent, one launch for all); mode 1: instance-mode bases (sequentially
-// coupled: one launch per base, base numbers 1..n_bases, enqueued back to back without host round trips)
+// coupled: one launch per base, base numbers 1..n_bases).  The whole chain -- bases, congruent sets, item
+// selection, fits, scores, best, result record -- is enqueued back to back against capacities and the
+// host synchronises ONCE, on the 200-byte state record (round 1: six synchronisations per pose).
 static int run_pipeline_impl(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, int max_sets, int mode, float dispersion,
                              stocs_b200_pipeline_result* result) {
   if (!ctx) return STOCS_E_ARG;
@@ -178,7 +247,8 @@ static int run_pipeline_impl(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, in
   memset(result, 0, sizeof(*result));
   result->best_index = -1;
   result->best_base = -1;
-  // 1. bases
+  // 1. bases (rejected ones keep their slot, flagged in d_valid: every later stage skips them, so the
+  // order of the valid bases -- base_set of the reference driver -- is preserved without compaction)
   DevBuf& d_bases = ctx->pool[POOL_PIPE_BASES];
   STOCS_CUDA(ctx, d_bases.ensure((size_t)n_bases * 25 + 64));
   int* d_ids = d_bases.as<int>();
@@ -193,94 +263,72 @@ static int run_pipeline_impl(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, in
       rc = stocs_launch_sample_instance(ctx, seed, b + 1, dispersion, d_ids + 4 * (size_t)b, d_inv + 2 * (size_t)b, d_valid + b, st);
   }
   if (rc) return rc;
-  std::vector<int> h_ids((size_t)4 * n_bases);
-  std::vector<float> h_inv((size_t)2 * n_bases);
-  std::vector<uint8_t> h_valid((size_t)n_bases);
-  STOCS_CUDA(ctx, cudaMemcpyAsync(h_ids.data(), d_ids, (size_t)n_bases * 16, cudaMemcpyDeviceToHost, st));
-  STOCS_CUDA(ctx, cudaMemcpyAsync(h_inv.data(), d_inv, (size_t)n_bases * 8, cudaMemcpyDeviceToHost, st));
-  STOCS_CUDA(ctx, cudaMemcpyAsync(h_valid.data(), d_valid, (size_t)n_bases, cudaMemcpyDeviceToHost, st));
-  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   tr.mark("pipeline: sample bases");
-  // keep the valid bases, in order (base_set of the reference driver)
-  std::vector<int> v_ids; std::vector<float> v_inv;
-  for (int b = 0; b < n_bases; ++b)
-    if (h_valid[b]) {
-      for (int k = 0; k < 4; ++k) v_ids.push_back(h_ids[4 * (size_t)b + k]);
-      v_inv.push_back(h_inv[2 * (size_t)b]); v_inv.push_back(h_inv[2 * (size_t)b + 1]);
-    }
-  const int nv = (int)(v_ids.size() / 4);
-  result->n_valid_bases = nv;
-  if (nv == 0) return STOCS_OK;
-  STOCS_CUDA(ctx, cudaMemcpyAsync(d_ids, v_ids.data(), (size_t)nv * 16, cudaMemcpyHostToDevice, st));
-  STOCS_CUDA(ctx, cudaMemcpyAsync(d_inv, v_inv.data(), (size_t)nv * 8, cudaMemcpyHostToDevice, st));
-  // 2. congruent sets
-  DevBuf& d_quads = ctx->pool[POOL_CONG_QUADS];
-  std::vector<long long> quad_off;
-  rc = stocs_congruent_device(ctx, nv, d_ids, d_inv, d_quads, quad_off, st);
-  if (rc) return rc;
-  result->n_congruent_sets = quad_off[nv];
-  tr.mark("pipeline: congruent sets");
-  // 3. at most max_sets transforms per base
-  std::vector<long long> item_off((size_t)nv + 1, 0);
-  for (int b = 0; b < nv; ++b) {
-    const long long cnt = quad_off[b + 1] - quad_off[b];
-    item_off[b + 1] = item_off[b] + (cnt < max_sets ? cnt : max_sets);
-  }
-  const long long n_items = item_off[nv];
-  if (n_items == 0) return STOCS_OK;
   DevBuf &d_off = ctx->pool[POOL_PIPE_OFF], &d_items = ctx->pool[POOL_PIPE_ITEMS], &d_fit = ctx->pool[POOL_PIPE_FIT];
-  auto cleanup = [&]() {};  // pool slots persist
-#define PL(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); cleanup(); return STOCS_E_CUDA; } } while (0)
-  PL(d_off.ensure((size_t)(nv + 1) * 16));
+  STOCS_CUDA(ctx, ctx->pool[POOL_PIPE_STATE].ensure(sizeof(StocsPipeState)));
+  StocsPipeState* d_state = ctx->pool[POOL_PIPE_STATE].as<StocsPipeState>();
+  STOCS_CUDA(ctx, d_off.ensure((size_t)(n_bases + 1) * 16));
   long long* d_qoff = d_off.as<long long>();
-  long long* d_ioff = d_qoff + (nv + 1);
-  PL(cudaMemcpyAsync(d_qoff, quad_off.data(), (size_t)(nv + 1) * 8, cudaMemcpyHostToDevice, st));
-  PL(cudaMemcpyAsync(d_ioff, item_off.data(), (size_t)(nv + 1) * 8, cudaMemcpyHostToDevice, st));
-  PL(d_items.ensure((size_t)n_items * 12));
-  long long* d_item_quad = d_items.as<long long>();
-  int* d_item_base = (int*)(d_item_quad + n_items);
-  select_items_kernel<<<nv, 128, 0, st>>>(d_qoff, d_ioff, nv, max_sets, d_item_base, d_item_quad);
-  PL(d_fit.ensure((size_t)n_items * (64 + 64 + 1 + 4 + 4) + 1024));
-  float* d_Tc = d_fit.as<float>();
-  float* d_Tw = d_Tc + 16 * (size_t)n_items;
-  float* d_lcp = d_Tw + 16 * (size_t)n_items;
-  int* d_inl = (int*)(d_lcp + n_items);
-  uint8_t* d_ok = (uint8_t*)(d_inl + n_items);
-  FitArgs a;
-  fill_fit_args(ctx, a);
-  a.base_idx4 = d_ids; a.quads4 = d_quads.as<int>(); a.item_base = d_item_base; a.item_quad = d_item_quad;
-  a.Tc = d_Tc; a.Tw = d_Tw; a.ok = d_ok; a.n = n_items;
-  fit_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(a);
-  tr.mark("pipeline: select + fit");
-  // 4. score + 5. best
-  rc = stocs_launch_score(ctx, d_Tc, n_items, d_lcp, d_inl, st, true);
-  if (rc) { cleanup(); return rc; }
-  long long* d_bi = (long long*)(ctx->d_small.as<char>() + 512);
-  float* d_bv = (float*)(ctx->d_small.as<char>() + 512 + 256);
-  rc = stocs_launch_topk(ctx, d_lcp, n_items, 1, 0, (int64_t*)d_bi, d_bv, st);
-  if (rc) { cleanup(); return rc; }
-  long long bi = -1; float bv = 0.f;
-  std::vector<uint8_t> h_ok((size_t)n_items);
-  PL(cudaMemcpyAsync(&bi, d_bi, 8, cudaMemcpyDeviceToHost, st));
-  PL(cudaMemcpyAsync(&bv, d_bv, 4, cudaMemcpyDeviceToHost, st));
-  PL(cudaMemcpyAsync(h_ok.data(), d_ok, (size_t)n_items, cudaMemcpyDeviceToHost, st));
-  PL(cudaStreamSynchronize(st));
-  tr.mark("pipeline: score + best");
-  long long n_ok = 0, rank_of_best = -1;
-  for (long long i = 0; i < n_items; ++i) { if (i == bi) rank_of_best = n_ok; n_ok += h_ok[i] ? 1 : 0; }
-  result->n_transforms = n_ok;
-  result->best_lcp = bv;
-  if (bi >= 0) {
-    result->best_index = rank_of_best;  // index into the list of pushed transforms, as in the reference
-    int bb = 0;
-    while (bb + 1 < nv && item_off[bb + 1] <= bi) ++bb;
-    result->best_base = bb;
-    PL(cudaMemcpyAsync(result->best_T_centred, d_Tc + 16 * bi, 64, cudaMemcpyDeviceToHost, st));
-    PL(cudaMemcpyAsync(result->best_T_world, d_Tw + 16 * bi, 64, cudaMemcpyDeviceToHost, st));
-    PL(cudaStreamSynchronize(st));
+  long long* d_ioff = d_qoff + (n_bases + 1);
+  StocsPipeState& hs = *ctx->h_pipe_state;
+  for (int attempt = 0;; ++attempt) {
+    STOCS_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(StocsPipeState), st));
+    // 2. congruent sets
+    rc = stocs_congruent_enqueue(ctx, n_bases, d_ids, d_inv, d_valid, d_state, d_qoff, st);
+    if (rc) return rc;
+    tr.mark("pipeline: congruent sets");
+    // 3. at most max_sets transforms per base; the count is bounded by both n_bases * max_sets and the quad capacity
+    long long cap_items = (long long)n_bases * max_sets;
+    if (cap_items > ctx->cong_cap_quads) cap_items = ctx->cong_cap_quads;
+    pipe_item_offsets_kernel<<<1, 256, 0, st>>>(d_qoff, n_bases, max_sets, d_ioff, d_state);
+    STOCS_CUDA(ctx, d_items.ensure((size_t)cap_items * 12));
+    long long* d_item_quad = d_items.as<long long>();
+    int* d_item_base = (int*)(d_item_quad + cap_items);
+    select_items_kernel<<<n_bases, 128, 0, st>>>(d_qoff, d_ioff, n_bases, max_sets, d_item_base, d_item_quad);
+    STOCS_CUDA(ctx, d_fit.ensure((size_t)cap_items * (64 + 64 + 1 + 4 + 4) + 1024));
+    float* d_Tc = d_fit.as<float>();
+    float* d_Tw = d_Tc + 16 * (size_t)cap_items;
+    float* d_lcp = d_Tw + 16 * (size_t)cap_items;
+    int* d_inl = (int*)(d_lcp + cap_items);
+    uint8_t* d_ok = (uint8_t*)(d_inl + cap_items);
+    FitArgs a;
+    fill_fit_args(ctx, a);
+    a.base_idx4 = d_ids; a.quads4 = ctx->pool[POOL_CONG_QUADS].as<int>(); a.item_base = d_item_base; a.item_quad = d_item_quad;
+    a.Tc = d_Tc; a.Tw = d_Tw; a.ok = d_ok; a.n = 0; a.n_dev = &d_state->n_items;
+    // grids follow the previous run's item count (any grid is correct: the kernels stride / claim up to the device count)
+    long long guess = ctx->pipe_last_items > 0 ? ctx->pipe_last_items + ctx->pipe_last_items / 4 : 4096;
+    if (guess > cap_items) guess = cap_items;
+    if (guess < 1) guess = 1;
+    long long fit_blocks = (guess + 127) / 128;
+    if (fit_blocks > (long long)ctx->num_sms * 16) fit_blocks = (long long)ctx->num_sms * 16;
+    fit_kernel<<<(unsigned)fit_blocks, 128, 0, st>>>(a);
+    tr.mark("pipeline: select + fit");
+    // 4. score + 5. best
+    rc = stocs_launch_score(ctx, d_Tc, cap_items, d_lcp, d_inl, st, true, 0, nullptr, false, &d_state->n_items, guess);
+    if (rc) return rc;
+    long long* d_bi = (long long*)(ctx->d_small.as<char>() + 512);
+    float* d_bv = (float*)(ctx->d_small.as<char>() + 512 + 256);
+    rc = stocs_launch_topk(ctx, d_lcp, cap_items, 1, 0, (int64_t*)d_bi, d_bv, st, nullptr, nullptr, nullptr, &d_state->n_items, guess);
+    if (rc) return rc;
+    pipe_finalize_kernel<<<1, 256, 0, st>>>(d_ok, d_valid, n_bases, d_item_base, d_bi, d_bv, d_Tc, d_Tw, d_state);
+    STOCS_CUDA(ctx, cudaGetLastError());
+    STOCS_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(StocsPipeState), cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+    tr.mark("pipeline: score + best");
+    if (!hs.overflow) break;
+    if (!stocs_congruent_grow(ctx, hs) || attempt >= 2) STOCS_FAIL(ctx, STOCS_E_ARG, "find_congruent: pair lists too long");
   }
-#undef PL
-  cleanup();
+  ctx->pipe_last_items = hs.n_items;
+  result->n_valid_bases = hs.n_valid;
+  result->n_congruent_sets = (long long)hs.total_quads;
+  result->n_transforms = hs.n_ok;
+  result->best_lcp = hs.best_lcp;
+  if (hs.best_item >= 0) {
+    result->best_index = hs.rank_of_best;  // index into the list of pushed transforms, as in the reference
+    result->best_base = hs.best_base;
+    memcpy(result->best_T_centred, hs.best_Tc, 64);
+    memcpy(result->best_T_world, hs.best_Tw, 64);
+  }
   return STOCS_OK;
 }
 

@@ -28,6 +28,15 @@ __device__ __forceinline__ bool ppf_key_exists(const PpfView& v, const stocsm::P
   return (__ldg(v.keybits + (bit >> 5)) >> (bit & 31)) & 1u;
 }
 
+// Cheap necessary condition for ppf_key_exists(ppf_compute(p1, n1, p2, n2)): the distance component alone
+// (first lines of ppf_compute, then the f[0] tests of ppf_key_exists).  False => the key cannot exist,
+// whatever the three angles are, so callers may skip the atan2 evaluations; true decides nothing.
+__device__ __forceinline__ bool ppf_distance_may_exist(const PpfView& v, stocsm::V3 p1, stocsm::V3 p2) {
+  const int a1 = (int)(stocsm::norm(stocsm::sub(p1, p2)) * 1000.0f);
+  const int f0 = stocsm::ppf_closest_bin(a1, v.tr);
+  return !(f0 <= 5 || f0 / v.tr > v.n1);
+}
+
 // Enumerates the own bins whose expansion contains key f; calls fn(bin_index) for each valid one
 // (at most 128).  Returns false when the key cannot exist (p1 <= 5).
 template <class Fn>

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ lcp
                                                    unsigned* __restrict__ ticket, int K, long long index_offset,
                                                    long long* __restrict__ out_idx, float* __restrict__ out_lcp,
                                                    const float* __restrict__ T16, const int* __restrict__ inl,
-                                                   stocs_b200_record* __restrict__ rec_out) {
+                                                   stocs_b200_record* __restrict__ rec_out, const long long* __restrict__ H_dev) {
+  if (H_dev) H = *H_dev;   // the online pipeline keeps its count on the device
   __shared__ unsigned long long s_keys[8 * 32];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -206,11 +207,11 @@ extern "C" int stocs_b200_select_above(stocs_b200_ctx* ctx, const float* lcp, in
 
 int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
                       int64_t* d_idx, float* d_val, cudaStream_t st, const float* d_T16, const int32_t* d_inl,
-                      stocs_b200_record* d_rec) {
+                      stocs_b200_record* d_rec, const long long* d_H, long long grid_hint) {
   if (K < 1 || K > 32) STOCS_FAIL(ctx, STOCS_E_ARG, "reduce_best: K must be in 1..32");
   if (H >= (1ll << 32)) STOCS_FAIL(ctx, STOCS_E_ARG, "reduce_best: H must be < 2^32");
   int blocks = ctx->num_sms * 2;
-  long long need = (H + 2047) / 2048;   // at least 256 keys per warp: fewer, longer lists for the merge
+  long long need = ((d_H && grid_hint > 0 && grid_hint < H ? grid_hint : H) + 2047) / 2048;   // at least 256 keys per warp: fewer, longer lists for the merge
   if (need < 1) need = 1;
   if (blocks > need) blocks = (int)need;
   // per-stream scratch: launches on the context stream and on its second stream (the host-buffer
@@ -220,7 +221,7 @@ int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K,
   STOCS_CUDA(ctx, lists.ensure((size_t)blocks * 32 * 8));
   unsigned* ticket = (unsigned*)(ctx->d_small.as<char>() + 3344) + which;   // zero at creation, reset by the last CTA
   topk_kernel<<<blocks, 256, 0, st>>>(d_lcp, H, lists.as<unsigned long long>(), ticket, K, index_offset,
-                                      (long long*)d_idx, d_val, d_T16, d_inl, d_rec);
+                                      (long long*)d_idx, d_val, d_T16, d_inl, d_rec, d_H);
   STOCS_CUDA(ctx, cudaGetLastError());
   return STOCS_OK;
 }

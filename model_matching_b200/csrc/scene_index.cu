@@ -131,7 +131,7 @@ __global__ void grid_count_kernel(const float4* __restrict__ pts, int n, GridDes
 
 __global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc g, float r,
                                  const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cursor,
-                                 float4* __restrict__ cand) {
+                                 float4* __restrict__ cand, uint32_t cap) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = pts[i];
@@ -142,7 +142,7 @@ __global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc
         if (!near_cell(g, p, r * r, x, y, z)) continue;
         size_t cell = cell_number(g, x, y, z);
         uint32_t slot = cell_start[cell] + atomicAdd(&cursor[cell], 1u);
-        cand[slot] = p;
+        if (slot < cap) cand[slot] = p;   // (the buffer is sized before the total is known; see stocs_build_scene_index)
       }
 }
 
@@ -170,7 +170,8 @@ __global__ void brick_mask_kernel(const uint32_t* __restrict__ cell_start, uint3
 
 // brick table {mask lo, mask hi, index of the brick's first occupied cell, 0} + compact starts
 __global__ void brick_table_kernel(const uint32_t* __restrict__ cell_start, const unsigned long long* __restrict__ masks,
-                                   const uint32_t* __restrict__ occ_scan, uint32_t nbricks, uint32_t total_cand,
+                                   const uint32_t* __restrict__ occ_scan, uint32_t nbricks,
+                                   const uint32_t* __restrict__ total_cand, uint32_t starts_cap,
                                    uint4* __restrict__ bricks, uint32_t* __restrict__ starts,
                                    uint32_t* __restrict__ coarse, GridDesc g, int cshift, int csx, int csy) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,10 +189,11 @@ __global__ void brick_table_kernel(const uint32_t* __restrict__ cell_start, cons
   uint32_t k = base;
   while (r) {
     const int bit = __ffsll((long long)r) - 1;
-    starts[k++] = cell_start[(size_t)b * 64 + bit];
+    if (k < starts_cap) starts[k] = cell_start[(size_t)b * 64 + bit];
+    ++k;
     r &= r - 1;
   }
-  if (b == nbricks - 1) starts[occ_scan[nbricks]] = total_cand;
+  if (b == nbricks - 1 && occ_scan[nbricks] < starts_cap) starts[occ_scan[nbricks]] = *total_cand;
 }
 
 // Host construction of the reference kd-tree (explicit work stack instead of recursion; node
@@ -423,68 +425,83 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   const double margin_cells = std::max(1.0 / 256.0, 2.0 * 4.0 * nmax * 5.9604644775390625e-8);
   const float r = (float)(eps * (1.0 + 1.0 / 256.0) + cell * margin_cells);
 
+  // Everything below is enqueued without a host round trip: the candidate buffer and the compact
+  // cell-start array are sized BEFORE the device knows their lengths -- from the expected replication
+  // (the volume formula above, +10 %), or from whatever an earlier scene left allocated if that is
+  // larger -- writes beyond the capacity are dropped, and the two lengths come back with the single
+  // synchronisation at the end; a scene that did not fit grows the buffers and runs the stage again.
+  // (Round 1 synchronised four times here: candidate total, occupied-cell total, tables, kd-tree.)
   size_t nc1 = (size_t)g.ncells + 1;
   DevBuf& d_dense = ctx->pool[POOL_INDEX_DENSE];  // dense per-cell starts (scratch)
   STOCS_CUDA(ctx, d_dense.ensure(nc1 * 4));
   STOCS_CUDA(ctx, ctx->d_work.ensure(nc1 * 4));
   uint32_t* counts = ctx->d_work.as<uint32_t>();
   uint32_t* dense_start = d_dense.as<uint32_t>();
-  STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
-  grid_count_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
-  size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, dense_start, (int)nc1, st);
-  STOCS_CUDA(ctx, ctx->d_tmp2.ensure(tmp_bytes));
-  cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, counts, dense_start, (int)nc1, st);
-  uint32_t total = 0;
-  STOCS_CUDA(ctx, cudaMemcpyAsync(&total, dense_start + g.ncells, 4, cudaMemcpyDeviceToHost, st));
-  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
-  ctx->ncand = total;
-  tr.mark("alloc + count + scan");
-  STOCS_CUDA(ctx, ctx->d_cand.ensure((size_t)(total ? total : 1) * 16));
-  STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
-  grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>());
-  tr.mark("fill candidates");
-  // brick table + compact starts
   DevBuf &d_masks = ctx->pool[POOL_INDEX_MASKS], &d_occ = ctx->pool[POOL_INDEX_OCC], &d_occ_scan = ctx->pool[POOL_INDEX_OCC_SCAN];
   STOCS_CUDA(ctx, d_masks.ensure((size_t)g.nbricks * 8));
   STOCS_CUDA(ctx, d_occ.ensure((size_t)(g.nbricks + 1) * 4));
   STOCS_CUDA(ctx, d_occ_scan.ensure((size_t)(g.nbricks + 1) * 4));
-  STOCS_CUDA(ctx, cudaMemsetAsync(d_occ.p, 0, (size_t)(g.nbricks + 1) * 4, st));
-  const unsigned bb = (g.nbricks + 127) / 128;
   STOCS_CUDA(ctx, ctx->d_brick_occ.ensure(((size_t)g.nbricks + 31) / 32 * 4));
-  brick_mask_kernel<<<bb, 128, 0, st>>>(dense_start, g.nbricks, d_masks.as<unsigned long long>(), d_occ.as<uint32_t>(),
-                                        ctx->d_brick_occ.as<uint32_t>());
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
-  STOCS_CUDA(ctx, ctx->d_tmp2.ensure(tmp_bytes));
-  cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
-  uint32_t n_occ = 0;
-  STOCS_CUDA(ctx, cudaMemcpyAsync(&n_occ, d_occ_scan.as<uint32_t>() + g.nbricks, 4, cudaMemcpyDeviceToHost, st));
-  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
   STOCS_CUDA(ctx, ctx->d_bricks.ensure((size_t)g.nbricks * 16));
   ctx->coarse_shift = cshift; ctx->coarse_nx = cnx; ctx->coarse_ny = cny; ctx->coarse_nz = cnz;
   ctx->coarse_words = (int)(((size_t)(cnx + 1) * (cny + 1) * (cnz + 1) + 31) / 32);
   STOCS_CUDA(ctx, ctx->d_coarse.ensure((size_t)ctx->coarse_words * 4));
-  STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_coarse.p, 0, (size_t)ctx->coarse_words * 4, st));
-  STOCS_CUDA(ctx, ctx->d_cell_start.ensure((size_t)(n_occ + 1) * 4));
-  brick_table_kernel<<<bb, 128, 0, st>>>(dense_start, d_masks.as<unsigned long long>(), d_occ_scan.as<uint32_t>(), g.nbricks,
-                                         total, ctx->d_bricks.as<uint4>(), ctx->d_cell_start.as<uint32_t>(),
-                                         ctx->d_coarse.as<uint32_t>(), g, cshift, cnx + 1, cny + 1);
-  STOCS_CUDA(ctx, cudaGetLastError());
-  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+  size_t tmp_bytes = 0, tmp_bytes2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, dense_start, (int)nc1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes2, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
+  STOCS_CUDA(ctx, ctx->d_tmp2.ensure(tmp_bytes > tmp_bytes2 ? tmp_bytes : tmp_bytes2));
+  const double cs_eff = cell / eps;
+  const double repl = (cs_eff * cs_eff * cs_eff + 6 * cs_eff * cs_eff + 3 * 3.14159265 * cs_eff + 4.19) / (cs_eff * cs_eff * cs_eff);
+  size_t cap = (size_t)((double)S * repl * 1.1) + 4096;
+  if (cap < ctx->d_cand.bytes / 16) cap = ctx->d_cand.bytes / 16;
+  if (const char* e = getenv("STOCS_CAND_CAP")) { const long long v = atoll(e); if (v >= 1) cap = (size_t)v; }   // tests: force the retry
+  if (cap > 0xfffffff0u) cap = 0xfffffff0u;
+  const unsigned bb = (g.nbricks + 127) / 128;
+  uint32_t* h_counts = ctx->h_index_counts;   // page-locked: {candidate records, occupied cells}
+  uint32_t total = 0, n_occ = 0;
+  bool kd_uploaded = false;
+  for (int attempt = 0;; ++attempt) {
+    const size_t starts_cap = (cap < (size_t)g.ncells ? cap : (size_t)g.ncells) + 1;
+    STOCS_CUDA(ctx, ctx->d_cand.ensure(cap * 16));
+    STOCS_CUDA(ctx, ctx->d_cell_start.ensure(starts_cap * 4));
+    STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
+    grid_count_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
+    cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, counts, dense_start, (int)nc1, st);
+    STOCS_CUDA(ctx, cudaMemcpyAsync(&h_counts[0], dense_start + g.ncells, 4, cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
+    grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>(), (uint32_t)cap);
+    // brick table + compact starts
+    STOCS_CUDA(ctx, cudaMemsetAsync(d_occ.p, 0, (size_t)(g.nbricks + 1) * 4, st));
+    brick_mask_kernel<<<bb, 128, 0, st>>>(dense_start, g.nbricks, d_masks.as<unsigned long long>(), d_occ.as<uint32_t>(),
+                                          ctx->d_brick_occ.as<uint32_t>());
+    cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes2, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
+    STOCS_CUDA(ctx, cudaMemcpyAsync(&h_counts[1], d_occ_scan.as<uint32_t>() + g.nbricks, 4, cudaMemcpyDeviceToHost, st));
+    STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_coarse.p, 0, (size_t)ctx->coarse_words * 4, st));
+    brick_table_kernel<<<bb, 128, 0, st>>>(dense_start, d_masks.as<unsigned long long>(), d_occ_scan.as<uint32_t>(), g.nbricks,
+                                           dense_start + g.ncells, (uint32_t)starts_cap, ctx->d_bricks.as<uint4>(),
+                                           ctx->d_cell_start.as<uint32_t>(), ctx->d_coarse.as<uint32_t>(), g, cshift, cnx + 1, cny + 1);
+    STOCS_CUDA(ctx, cudaGetLastError());
+    if (!kd_uploaded) {
+      // reference kd-tree (tie resolution only): built by the host thread started above, while this
+      // one enqueued the grid kernels; its upload joins the same queue
+      kd_thread.join();
+      ctx->kd_nodes = (int)kb.nodes.size();
+      STOCS_CUDA(ctx, ctx->d_kd_nodes.ensure(kb.nodes.size() * sizeof(KdNodeDev)));
+      STOCS_CUDA(ctx, ctx->d_kd_pts.ensure((size_t)S * 16));
+      STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_nodes.p, kb.nodes.data(), kb.nodes.size() * sizeof(KdNodeDev),
+                                      cudaMemcpyHostToDevice, st));
+      STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_pts.p, kp.data(), (size_t)S * 16, cudaMemcpyHostToDevice, st));
+      kd_uploaded = true;
+    }
+    STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+    total = h_counts[0]; n_occ = h_counts[1];
+    if ((size_t)total <= cap) break;
+    if (attempt >= 1) STOCS_FAIL(ctx, STOCS_E_CUDA, "upload_scene: candidate buffer sizing failed");
+    cap = (size_t)total + 1024;
+  }
+  ctx->ncand = total;
   ctx->counters[4] = n_occ;
-  tr.mark("bricks + coarse");
-
-  // reference kd-tree (tie resolution only): built by the host thread started above
-  kd_thread.join();
-  tr.mark("kd-tree build (host)");
-  ctx->kd_nodes = (int)kb.nodes.size();
-  STOCS_CUDA(ctx, ctx->d_kd_nodes.ensure(kb.nodes.size() * sizeof(KdNodeDev)));
-  STOCS_CUDA(ctx, ctx->d_kd_pts.ensure((size_t)S * 16));
-  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_nodes.p, kb.nodes.data(), kb.nodes.size() * sizeof(KdNodeDev),
-                                  cudaMemcpyHostToDevice, st));
-  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_pts.p, kp.data(), (size_t)S * 16, cudaMemcpyHostToDevice, st));
-  STOCS_CUDA(ctx, cudaStreamSynchronize(st));
-  tr.mark("kd-tree upload");
+  tr.mark("index build + kd-tree");
   ctx->counters[2] = g.ncells;
   ctx->counters[3] = total;
   return STOCS_OK;

@@ -74,6 +74,7 @@ struct ScoreArgs {
   unsigned long long* cnt;   // counting variant only (stocs_b200_score_counters): see ScoreCounter
   const int* __restrict__ order;   // claim number -> hypothesis (heavy-first schedule, see probe_order_kernel) or NULL
   long long H;
+  const long long* __restrict__ H_dev;   // optional: the count lives on the device (H is then an upper bound)
   GridDesc g;
   int M, Mpad;
   float sq_eps, dot_thr;
@@ -381,7 +382,9 @@ __device__ __forceinline__ void drain_queue(const ScoreArgs& a, WarpQueue& q, in
 // heavy-first order when there is one; any value >= H ends the warp
 __device__ __forceinline__ int claim_hypothesis(const ScoreArgs& a) {
   const unsigned long long c = atomicAdd(a.work_counter, 1ull);
-  if (c >= (unsigned long long)a.H) return 0x7fffffff;
+  // (the online pipeline keeps its transform count on the device: H is then only an upper bound)
+  const unsigned long long lim = a.H_dev ? (unsigned long long)__ldg(a.H_dev) : (unsigned long long)a.H;
+  if (c >= lim) return 0x7fffffff;
   return a.order ? __ldg(a.order + c) : (int)c;
 }
 
@@ -640,7 +643,8 @@ bool stocs_fmad_selftest(stocs_b200_ctx* ctx) {
 }
 
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp, int32_t* d_inl,
-                       cudaStream_t st, bool time_it, int slot, unsigned long long* d_counters, bool T_in_host_memory) {
+                       cudaStream_t st, bool time_it, int slot, unsigned long long* d_counters, bool T_in_host_memory,
+                       const long long* d_H, long long grid_hint) {
   if (H <= 0) return STOCS_OK;
   if (H >= (1ll << 31)) STOCS_FAIL(ctx, STOCS_E_ARG, "score: at most 2^31-1 hypotheses per call");
   ScoreArgs a;
@@ -668,6 +672,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   a.cnt = d_counters;
   a.order = nullptr;
   a.H = H;
+  a.H_dev = d_H;
   a.g = ctx->grid;
   a.M = ctx->M;
   a.Mpad = ctx->Mpad;
@@ -683,7 +688,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   int per_sm = 0;
   STOCS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarps * 32, smem));
   if (per_sm < 1) STOCS_FAIL(ctx, STOCS_E_ARG, "score: model too large for shared memory");
-  long long want = (H + kWarps - 1) / kWarps;
+  long long want = ((d_H && grid_hint > 0 && grid_hint < H ? grid_hint : H) + kWarps - 1) / kWarps;
   long long grid = (long long)ctx->num_sms * per_sm;
   if (grid > want) grid = want;
   STOCS_CUDA(ctx, cudaMemsetAsync(wctr, 0, 8, st));  // work counter only; tie counter accumulates
@@ -697,7 +702,7 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
   const long long lpt_max = getenv("STOCS_LPT_MAX") ? atoll(getenv("STOCS_LPT_MAX")) : 300000;
   // (not when the transforms are read in place from page-locked host memory: the probe would pull
   // every transform over PCIe a second time -- measured 1.7e9 -> 0.9e9 hypotheses/s end to end on 8 GPUs)
-  if (!no_lpt && !d_counters && !T_in_host_memory && H >= 32768 && H <= lpt_max && slot == 0) {
+  if (!no_lpt && !d_counters && !T_in_host_memory && !d_H && H >= 32768 && H <= lpt_max && slot == 0) {
     DevBuf& b_order = ctx->pool[POOL_SCORE_ORDER];
     STOCS_CUDA(ctx, b_order.ensure((size_t)H * 4));
     unsigned* fill = (unsigned*)(ctx->d_small.as<char>() + 3328);

@@ -57,7 +57,7 @@ struct PpfTableDesc {
 // Scratch-pool slot names (stocs_b200_ctx::pool).  Ranges that overlap belong to stages that are
 // never active inside the same ABI call on the same stream.
 enum PoolSlot : int {
-  // congruent.cu (stocs_congruent_device): 0..11; POOL_CONG_QUADS is its output, read by run_pipeline
+  // congruent.cu (stocs_congruent_enqueue): 0..11; POOL_CONG_QUADS is its output, read by run_pipeline
   POOL_CONG_INFO = 0, POOL_CONG_SEG, POOL_CONG_CODES_A, POOL_CONG_CODES_B, POOL_CONG_TMP, POOL_CONG_PE,
   POOL_CONG_QE, POOL_CONG_QCELL, POOL_CONG_CNT, POOL_CONG_SCAN, POOL_CONG_QOFF, POOL_CONG_QUADS = 11,
   // scene_index.cu (upload_scene): 12..15
@@ -83,7 +83,28 @@ enum PoolSlot : int {
   POOL_SCORE_ORDER = 45,
   // reduce.cu: per-CTA top-32 lists of reductions launched on the context's second stream
   POOL_TOPK_LISTS_AUX = 46,
+  // congruent.cu / fit.cu: device scalars of one congruent-set search or pipeline run (StocsPipeState)
+  POOL_PIPE_STATE = 47,
   POOL_COUNT = 48
+};
+
+// Device scalars of one congruent-set search (congruent.cu) and of the pipeline run around it (fit.cu).
+// Every list size of the online stages lives here, so the host enqueues the whole chain against
+// CAPACITIES and reads this record back once at the end; a search that did not fit sets `overflow`
+// (and turns its own later stages into no-ops), the host grows the buffers and enqueues it again.
+struct StocsPipeState {
+  unsigned long long need_codes;   // P + Q list entries of all bases (valid also when they did not fit)
+  unsigned long long need_quads;   // congruent sets of all bases
+  uint32_t totalP, total;          // entries of the flat code buffer in use: P lists first, then Q lists
+  uint32_t total_quads;
+  uint32_t overflow;               // 1: code buffers too small, 2: quad buffer too small, 4: pair lists >= 2^31 entries
+  long long n_items;               // transforms to fit (at most max_sets per base)
+  long long n_ok;                  // of which pass the fit's orthogonality test
+  long long best_item, rank_of_best;
+  int n_valid, best_base;
+  float best_lcp;
+  int pad;
+  float best_Tc[16], best_Tw[16];
 };
 
 struct stocs_b200_ctx {
@@ -157,6 +178,12 @@ struct stocs_b200_ctx {
   void* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
 
+  // capacities the online stages are enqueued against (entries; grown when a search reports overflow)
+  long long cong_cap_codes = 1 << 18, cong_cap_quads = 1 << 21;
+  long long pipe_last_items = 0;       // transforms of the previous pipeline run (sizes the next run's grids)
+  StocsPipeState* h_pipe_state = nullptr;   // page-locked landing zone of the state record
+  uint32_t* h_index_counts = nullptr;       // page-locked: list lengths of the scene-index build
+
   // last score call
   int64_t last_H = 0;
   const float* last_T_dev = nullptr;   // device-visible transforms of the last host-buffer score call
@@ -192,7 +219,9 @@ int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4*
 int stocs_pack_scene_attr(stocs_b200_ctx* ctx, const float* d_nrm3, const float* d_cls, int S);
 int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* d_lcp,
                        int32_t* d_inl, cudaStream_t st, bool time_it, int slot = 0,
-                       unsigned long long* d_counters = nullptr, bool T_in_host_memory = false);  // score.cu
+                       unsigned long long* d_counters = nullptr, bool T_in_host_memory = false,
+                       const long long* d_H = nullptr, long long grid_hint = 0);  // score.cu (d_H: the count lives on
+                                                                                  // the device, H bounds it, grid_hint sizes the launch)
 int stocs_launch_backproject(stocs_b200_ctx* ctx, const uint16_t* d_depth, const uint8_t* d_bgr,
                              int W, int H, float fx, float cx, float fy, float cy, float scale,
                              float* d_xyz, uint32_t* d_rgb, cudaStream_t st);  // backproject.cu
@@ -201,7 +230,8 @@ bool stocs_is_host_memory(const void* p);                                  // ca
 // top-K of a device lcp array (reduce.cu); d_idx/d_val may be NULL when only records are wanted
 int stocs_launch_topk(stocs_b200_ctx* ctx, const float* d_lcp, int64_t H, int K, int64_t index_offset,
                       int64_t* d_idx, float* d_val, cudaStream_t st, const float* d_T16 = nullptr,
-                      const int32_t* d_inl = nullptr, stocs_b200_record* d_rec = nullptr);
+                      const int32_t* d_inl = nullptr, stocs_b200_record* d_rec = nullptr,
+                      const long long* d_H = nullptr, long long grid_hint = 0);   // as for stocs_launch_score
 float stocs_angle_threshold_dot();                                         // capi.cu (host)
 
 // STOCS_TRACE=1: wall-clock of each stage of a host-driven sequence on stderr (adds a synchronize

@@ -1,12 +1,6 @@
-mkdir -p gpurun_out/r2q
-(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -30) > gpurun_out/r2q/pytest.log
-B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
-$B > gpurun_out/r2q/plain_bench.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2q/launches.csv $B > gpurun_out/r2q/ncu_launch.log 2>&1
-K1="python profiles/kernel_target.py s1 5"
-$K1 > gpurun_out/r2q/plain_s1.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:score_lcp_kernel -s 3 -c 1 -f -o gpurun_out/r2q/score_s1 $K1 > gpurun_out/r2q/ncu_s1.log 2>&1
-K2="python profiles/kernel_target.py s1fit 5"
-$K2 > gpurun_out/r2q/plain_s1fit.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:score_lcp_kernel -s 3 -c 1 -f -o gpurun_out/r2q/score_s1fit $K2 > gpurun_out/r2q/ncu_s1fit.log 2>&1
-tail -4 gpurun_out/r2q/pytest.log; cat gpurun_out/r2q/plain_s1.log gpurun_out/r2q/plain_s1fit.log; ls gpurun_out/r2q
+mkdir -p gpurun_out/r2s
+(timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -30) > gpurun_out/r2s/pytest.log
+P="python profiles/pose_latency.py --trace-child"
+$P > gpurun_out/r2s/plain_child.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r2s/pose_launches.csv $P > gpurun_out/r2s/ncu_child.log 2>&1
+tail -5 gpurun_out/r2s/pytest.log; tail -3 gpurun_out/r2s/ncu_child.log; wc -l gpurun_out/r2s/pose_launches.csv

@@ -175,3 +175,73 @@ def test_sample_instance_base_sequence_bit_exact(gpu_ctx):
 def synth_hyp(sc, mpos):
     from model_matching_b200 import synth
     return synth.make_hypotheses(300, sc["pos"], mpos, sc["gt_R"], sc["gt_t"], seed=3, near_fraction=0.3)
+
+
+def test_sample_bases_scene_larger_than_one_candidate_chunk(small_scene):
+    """The sampler builds its candidate lists 16 384 scene points at a time: a 40 000-point scene takes
+    three rounds per stage, and the bases must still be the oracle's."""
+    from model_matching_b200 import Context
+    sc, mpos, mnrm = small_scene
+    assert len(sc["pos"]) > 2 * 16384
+    est = oracle.Estimator(sc["pos"], sc["nrm"], sc["cls"], mpos, mnrm, ppfmap=oracle.PPFMap(mpos, mnrm))
+    ctx = Context(0)
+    try:
+        ctx.upload_model(mpos, mnrm)
+        ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+        n = 16
+        gids, ginv, gok = ctx.sample_bases(SEED, 0, n)
+        out = [est.sample_class_base(SEED, b) for b in range(n)]
+        ok = np.array([o[0] for o in out])
+        assert ok.sum() >= 4
+        assert np.array_equal(gok, ok)
+        assert np.array_equal(gids[ok], np.stack([o[1] for o in out])[ok])
+        assert np.array_equal(ginv[ok].view(np.uint32), np.stack([o[2] for o in out])[ok].view(np.uint32))
+    finally:
+        ctx.close()
+
+
+def test_capacity_retry_paths_give_the_same_results(world, monkeypatch):
+    """Every online stage is enqueued against buffer CAPACITIES and reads its list lengths back once;
+    a run that does not fit grows the buffers and is enqueued again.  With absurdly small initial
+    capacities (scene-index candidates, congruent-set code and quad buffers) every retry path runs,
+    and the results must be those of the default context."""
+    from model_matching_b200 import Context
+    ctx0, est, sc, mpos, mnrm = world
+    ctx0.upload_model(mpos, mnrm)                      # (other tests of this module re-use the session context)
+    ctx0.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+    ok, ids, inv = _oracle_bases(est, N_BASES)
+    bases, invs = ids[ok], inv[ok]
+    quads0, offs0 = ctx0.find_congruent(bases, invs)
+    r0 = ctx0.run_pipeline(SEED, n_bases=N_BASES, max_sets=40)
+    rng = np.random.default_rng(5)
+    T = np.tile(np.array(r0.best_T_centred[:], np.float32), (64, 1))     # the winning pose, jittered
+    T[1:, 12:15] += rng.normal(0, 0.004, (63, 3)).astype(np.float32)
+    lcp0, inl0 = ctx0.score_lcp(T)[:2]
+    assert inl0.max() > 0.5 * len(mpos)
+    monkeypatch.setenv("STOCS_CONG_CAP_CODES", "64")
+    monkeypatch.setenv("STOCS_CONG_CAP_QUADS", "16")
+    monkeypatch.setenv("STOCS_CAND_CAP", "1000")
+    ctx = Context(0)
+    try:
+        ctx.upload_model(mpos, mnrm)
+        ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])      # candidate buffer too small: index retry
+        monkeypatch.delenv("STOCS_CAND_CAP")
+        lcp, inl = ctx.score_lcp(T)[:2]
+        assert np.array_equal(lcp.view(np.uint32), lcp0.view(np.uint32)) and np.array_equal(inl, inl0)
+        r = ctx.run_pipeline(SEED, n_bases=N_BASES, max_sets=40)   # code buffers, then quad buffer too small
+        for f in ("n_valid_bases", "n_congruent_sets", "n_transforms", "best_index", "best_lcp", "best_base"):
+            assert getattr(r, f) == getattr(r0, f), f
+        assert list(r.best_T_centred) == list(r0.best_T_centred) and list(r.best_T_world) == list(r0.best_T_world)
+        quads, offs = ctx.find_congruent(bases, invs)
+        assert np.array_equal(quads, quads0) and np.array_equal(offs, offs0)
+    finally:
+        ctx.close()
+    # a second context with tiny capacities, find_congruent first (its own retry loop)
+    ctx = Context(0)
+    try:
+        ctx.upload_model(mpos, mnrm)
+        ctx.upload_scene(sc["pos"], sc["nrm"], sc["cls"])
+        quads, offs = ctx.find_congruent(bases, invs)
+        assert np.array_equal(quads, quads0) and np.array_equal(offs, offs0)
+    finally:
+        ctx.close()
