@@ -137,35 +137,63 @@ __global__ void __launch_bounds__(256) pipe_item_offsets_kernel(const long long*
   if (j == 255) { item_off[n_bases] = (long long)s_buf[255]; stt->n_items = (long long)s_buf[255]; }
 }
 
-// closes a pipeline run (one block): transforms that passed the fit, the winner's rank among them (the
-// index the reference's transform list gives it), its base's rank among the valid bases, its two poses
-__global__ void __launch_bounds__(256) pipe_finalize_kernel(const uint8_t* __restrict__ ok, const uint8_t* __restrict__ valid, int n_bases,
-                                                             const int* __restrict__ item_base, const long long* __restrict__ best_idx,
-                                                             const float* __restrict__ best_val, const float* __restrict__ Tc,
-                                                             const float* __restrict__ Tw, StocsPipeState* __restrict__ stt) {
-  __shared__ long long s_a[256], s_b[256];
-  __shared__ int s_c[256], s_d[256];
-  const int j = threadIdx.x;
+// closes a pipeline run (one block): the best hypothesis -- first strict maximum of the LCP array, as
+// reduce.cu orders its keys: (lcp bits, lower index first), lcp > 0 only; taken from best_idx/best_val
+// instead when the caller ran the general top-K reduction (lcp == NULL) --, the transforms that passed
+// the fit, the winner's rank among them (the index the reference's transform list gives it), its
+// base's rank among the valid bases, its two poses
+__global__ void __launch_bounds__(1024) pipe_finalize_kernel(const float* __restrict__ lcp, const uint8_t* __restrict__ ok,
+                                                              const uint8_t* __restrict__ valid, int n_bases,
+                                                              const int* __restrict__ item_base, const long long* __restrict__ best_idx,
+                                                              const float* __restrict__ best_val, const float* __restrict__ Tc,
+                                                              const float* __restrict__ Tw, StocsPipeState* __restrict__ stt) {
+  __shared__ unsigned long long s_key[32];
+  __shared__ long long s_a[32], s_b[32];
+  __shared__ int s_c[32], s_d[32];
+  __shared__ long long s_bi;
+  __shared__ float s_bv;
+  const int j = threadIdx.x, lane = j & 31, w = j >> 5;
   const long long n = stt->n_items;
-  const long long bi = best_idx[0];
+  if (lcp) {
+    unsigned long long key = 0ull;
+    for (long long i = j; i < n; i += 1024) {
+      const float v = lcp[i];
+      const unsigned long long k = (v > 0.f) ? (((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffull - (unsigned long long)i)) : 0ull;
+      key = k > key ? k : key;
+    }
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o); key = other > key ? other : key; }
+    if (lane == 0) s_key[w] = key;
+    __syncthreads();
+    if (j == 0) {
+      for (int k = 1; k < 32; ++k) key = s_key[k] > key ? s_key[k] : key;
+      s_bi = key ? (long long)(0xffffffffull - (key & 0xffffffffull)) : -1ll;
+      s_bv = key ? __uint_as_float((unsigned)(key >> 32)) : 0.f;
+    }
+  } else if (j == 0) {
+    s_bi = best_idx[0];
+    s_bv = best_val[0];
+  }
+  __syncthreads();
+  const long long bi = s_bi;
   long long n_ok = 0, before = 0;
-  for (long long i = j; i < n; i += 256) { const int o = ok[i] ? 1 : 0; n_ok += o; if (i < bi) before += o; }
+  for (long long i = j; i < n; i += 1024) { const int o = ok[i] ? 1 : 0; n_ok += o; if (i < bi) before += o; }
   const int bb = (bi >= 0) ? item_base[bi] : -1;
   int n_valid = 0, valid_before = 0;
-  for (int b = j; b < n_bases; b += 256) { const int o = valid[b] ? 1 : 0; n_valid += o; if (b < bb) valid_before += o; }
-  s_a[j] = n_ok; s_b[j] = before; s_c[j] = n_valid; s_d[j] = valid_before;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (j < o) { s_a[j] += s_a[j + o]; s_b[j] += s_b[j + o]; s_c[j] += s_c[j + o]; s_d[j] += s_d[j + o]; }
-    __syncthreads();
+  for (int b = j; b < n_bases; b += 1024) { const int o = valid[b] ? 1 : 0; n_valid += o; if (b < bb) valid_before += o; }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o); before += __shfl_xor_sync(0xffffffffu, before, o);
+    n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o); valid_before += __shfl_xor_sync(0xffffffffu, valid_before, o);
   }
+  if (lane == 0) { s_a[w] = n_ok; s_b[w] = before; s_c[w] = n_valid; s_d[w] = valid_before; }
+  __syncthreads();
   if (j == 0) {
-    stt->n_ok = s_a[0];
-    stt->n_valid = s_c[0];
+    for (int k = 1; k < 32; ++k) { n_ok += s_a[k]; before += s_b[k]; n_valid += s_c[k]; valid_before += s_d[k]; }
+    stt->n_ok = n_ok;
+    stt->n_valid = n_valid;
     stt->best_item = bi;
-    stt->rank_of_best = (bi >= 0) ? s_b[0] : -1;
-    stt->best_base = (bi >= 0) ? s_d[0] : -1;
-    stt->best_lcp = best_val[0];
+    stt->rank_of_best = (bi >= 0) ? before : -1;
+    stt->best_base = (bi >= 0) ? valid_before : -1;
+    stt->best_lcp = s_bv;
   }
   if (j < 16) {
     stt->best_Tc[j] = (bi >= 0) ? Tc[16 * bi + j] : 0.f;
@@ -308,9 +336,13 @@ static int run_pipeline_impl(stocs_b200_ctx* ctx, uint64_t seed, int n_bases, in
     if (rc) return rc;
     long long* d_bi = (long long*)(ctx->d_small.as<char>() + 512);
     float* d_bv = (float*)(ctx->d_small.as<char>() + 512 + 256);
-    rc = stocs_launch_topk(ctx, d_lcp, cap_items, 1, 0, (int64_t*)d_bi, d_bv, st, nullptr, nullptr, nullptr, &d_state->n_items, guess);
-    if (rc) return rc;
-    pipe_finalize_kernel<<<1, 256, 0, st>>>(d_ok, d_valid, n_bases, d_item_base, d_bi, d_bv, d_Tc, d_Tw, d_state);
+    // lists the closing block can scan itself (every online frame) skip the general top-K launch
+    const bool small_list = cap_items <= (1ll << 20);
+    if (!small_list) {
+      rc = stocs_launch_topk(ctx, d_lcp, cap_items, 1, 0, (int64_t*)d_bi, d_bv, st, nullptr, nullptr, nullptr, &d_state->n_items, guess);
+      if (rc) return rc;
+    }
+    pipe_finalize_kernel<<<1, 1024, 0, st>>>(small_list ? d_lcp : nullptr, d_ok, d_valid, n_bases, d_item_base, d_bi, d_bv, d_Tc, d_Tw, d_state);
     STOCS_CUDA(ctx, cudaGetLastError());
     STOCS_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(StocsPipeState), cudaMemcpyDeviceToHost, st));
     STOCS_CUDA(ctx, cudaStreamSynchronize(st));

@@ -117,55 +117,77 @@ __device__ __forceinline__ bool near_cell(const GridDesc& g, float4 p, float r2,
   return dx * dx + dy * dy + dz * dz <= r2;
 }
 
+// LPP lanes share one scene point and split the cells of its dilated range (LPP = 32 for frame-sized
+// scenes: 13 419 threads walking ~150 cells each left the GPU idle for 90 us; LPP = 1 for large ones)
+template <int LPP>
 __global__ void grid_count_kernel(const float4* __restrict__ pts, int n, GridDesc g, float r,
                                   uint32_t* __restrict__ counts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / LPP;
+  const int sub = (int)(t % LPP);
   if (i >= n) return;
   const float4 p = pts[i];
-  CellRange c = dilated_range(g, p, r);
-  for (int z = c.z0; z <= c.z1; ++z)
-    for (int y = c.y0; y <= c.y1; ++y)
-      for (int x = c.x0; x <= c.x1; ++x)
-        if (near_cell(g, p, r * r, x, y, z)) atomicAdd(&counts[cell_number(g, x, y, z)], 1u);
+  const CellRange c = dilated_range(g, p, r);
+  const int nx = c.x1 - c.x0 + 1, ny = c.y1 - c.y0 + 1, nz = c.z1 - c.z0 + 1;
+  if (nx <= 0 || ny <= 0 || nz <= 0) return;
+  const int total = nx * ny * nz;
+  for (int k = sub; k < total; k += LPP) {
+    const int x = c.x0 + k % nx, y = c.y0 + (k / nx) % ny, z = c.z0 + k / (nx * ny);
+    if (near_cell(g, p, r * r, x, y, z)) atomicAdd(&counts[cell_number(g, x, y, z)], 1u);
+  }
 }
 
+// `remaining` holds the per-cell counts on entry: each record takes the next free slot of its cell from
+// the back (no second zeroed cursor array; the order inside a cell's list is immaterial -- the scoring
+// kernel takes the minimum distance and resolves exact ties through the kd-tree)
+template <int LPP>
 __global__ void grid_fill_kernel(const float4* __restrict__ pts, int n, GridDesc g, float r,
-                                 const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cursor,
+                                 const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ remaining,
                                  float4* __restrict__ cand, uint32_t cap) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / LPP;
+  const int sub = (int)(t % LPP);
   if (i >= n) return;
-  float4 p = pts[i];
-  CellRange c = dilated_range(g, p, r);
-  for (int z = c.z0; z <= c.z1; ++z)
-    for (int y = c.y0; y <= c.y1; ++y)
-      for (int x = c.x0; x <= c.x1; ++x) {
-        if (!near_cell(g, p, r * r, x, y, z)) continue;
-        size_t cell = cell_number(g, x, y, z);
-        uint32_t slot = cell_start[cell] + atomicAdd(&cursor[cell], 1u);
-        if (slot < cap) cand[slot] = p;   // (the buffer is sized before the total is known; see stocs_build_scene_index)
-      }
+  const float4 p = pts[i];
+  const CellRange c = dilated_range(g, p, r);
+  const int nx = c.x1 - c.x0 + 1, ny = c.y1 - c.y0 + 1, nz = c.z1 - c.z0 + 1;
+  if (nx <= 0 || ny <= 0 || nz <= 0) return;
+  const int total = nx * ny * nz;
+  for (int k = sub; k < total; k += LPP) {
+    const int x = c.x0 + k % nx, y = c.y0 + (k / nx) % ny, z = c.z0 + k / (nx * ny);
+    if (!near_cell(g, p, r * r, x, y, z)) continue;
+    const size_t cell = cell_number(g, x, y, z);
+    const uint32_t slot = cell_start[cell] + atomicSub(&remaining[cell], 1u) - 1u;
+    if (slot < cap) cand[slot] = p;   // (the buffer is sized before the total is known; see stocs_build_scene_index)
+  }
 }
 
-// per brick: occupancy mask and number of occupied cells
+// per brick: occupancy mask and number of occupied cells.  One warp per 32 consecutive bricks, one
+// brick per step: the 65 cell starts of a brick are two coalesced loads + one broadcast (a thread per
+// brick read 65 words at a 256-byte stride: 89 us for the 21 M cells of the YCB frame).
 __global__ void brick_mask_kernel(const uint32_t* __restrict__ cell_start, uint32_t nbricks,
                                   unsigned long long* __restrict__ masks, uint32_t* __restrict__ occ,
                                   uint32_t* __restrict__ brick_occ) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long m = 0ull;
-  if (b < nbricks) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // bricks 32*group .. 32*group + 31
+  if ((size_t)group * 32 >= nbricks) return;
+  uint32_t word = 0u;
+  for (int t = 0; t < 32; ++t) {
+    const uint32_t b = group * 32 + t;
+    if (b >= nbricks) break;
     const uint32_t* cs = cell_start + (size_t)b * 64;
-    uint32_t prev = cs[0];
-    for (int k = 0; k < 64; ++k) {
-      const uint32_t nxt = cs[k + 1];
-      if (nxt != prev) m |= 1ull << k;
-      prev = nxt;
-    }
-    masks[b] = m;
-    occ[b] = (uint32_t)__popcll(m);
+    const uint32_t v0 = cs[lane], v1 = cs[32 + lane];
+    const uint32_t v2 = cs[64];
+    uint32_t n0 = __shfl_down_sync(0xffffffffu, v0, 1), n1 = __shfl_down_sync(0xffffffffu, v1, 1);
+    const uint32_t first1 = __shfl_sync(0xffffffffu, v1, 0);
+    if (lane == 31) { n0 = first1; n1 = v2; }
+    const unsigned lo = __ballot_sync(0xffffffffu, n0 != v0), hi = __ballot_sync(0xffffffffu, n1 != v1);
+    const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    if (lane == 0) { masks[b] = m; occ[b] = (uint32_t)__popcll(m); }
+    if (m) word |= 1u << t;
   }
   // 1 bit per brick: "has an occupied cell" (the scoring kernel's second-level filter)
-  const unsigned w = __ballot_sync(0xffffffffu, m != 0ull);
-  if ((threadIdx.x & 31) == 0 && b < nbricks) brick_occ[b >> 5] = w;
+  if (lane == 0) brick_occ[group] = word;
 }
 
 // brick table {mask lo, mask hi, index of the brick's first occupied cell, 0} + compact starts
@@ -465,15 +487,16 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
     STOCS_CUDA(ctx, ctx->d_cand.ensure(cap * 16));
     STOCS_CUDA(ctx, ctx->d_cell_start.ensure(starts_cap * 4));
     STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
-    grid_count_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
+    if (S <= (1 << 18)) grid_count_kernel<32><<<(unsigned)(((size_t)S * 32 + 255) / 256), 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
+    else grid_count_kernel<1><<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
     cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, counts, dense_start, (int)nc1, st);
     STOCS_CUDA(ctx, cudaMemcpyAsync(&h_counts[0], dense_start + g.ncells, 4, cudaMemcpyDeviceToHost, st));
-    STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
-    grid_fill_kernel<<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>(), (uint32_t)cap);
+    if (S <= (1 << 18)) grid_fill_kernel<32><<<(unsigned)(((size_t)S * 32 + 255) / 256), 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>(), (uint32_t)cap);
+    else grid_fill_kernel<1><<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, dense_start, counts, ctx->d_cand.as<float4>(), (uint32_t)cap);
     // brick table + compact starts
     STOCS_CUDA(ctx, cudaMemsetAsync(d_occ.p, 0, (size_t)(g.nbricks + 1) * 4, st));
-    brick_mask_kernel<<<bb, 128, 0, st>>>(dense_start, g.nbricks, d_masks.as<unsigned long long>(), d_occ.as<uint32_t>(),
-                                          ctx->d_brick_occ.as<uint32_t>());
+    brick_mask_kernel<<<(unsigned)(((size_t)g.nbricks + 255) / 256), 256, 0, st>>>(dense_start, g.nbricks, d_masks.as<unsigned long long>(),
+                                                                                  d_occ.as<uint32_t>(), ctx->d_brick_occ.as<uint32_t>());
     cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes2, d_occ.as<uint32_t>(), d_occ_scan.as<uint32_t>(), (int)(g.nbricks + 1), st);
     STOCS_CUDA(ctx, cudaMemcpyAsync(&h_counts[1], d_occ_scan.as<uint32_t>() + g.nbricks, 4, cudaMemcpyDeviceToHost, st));
     STOCS_CUDA(ctx, cudaMemsetAsync(ctx->d_coarse.p, 0, (size_t)ctx->coarse_words * 4, st));

@@ -85,7 +85,9 @@ enum PoolSlot : int {
   POOL_TOPK_LISTS_AUX = 46,
   // congruent.cu / fit.cu: device scalars of one congruent-set search or pipeline run (StocsPipeState)
   POOL_PIPE_STATE = 47,
-  POOL_COUNT = 48
+  // congruent.cu: per-base occupancy filter over the Q entries' position cells (128 words per base)
+  POOL_CONG_BLOOM = 48,
+  POOL_COUNT = 56
 };
 
 // Device scalars of one congruent-set search (congruent.cu) and of the pipeline run around it (fit.cu).
@@ -172,7 +174,7 @@ struct stocs_b200_ctx {
   // grow-only scratch slots reused by the multi-kernel stages (no cudaMalloc/cudaFree per call).
   // Slots are named by PoolSlot below.  Rule: a slot is single-stream scratch -- NO slot may hold
   // state across ABI calls, so stages that never run inside one another may share a number.
-  DevBuf pool[48];
+  DevBuf pool[POOL_COUNT];
   // scratch
   DevBuf d_T, d_lcp, d_inl, d_work, d_tmp, d_tmp2, d_small;
   void* h_pinned = nullptr;

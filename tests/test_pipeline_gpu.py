@@ -234,6 +234,14 @@ def test_capacity_retry_paths_give_the_same_results(world, monkeypatch):
         assert list(r.best_T_centred) == list(r0.best_T_centred) and list(r.best_T_world) == list(r0.best_T_world)
         quads, offs = ctx.find_congruent(bases, invs)
         assert np.array_equal(quads, quads0) and np.array_equal(offs, offs0)
+        # item capacity above 2^20: the best pose comes from the general top-K launch instead of the
+        # closing block's own scan; with max_sets beyond every base's quad count both take all quads
+        assert np.diff(offs0).max() < 20000
+        ra, rb = ctx0.run_pipeline(SEED, n_bases=N_BASES, max_sets=20000), ctx0.run_pipeline(SEED, n_bases=N_BASES, max_sets=30000)   # (default quad capacity: 2^21)
+        assert N_BASES * 20000 <= (1 << 20) < N_BASES * 30000
+        for f in ("n_valid_bases", "n_congruent_sets", "n_transforms", "best_index", "best_lcp", "best_base"):
+            assert getattr(ra, f) == getattr(rb, f), f
+        assert ra.n_transforms > r0.n_transforms and list(ra.best_T_world) == list(rb.best_T_world)
     finally:
         ctx.close()
     # a second context with tiny capacities, find_congruent first (its own retry loop)
