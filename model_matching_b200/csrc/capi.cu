@@ -108,6 +108,7 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   if (ctx->h_top) cudaFreeHost(ctx->h_top);
   if (ctx->h_pipe_state) cudaFreeHost(ctx->h_pipe_state);
   if (ctx->h_index_counts) cudaFreeHost(ctx->h_index_counts);
+  if (ctx->h_kd_stage) cudaFreeHost(ctx->h_kd_stage);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;

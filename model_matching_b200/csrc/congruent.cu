@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(256) cong_gather_kernel(PpfView v, const BaseI
   __syncthreads();
   const uint32_t n = bi.nP + bi.nQ;       // == total (bins 0..127 hold the P list, 128..255 the Q list)
   const uint32_t outP = seg_off[b], outQ = seg_off[n_bases + b];
-  for (uint32_t e = j; e < n; e += 256) {
+  // gridDim.y blocks share a base (a few bases carry lists of 10^4 entries: one block each was the stage's tail)
+  for (uint32_t e = blockIdx.y * 256 + j; e < n; e += 256 * gridDim.y) {
     int lo = 0, hi = 256;                 // last bin whose offset is <= e (empty bins share offsets: the last one is the non-empty one)
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_loc[mid] <= e) lo = mid; else hi = mid; }
     const uint32_t code = v.pairs[s_start[lo] + (e - s_loc[lo])];
@@ -301,36 +302,50 @@ __global__ void cong_match_kernel(const uint32_t* __restrict__ codes, const uint
   const uint32_t q0 = seg_off[n_bases + b] - totalP, q1 = seg_off[n_bases + b + 1] - totalP;
   const PEntry p = pe[wid];
   const bool pvalid = p.nbin >= 0 && p.nbin < 343;  // std::array::at would throw otherwise
+  if (!pvalid) continue;   // no congruent set (counts[wid] stays 0; the write pass never gets here: its count is 0)
   if (!WRITE) {
     const uint32_t h = bloom_slot(p.cell);
-    if (!pvalid || !((bloom[(size_t)b * kBloomWords + (h >> 5)] >> (h & 31)) & 1u)) continue;   // counts[wid] stays 0
+    if (!((bloom[(size_t)b * kBloomWords + (h >> 5)] >> (h & 31)) & 1u)) continue;   // counts[wid] stays 0
   }
   const uint32_t pcode = codes[wid];
   uint32_t cnt = 0;
   uint32_t wpos = WRITE ? out_off[wid] : 0;
-  for (uint32_t base = q0; base < q1; base += 32) {
-    const uint32_t i = base + lane;
-    bool m = false;
-    if (i < q1 && pvalid && qcell[i] == p.cell) {
-      const QEntry& q = qe[i];
-      if ((q.mask[p.nbin >> 5] >> (p.nbin & 31)) & 1u) {
-        const float dx = q.qx - p.ix, dy = q.qy - p.iy, dz = q.qz - p.iz;
-        m = (dx * dx + (dy * dy + dz * dz)) <= thr;  // squared distance vs UNSQUARED threshold (quirk 1)
-      }
+  // 8 tiles of 32 Q entries per round, their cell loads issued together: one round trip to L2 per
+  // 256 entries (one per 32 left a warp waiting ~0.3 us per tile: 130 us for the 10 540-entry list of
+  // one YCB base, whatever the other 9 000 warps did)
+  constexpr int kTiles = 8;
+  for (uint32_t base = q0; base < q1; base += 32 * kTiles) {
+    int qc[kTiles];
+#pragma unroll
+    for (int k = 0; k < kTiles; ++k) {
+      const uint32_t i = base + 32 * k + lane;
+      qc[k] = (i < q1) ? qcell[i] : -1;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, m);
-    if (WRITE) {
-      if (m) {
-        const uint32_t o = wpos + __popc(bal & ((1u << lane) - 1u));
-        const uint32_t qcode = codes[totalP + i];
-        quads[4 * (size_t)o + 0] = (int)(pcode >> 16);
-        quads[4 * (size_t)o + 1] = (int)(pcode & 0xffffu);
-        quads[4 * (size_t)o + 2] = (int)(qcode >> 16);
-        quads[4 * (size_t)o + 3] = (int)(qcode & 0xffffu);
+#pragma unroll
+    for (int k = 0; k < kTiles; ++k) {
+      const uint32_t i = base + 32 * k + lane;
+      bool m = false;
+      if (i < q1 && qc[k] == p.cell) {
+        const QEntry& q = qe[i];
+        if ((q.mask[p.nbin >> 5] >> (p.nbin & 31)) & 1u) {
+          const float dx = q.qx - p.ix, dy = q.qy - p.iy, dz = q.qz - p.iz;
+          m = (dx * dx + (dy * dy + dz * dz)) <= thr;  // squared distance vs UNSQUARED threshold (quirk 1)
+        }
       }
-      wpos += __popc(bal);
-    } else {
-      cnt += __popc(bal);
+      const unsigned bal = __ballot_sync(0xffffffffu, m);
+      if (WRITE) {
+        if (m) {
+          const uint32_t o = wpos + __popc(bal & ((1u << lane) - 1u));
+          const uint32_t qcode = codes[totalP + i];
+          quads[4 * (size_t)o + 0] = (int)(pcode >> 16);
+          quads[4 * (size_t)o + 1] = (int)(pcode & 0xffffu);
+          quads[4 * (size_t)o + 2] = (int)(qcode >> 16);
+          quads[4 * (size_t)o + 3] = (int)(qcode & 0xffffu);
+        }
+        wpos += __popc(bal);
+      } else {
+        cnt += __popc(bal);
+      }
     }
   }
   if (!WRITE && lane == 0) counts[wid] = cnt;
@@ -420,7 +435,7 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   cong_count_kernel<<<n_bases, 256, 0, st>>>(ctx->d_spos4.as<float4>(), ctx->d_sattr.as<float4>(), v, d_base_idx4, d_inv2,
                                              d_valid, n_bases, d_info.as<BaseInfo>());
   cong_seg_kernel<<<1, 256, 0, st>>>(d_info.as<BaseInfo>(), n_bases, d_seg.as<uint32_t>(), (unsigned long long)cap, d_state);
-  cong_gather_kernel<<<n_bases, 256, 0, st>>>(v, d_info.as<BaseInfo>(), d_seg.as<uint32_t>(), n_bases, d_codes_a.as<uint32_t>(), d_state);
+  cong_gather_kernel<<<dim3((unsigned)n_bases, 8), 256, 0, st>>>(v, d_info.as<BaseInfo>(), d_seg.as<uint32_t>(), n_bases, d_codes_a.as<uint32_t>(), d_state);
   // per-list sort by (id1, id2): the reference's list order (insertion order of the pair loop).
   // num_items only sizes the library's scratch; the segments come from d_seg on the device.
   cub::DeviceSegmentedRadixSort::SortKeys(d_tmp.p, tb, d_codes_a.as<uint32_t>(), d_codes_b.as<uint32_t>(), (int)cap,

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(1024) sample_bases_kernel(SampleArgs a) {
     // is the same set of points.
     if (stage >= 1) {
       const int bsel = s_b[stage - 1];
+      if (tid < 32) s_wsum[tid] = 0ull;   // (ordered before the adds below by the first barrier of the chunk loop)
       for (int c0 = 0; c0 < a.S; c0 += kChunk) {
         const int cn = min(kChunk, a.S - c0);           // points of this chunk
         const int cw = (cn + 31) >> 5;                  // bitmap words of this chunk
@@ -122,27 +123,31 @@ __global__ void __launch_bounds__(1024) sample_bases_kernel(SampleArgs a) {
             zero = zero || (planar > plane_threshold) || (norm(sub(p, pb[0])) < min_distance_base) ||
                    (norm(sub(p, pb[1])) < min_distance_base) || (norm(sub(p, pb[2])) < min_distance_base);
           }
-          if (!zero) atomicOr(&s_alive[o >> 5], 1u << (o & 31));
+          if (!zero) {
+            atomicOr(&s_alive[o >> 5], 1u << (o & 31));
+            // the survivor's weight goes straight to the sum of the warp range that owns its tile
+            // (integer adds: any order gives the sums the per-range pass of stage 0 would)
+            atomicAdd(&s_wsum[(i >> 5) / tpw], prob_weight(n4.w));
+          }
         }
         __syncthreads();
         if (tid < cw) alive[(c0 >> 5) + tid] = s_alive[tid];
         __syncthreads();
       }
     }
-    // ---- weights of the survivors, summed per warp range (integers: any order gives the same sums)
-    unsigned long long lsum = 0;
-    for (int t = t0; t < t1; ++t) {
-      const int i = t * 32 + lane;
-      bool al = false;
-      if (i < a.S) al = (stage == 0) ? true : (((alive[t] >> lane) & 1u) != 0u);
-      if (stage == 0) {
+    // ---- stage 0: every point is alive; weights summed per warp range
+    if (stage == 0) {
+      unsigned long long lsum = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int i = t * 32 + lane;
+        const bool al = i < a.S;
         const unsigned word = __ballot_sync(0xffffffffu, al);
         if (lane == 0) alive[t] = word;
+        if (al) lsum += prob_weight(a.sattr[i].w);
       }
-      if (al) lsum += prob_weight(a.sattr[i].w);
+      lsum = warp_sum_u64(lsum);
+      if (lane == 0) s_wsum[w] = lsum;
     }
-    lsum = warp_sum_u64(lsum);
-    if (lane == 0) s_wsum[w] = lsum;
     __syncthreads();
     if (tid == 0) {
       unsigned long long total = 0;
@@ -170,8 +175,10 @@ __global__ void __launch_bounds__(1024) sample_bases_kernel(SampleArgs a) {
       unsigned long long rem = s_rem;
       for (int t = t0; t < t1; ++t) {
         const int i = t * 32 + lane;
+        const uint32_t word = alive[t];
+        if (word == 0u) continue;          // (warp-uniform) nothing to walk over in this tile
         unsigned long long wt = 0;
-        if (i < a.S && ((alive[t] >> lane) & 1u)) wt = prob_weight(a.sattr[i].w);
+        if (i < a.S && ((word >> lane) & 1u)) wt = prob_weight(a.sattr[i].w);
         unsigned long long inc = wt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

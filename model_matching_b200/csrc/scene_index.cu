@@ -15,7 +15,6 @@
 // reproduce the reference's traversal-order tie rule (kdtree.h:416-428).
 #include <cub/device/device_scan.cuh>
 
-#include <thread>
 #include <cstdio>
 #include <algorithm>
 #include <cfloat>
@@ -172,19 +171,26 @@ __global__ void brick_mask_kernel(const uint32_t* __restrict__ cell_start, uint3
   const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // bricks 32*group .. 32*group + 31
   if ((size_t)group * 32 >= nbricks) return;
   uint32_t word = 0u;
-  for (int t = 0; t < 32; ++t) {
-    const uint32_t b = group * 32 + t;
-    if (b >= nbricks) break;
-    const uint32_t* cs = cell_start + (size_t)b * 64;
-    const uint32_t v0 = cs[lane], v1 = cs[32 + lane];
-    const uint32_t v2 = cs[64];
-    uint32_t n0 = __shfl_down_sync(0xffffffffu, v0, 1), n1 = __shfl_down_sync(0xffffffffu, v1, 1);
-    const uint32_t first1 = __shfl_sync(0xffffffffu, v1, 0);
-    if (lane == 31) { n0 = first1; n1 = v2; }
-    const unsigned lo = __ballot_sync(0xffffffffu, n0 != v0), hi = __ballot_sync(0xffffffffu, n1 != v1);
-    const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
-    if (lane == 0) { masks[b] = m; occ[b] = (uint32_t)__popcll(m); }
-    if (m) word |= 1u << t;
+  for (int t0 = 0; t0 < 32; t0 += 4) {   // 4 bricks per round: their 12 loads are issued together
+    uint32_t v0[4], v1[4], v2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t b = group * 32 + t0 + u;
+      const uint32_t* cs = cell_start + (size_t)(b < nbricks ? b : nbricks - 1) * 64;
+      v0[u] = cs[lane]; v1[u] = cs[32 + lane]; v2[u] = cs[64];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t b = group * 32 + t0 + u;
+      if (b >= nbricks) break;
+      uint32_t n0 = __shfl_down_sync(0xffffffffu, v0[u], 1), n1 = __shfl_down_sync(0xffffffffu, v1[u], 1);
+      const uint32_t first1 = __shfl_sync(0xffffffffu, v1[u], 0);
+      if (lane == 31) { n0 = first1; n1 = v2[u]; }
+      const unsigned lo = __ballot_sync(0xffffffffu, n0 != v0[u]), hi = __ballot_sync(0xffffffffu, n1 != v1[u]);
+      const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+      if (lane == 0) { masks[b] = m; occ[b] = (uint32_t)__popcll(m); }
+      if (m) word |= 1u << (t0 + u);
+    }
   }
   // 1 bit per brick: "has an occupied cell" (the scoring kernel's second-level filter)
   if (lane == 0) brick_occ[group] = word;
@@ -368,20 +374,10 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
     if (!(mn[k] <= mx[k]) || !std::isfinite(mn[k]) || !std::isfinite(mx[k]))
       STOCS_FAIL(ctx, STOCS_E_ARG, "upload_scene: scene contains non-finite coordinates");
 
-  // the reference kd-tree is host work on the centred points: build it on a second host thread
-  // while this one drives the grid kernels
+  // the reference kd-tree is host work on the centred points: it is built on THIS thread further
+  // down, after the grid kernels have been enqueued, so that the device works meanwhile (a second
+  // host thread cost more to start and join than the 90 us build it hid)
   KdBuild kb;
-  std::vector<float4> kp((size_t)S);
-  std::thread kd_thread([&kb, &kp, ctx, S] {
-    kb.build(ctx->h_spos.data(), S);
-    for (int i = 0; i < S; ++i) {
-      float w;
-      const int id = kb.idx[i];
-      memcpy(&w, &id, 4);
-      kp[i] = make_float4(kb.x[i], kb.y[i], kb.z[i], w);
-    }
-  });
-  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{kd_thread};
 
   // grid geometry.  Cell edge in units of eps, measured on B200 with the S1 workload (10^6
   // hypotheses, all bit-identical): 2.0 -> 4.3 ms, 1.0 -> 2.93 ms, 0.6 -> 2.73 ms, 0.5 -> 2.64 ms,
@@ -456,8 +452,12 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   size_t nc1 = (size_t)g.ncells + 1;
   DevBuf& d_dense = ctx->pool[POOL_INDEX_DENSE];  // dense per-cell starts (scratch)
   STOCS_CUDA(ctx, d_dense.ensure(nc1 * 4));
-  STOCS_CUDA(ctx, ctx->d_work.ensure(nc1 * 4));
-  uint32_t* counts = ctx->d_work.as<uint32_t>();
+  // per-cell counters: a buffer of their own that every build leaves ZEROED (the fill pass takes each
+  // count back down to 0), so only its first use -- or a larger grid -- pays the memset (84 MB on the YCB frame)
+  DevBuf& d_counts = ctx->pool[POOL_INDEX_COUNTS];
+  if (d_counts.bytes < nc1 * 4) ctx->index_counts_clean = 0;
+  STOCS_CUDA(ctx, d_counts.ensure(nc1 * 4));
+  uint32_t* counts = d_counts.as<uint32_t>();
   uint32_t* dense_start = d_dense.as<uint32_t>();
   DevBuf &d_masks = ctx->pool[POOL_INDEX_MASKS], &d_occ = ctx->pool[POOL_INDEX_OCC], &d_occ_scan = ctx->pool[POOL_INDEX_OCC_SCAN];
   STOCS_CUDA(ctx, d_masks.ensure((size_t)g.nbricks * 8));
@@ -486,7 +486,8 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
     const size_t starts_cap = (cap < (size_t)g.ncells ? cap : (size_t)g.ncells) + 1;
     STOCS_CUDA(ctx, ctx->d_cand.ensure(cap * 16));
     STOCS_CUDA(ctx, ctx->d_cell_start.ensure(starts_cap * 4));
-    STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
+    if (ctx->index_counts_clean < nc1) STOCS_CUDA(ctx, cudaMemsetAsync(counts, 0, nc1 * 4, st));
+    ctx->index_counts_clean = 0;   // dirty until this attempt's fill pass has run to completion
     if (S <= (1 << 18)) grid_count_kernel<32><<<(unsigned)(((size_t)S * 32 + 255) / 256), 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
     else grid_count_kernel<1><<<nb, 256, 0, st>>>(ctx->d_spos4.as<float4>(), S, g, r, counts);
     cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tmp_bytes, counts, dense_start, (int)nc1, st);
@@ -505,18 +506,45 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
                                            ctx->d_cell_start.as<uint32_t>(), ctx->d_coarse.as<uint32_t>(), g, cshift, cnx + 1, cny + 1);
     STOCS_CUDA(ctx, cudaGetLastError());
     if (!kd_uploaded) {
-      // reference kd-tree (tie resolution only): built by the host thread started above, while this
-      // one enqueued the grid kernels; its upload joins the same queue
-      kd_thread.join();
+      // reference kd-tree (tie resolution only), built here while the device runs the kernels above;
+      // leaf points and nodes go through a page-locked staging buffer (frame-sized scenes) so that the
+      // upload does not block this thread either
+      kb.build(ctx->h_spos.data(), S);
       ctx->kd_nodes = (int)kb.nodes.size();
-      STOCS_CUDA(ctx, ctx->d_kd_nodes.ensure(kb.nodes.size() * sizeof(KdNodeDev)));
-      STOCS_CUDA(ctx, ctx->d_kd_pts.ensure((size_t)S * 16));
-      STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_nodes.p, kb.nodes.data(), kb.nodes.size() * sizeof(KdNodeDev),
-                                      cudaMemcpyHostToDevice, st));
-      STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_pts.p, kp.data(), (size_t)S * 16, cudaMemcpyHostToDevice, st));
+      const size_t node_bytes = kb.nodes.size() * sizeof(KdNodeDev), pts_bytes = (size_t)S * 16;
+      STOCS_CUDA(ctx, ctx->d_kd_nodes.ensure(node_bytes));
+      STOCS_CUDA(ctx, ctx->d_kd_pts.ensure(pts_bytes));
+      float4* kp = nullptr;
+      std::vector<float4> kp_pageable;
+      if (pts_bytes + node_bytes <= (size_t)(64u << 20)) {
+        if (ctx->h_kd_stage_bytes < pts_bytes + node_bytes) {
+          STOCS_CUDA(ctx, cudaStreamSynchronize(st));   // (an earlier upload may still read the old buffer)
+          if (ctx->h_kd_stage) cudaFreeHost(ctx->h_kd_stage);
+          ctx->h_kd_stage = nullptr; ctx->h_kd_stage_bytes = 0;
+          const size_t want = (pts_bytes + node_bytes) * 2;
+          STOCS_CUDA(ctx, cudaHostAlloc(&ctx->h_kd_stage, want, cudaHostAllocDefault));
+          ctx->h_kd_stage_bytes = want;
+        }
+        kp = (float4*)ctx->h_kd_stage;
+      } else {
+        kp_pageable.resize((size_t)S);
+        kp = kp_pageable.data();
+      }
+      for (int i = 0; i < S; ++i) {
+        float w;
+        const int id = kb.idx[i];
+        memcpy(&w, &id, 4);
+        kp[i] = make_float4(kb.x[i], kb.y[i], kb.z[i], w);
+      }
+      const void* nodes_src = kb.nodes.data();
+      if (kp_pageable.empty()) { memcpy((char*)ctx->h_kd_stage + pts_bytes, kb.nodes.data(), node_bytes); nodes_src = (char*)ctx->h_kd_stage + pts_bytes; }
+      STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_nodes.p, nodes_src, node_bytes, cudaMemcpyHostToDevice, st));
+      STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_pts.p, kp, pts_bytes, cudaMemcpyHostToDevice, st));
       kd_uploaded = true;
+      // (pageable sources have been consumed when cudaMemcpyAsync returns; the staging buffer lives in the context)
     }
     STOCS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->index_counts_clean = nc1;
     total = h_counts[0]; n_occ = h_counts[1];
     if ((size_t)total <= cap) break;
     if (attempt >= 1) STOCS_FAIL(ctx, STOCS_E_CUDA, "upload_scene: candidate buffer sizing failed");

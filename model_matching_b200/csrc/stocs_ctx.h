@@ -87,6 +87,8 @@ enum PoolSlot : int {
   POOL_PIPE_STATE = 47,
   // congruent.cu: per-base occupancy filter over the Q entries' position cells (128 words per base)
   POOL_CONG_BLOOM = 48,
+  // scene_index.cu: per-cell counters of the index build, zero between builds (state across calls by design)
+  POOL_INDEX_COUNTS = 49,
   POOL_COUNT = 56
 };
 
@@ -185,6 +187,9 @@ struct stocs_b200_ctx {
   long long pipe_last_items = 0;       // transforms of the previous pipeline run (sizes the next run's grids)
   StocsPipeState* h_pipe_state = nullptr;   // page-locked landing zone of the state record
   uint32_t* h_index_counts = nullptr;       // page-locked: list lengths of the scene-index build
+  size_t index_counts_clean = 0;            // leading words of pool[POOL_INDEX_COUNTS] known to be zero
+  void* h_kd_stage = nullptr;               // page-locked staging of the kd-tree upload (frame-sized scenes)
+  size_t h_kd_stage_bytes = 0;
 
   // last score call
   int64_t last_H = 0;
