@@ -91,6 +91,7 @@ int stocs_b200_create(stocs_b200_ctx** out, int device) {
 void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  stocs_kd_finish(ctx, ctx->stream, false);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   stocs_b200_comm_destroy(ctx);
   DevBuf* bufs[] = {&ctx->d_model, &ctx->d_mpos4, &ctx->d_mnrm4, &ctx->d_spos4, &ctx->d_sattr, &ctx->d_spix,
@@ -109,6 +110,7 @@ void stocs_b200_destroy(stocs_b200_ctx* ctx) {
   if (ctx->h_pipe_state) cudaFreeHost(ctx->h_pipe_state);
   if (ctx->h_index_counts) cudaFreeHost(ctx->h_index_counts);
   if (ctx->h_kd_stage) cudaFreeHost(ctx->h_kd_stage);
+  if (ctx->kd_copy_done) cudaEventDestroy(ctx->kd_copy_done);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -205,6 +207,7 @@ int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float*
   // so an early error return cannot leave S > 0 describing buffers that were half replaced.
   ctx->S = 0;
   ctx->S_pending = S;
+  stocs_kd_finish(ctx, st, false);   // a kd-tree still being built belongs to the scene this call replaces
   // attributes: d_tmp = nrm3 | cls
   STOCS_CUDA(ctx, ctx->d_tmp.ensure((size_t)S * 16));
   float* d_n = ctx->d_tmp.as<float>();

@@ -49,14 +49,17 @@ struct BaseInfo {
   Ppf4 f1, f2;
   float inv1, inv2, cos_alpha;
   uint32_t nP, nQ;
+  uint32_t nb_sample;   // directions on the base's cone (normalset.hpp:178-195); table in the cone buffer when <= kConeMax
 };
+constexpr int kConeMax = 64;   // 2 * ceil(3.5 * 2 pi atan(alpha)) <= 56 for alpha in [0, pi]
 
 __device__ __forceinline__ V3 ld3(const float4* p, int i) { const float4 v = p[i]; return v3(v.x, v.y, v.z); }
 
 // per base: PPF keys of the two base segments, alpha, list lengths
 __global__ void cong_count_kernel(const float4* __restrict__ spos4, const float4* __restrict__ sattr, PpfView v,
                                   const int* __restrict__ base_idx4, const float* __restrict__ inv2,
-                                  const uint8_t* __restrict__ valid, int n_bases, BaseInfo* __restrict__ info) {
+                                  const uint8_t* __restrict__ valid, int n_bases, BaseInfo* __restrict__ info,
+                                  float4* __restrict__ cone) {
   const int b = blockIdx.x;
   const int j = threadIdx.x;  // 256 threads: 0..127 -> P bins, 128..255 -> Q bins
   __shared__ BaseInfo s;
@@ -88,8 +91,24 @@ __global__ void cong_count_kernel(const float4* __restrict__ spos4, const float4
     // src/stocs.cpp:788: either list empty => no congruent set
     if (nP == 0 || nQ == 0) { nP = 0; nQ = 0; }
     s.nP = nP; s.nQ = nQ;
-    info[b] = s;
   }
+  // The cone of directions every Q entry of this base rasterises (normalset.hpp:178-195) is the same
+  // set of vectors d0[a] = (sin(alpha) cos(theta_a), sin(alpha) sin(theta_a), cos(alpha)) before the
+  // per-entry rotation: computed here once per base instead of once per Q entry (two binary64
+  // sin/cos per direction, up to 56 directions, 10^4 entries on some bases)
+  float cosAlpha = s.cos_alpha;
+  if (cosAlpha > 1.0f) cosAlpha = 1.0f;      // (deviation D2: clamped)
+  if (cosAlpha < -1.0f) cosAlpha = -1.0f;
+  const float alpha = acos_f(cosAlpha);
+  const float perimeter = (float)((double)2.0f * kPi * (double)atan_f(alpha));
+  const unsigned nbSample = (unsigned)(2.0f * ceilf(perimeter * 7.0f / 2.0f));
+  if ((unsigned)j < nbSample && j < kConeMax) {
+    const float angleStep = (float)((double)2.0f * kPi / (double)(float)nbSample);
+    const float sinAlpha = sin_f(alpha);
+    const float theta = (float)j * angleStep;
+    cone[(size_t)b * kConeMax + j] = make_float4(sinAlpha * cos_f(theta), sinAlpha * sin_f(theta), cosAlpha, 0.f);
+  }
+  if (j == 0) { s.nb_sample = nbSample; info[b] = s; }
 }
 
 // exclusive scan of one value per thread over a 256-thread block; *total = the block's sum
@@ -201,7 +220,8 @@ struct QEntry { float qx, qy, qz; uint32_t mask[11]; };          // queryQ (mode
 __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
                                     const BaseInfo* __restrict__ info, int n_bases, const StocsPipeState* __restrict__ stt,
                                     const float4* __restrict__ mpos4, ModelNorm mn, PEntry* __restrict__ pe,
-                                    QEntry* __restrict__ qe, int* __restrict__ qcell, uint32_t* __restrict__ bloom) {
+                                    QEntry* __restrict__ qe, int* __restrict__ qcell, uint32_t* __restrict__ bloom,
+                                    const float4* __restrict__ cone) {
   const uint32_t totalP = stt->totalP, total = stt->total;
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
   const bool isP = e < totalP;
@@ -233,15 +253,18 @@ __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const ui
     const V3 qq = add(w1, scale(sub(w2, w1), bi.inv2));
     o.qx = qq.x; o.qy = qq.y; o.qz = qq.z;
     for (int k = 0; k < 11; ++k) o.mask[k] = 0u;
-    // normalset.hpp:178-195 (cosAlpha clamped: deviation D2)
+    // normalset.hpp:178-195 (cosAlpha clamped: deviation D2); the unrotated cone comes from the base's table
+    const unsigned nbSample = bi.nb_sample;
+    const bool tabled = nbSample <= (unsigned)kConeMax;
     float cosAlpha = bi.cos_alpha;
     if (cosAlpha > 1.0f) cosAlpha = 1.0f;
     if (cosAlpha < -1.0f) cosAlpha = -1.0f;
-    const float alpha = acos_f(cosAlpha);
-    const float perimeter = (float)((double)2.0f * kPi * (double)atan_f(alpha));
-    const unsigned nbSample = (unsigned)(2.0f * ceilf(perimeter * 7.0f / 2.0f));
-    const float angleStep = (float)((double)2.0f * kPi / (double)(float)nbSample);
-    const float sinAlpha = sin_f(alpha);
+    float angleStep = 0.f, sinAlpha = 0.f;
+    if (!tabled) {   // (cannot happen for alpha in [0, pi]; kept so that the result never depends on the table size)
+      const float alpha = acos_f(cosAlpha);
+      angleStep = (float)((double)2.0f * kPi / (double)(float)nbSample);
+      sinAlpha = sin_f(alpha);
+    }
     // Quaternion::setFromTwoVectors((0,0,1), dirn)  (deviation D5 on the antiparallel branch)
     const V3 v0 = v3(0.f, 0.f, 1.f);
     const V3 v1 = normalized(dirn);
@@ -262,8 +285,14 @@ __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const ui
       qw = s * 0.5f;
     }
     for (unsigned a = 0; a != nbSample; a++) {
-      const float theta = (float)a * angleStep;
-      const V3 d0 = v3(sinAlpha * cos_f(theta), sinAlpha * sin_f(theta), cosAlpha);
+      V3 d0;
+      if (tabled) {
+        const float4 t = cone[(size_t)b * kConeMax + a];
+        d0 = v3(t.x, t.y, t.z);
+      } else {
+        const float theta = (float)a * angleStep;
+        d0 = v3(sinAlpha * cos_f(theta), sinAlpha * sin_f(theta), cosAlpha);
+      }
       V3 uv = cross(qv, d0);
       uv = add(uv, uv);
       const V3 rot = add(add(d0, scale(uv, qw)), cross(qv, uv));
@@ -285,14 +314,25 @@ __global__ void cong_match_kernel(const uint32_t* __restrict__ codes, const uint
                                   int n_bases, const StocsPipeState* __restrict__ stt, const PEntry* __restrict__ pe,
                                   const QEntry* __restrict__ qe, const int* __restrict__ qcell, float thr,
                                   uint32_t* __restrict__ counts, const uint32_t* __restrict__ out_off,
-                                  int* __restrict__ quads, const uint32_t* __restrict__ bloom) {
+                                  int* __restrict__ quads, const uint32_t* __restrict__ bloom, uint32_t* __restrict__ first2) {
   const int lane = threadIdx.x & 31;
   const uint32_t totalP = stt->totalP;
   if (WRITE && stt->overflow) return;   // the quads would not fit: the caller grows the buffer and searches again
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < totalP; wid += nwarps) {
   // the write pass only visits P entries that counted at least one set (counts were zeroed: skipped entries hold 0)
-  if (WRITE && out_off[wid + 1] == out_off[wid]) continue;
+  if (WRITE) {
+    const uint32_t o0 = out_off[wid], c = out_off[wid + 1] - o0;
+    if (c == 0) continue;
+    if (c <= 2) {   // the counting pass left the entry's first two partners in first2: no second sweep
+      if (lane < (int)c) {
+        const uint32_t pc = codes[wid], qc = codes[totalP + first2[2 * (size_t)wid + lane]];
+        int4 q4 = make_int4((int)(pc >> 16), (int)(pc & 0xffffu), (int)(qc >> 16), (int)(qc & 0xffffu));
+        reinterpret_cast<int4*>(quads)[o0 + lane] = q4;
+      }
+      continue;
+    }
+  }
   int lo = 0, hi = n_bases;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -344,6 +384,10 @@ __global__ void cong_match_kernel(const uint32_t* __restrict__ codes, const uint
         }
         wpos += __popc(bal);
       } else {
+        if (m) {   // remember the first two partners (Q index relative to the Q block) for the write pass
+          const uint32_t rank = cnt + __popc(bal & ((1u << lane) - 1u));
+          if (rank < 2) first2[2 * (size_t)wid + rank] = i;
+        }
         cnt += __popc(bal);
       }
     }
@@ -409,7 +453,8 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   const PpfView v = stocs_ppf_view(ctx);
   DevBuf &d_info = ctx->pool[POOL_CONG_INFO], &d_seg = ctx->pool[POOL_CONG_SEG], &d_codes_a = ctx->pool[POOL_CONG_CODES_A], &d_codes_b = ctx->pool[POOL_CONG_CODES_B], &d_tmp = ctx->pool[POOL_CONG_TMP],
          &d_pe = ctx->pool[POOL_CONG_PE], &d_qe = ctx->pool[POOL_CONG_QE], &d_qcell = ctx->pool[POOL_CONG_QCELL], &d_cnt = ctx->pool[POOL_CONG_CNT], &d_scan = ctx->pool[POOL_CONG_SCAN],
-         &quads_buf = ctx->pool[POOL_CONG_QUADS], &d_bloom = ctx->pool[POOL_CONG_BLOOM];
+         &quads_buf = ctx->pool[POOL_CONG_QUADS], &d_bloom = ctx->pool[POOL_CONG_BLOOM], &d_cone = ctx->pool[POOL_CONG_CONE],
+         &d_first2 = ctx->pool[POOL_CONG_FIRST2];
 #define CG(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return STOCS_E_CUDA; } } while (0)
   const size_t cap = (size_t)ctx->cong_cap_codes, capq = (size_t)ctx->cong_cap_quads;
   CG(d_info.ensure((size_t)n_bases * sizeof(BaseInfo)));
@@ -423,6 +468,8 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   CG(d_scan.ensure((cap + 1) * 4));
   CG(quads_buf.ensure(capq * 16));
   CG(d_bloom.ensure((size_t)n_bases * kBloomWords * 4));
+  CG(d_cone.ensure((size_t)n_bases * kConeMax * 16));
+  CG(d_first2.ensure(cap * 8));
   // (id1 << 16) | id2 with ids < M: the bits above 16 + ceil(log2 M) are zero
   int end_bit = 17;
   while (end_bit < 32 && (1 << (end_bit - 16)) < ctx->M) ++end_bit;
@@ -433,7 +480,7 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   CG(d_tmp.ensure(tb > tb2 ? tb : tb2));
 
   cong_count_kernel<<<n_bases, 256, 0, st>>>(ctx->d_spos4.as<float4>(), ctx->d_sattr.as<float4>(), v, d_base_idx4, d_inv2,
-                                             d_valid, n_bases, d_info.as<BaseInfo>());
+                                             d_valid, n_bases, d_info.as<BaseInfo>(), d_cone.as<float4>());
   cong_seg_kernel<<<1, 256, 0, st>>>(d_info.as<BaseInfo>(), n_bases, d_seg.as<uint32_t>(), (unsigned long long)cap, d_state);
   cong_gather_kernel<<<dim3((unsigned)n_bases, 8), 256, 0, st>>>(v, d_info.as<BaseInfo>(), d_seg.as<uint32_t>(), n_bases, d_codes_a.as<uint32_t>(), d_state);
   // per-list sort by (id1, id2): the reference's list order (insertion order of the pair loop).
@@ -446,17 +493,17 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   CG(cudaMemsetAsync(d_bloom.p, 0, (size_t)n_bases * kBloomWords * 4, st));
   cong_prepare_kernel<<<wide, 128, 0, st>>>(codes, d_seg.as<uint32_t>(), d_info.as<BaseInfo>(), n_bases, d_state,
                                             ctx->d_mpos4.as<float4>(), mn, d_pe.as<PEntry>(), d_qe.as<QEntry>(), d_qcell.as<int>(),
-                                            d_bloom.as<uint32_t>());
+                                            d_bloom.as<uint32_t>(), d_cone.as<float4>());
   CG(cudaMemsetAsync(d_cnt.p, 0, (cap + 1) * 4, st));
   cong_match_kernel<false><<<wide, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
                                                  d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, d_cnt.as<uint32_t>(), nullptr, nullptr,
-                                                 d_bloom.as<uint32_t>());
+                                                 d_bloom.as<uint32_t>(), d_first2.as<uint32_t>());
   cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(cap + 1), st);
   cong_base_offsets_kernel<<<1, 256, 0, st>>>(d_seg.as<uint32_t>(), d_scan.as<uint32_t>(), n_bases, (unsigned long long)capq,
                                               d_state, d_quad_off);
   cong_match_kernel<true><<<wide, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
                                                 d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, nullptr, d_scan.as<uint32_t>(),
-                                                quads_buf.as<int>(), nullptr);
+                                                quads_buf.as<int>(), nullptr, d_first2.as<uint32_t>());
   CG(cudaGetLastError());
 #undef CG
   return STOCS_OK;

@@ -22,6 +22,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <thread>
 
 #include "stocs_ctx.h"
 
@@ -232,18 +234,29 @@ struct KdBuild {
   std::vector<KdNodeDev> nodes;
   const float* comp(unsigned d) const { return d == 0 ? x.data() : (d == 1 ? y.data() : z.data()); }
 
+  // The reference's partition (kdtree.h:522-538) walks l up to the first element >= sv and r down to the
+  // first element < sv, swaps them and repeats: it pairs the k-th misplaced element of the left part
+  // with the k-th misplaced element, counted from the end, of the right part, where "left part" is the
+  // first mid = #{c < sv} slots, and returns mid.  Written as count -> two branch-free compactions ->
+  // swaps it produces the SAME permutation (checked against the loop form on 2*10^5 random arrays with
+  // repeated values) at a third of the cost: the loop form mispredicts on every other element.
+  std::vector<int> Lbuf, Rbuf;
   unsigned partition(int start, int end, unsigned dim, float sv) {
     const float* c = comp(dim);
-    int l = start, r = end - 1;
-    for (; l < r; ++l, --r) {
-      while (l < end && c[l] < sv) l++;
-      while (r >= start && c[r] >= sv) r--;
-      if (l > r) break;
+    int mid = start;
+    for (int i = start; i < end; ++i) mid += (c[i] < sv) ? 1 : 0;
+    if ((int)Lbuf.size() < end - start) { Lbuf.resize((size_t)(end - start)); Rbuf.resize((size_t)(end - start)); }
+    int nl = 0, nr = 0;
+    int* L = Lbuf.data();
+    int* R = Rbuf.data();
+    for (int i = start; i < mid; ++i) { L[nl] = i; nl += (c[i] >= sv) ? 1 : 0; }
+    for (int i = end - 1; i >= mid; --i) { R[nr] = i; nr += (c[i] < sv) ? 1 : 0; }
+    for (int k = 0; k < nl; ++k) {   // nl == nr
+      const int l = L[k], r = R[k];
       std::swap(x[l], x[r]); std::swap(y[l], y[r]); std::swap(z[l], z[r]);
       std::swap(idx[l], idx[r]);
     }
-    if (l >= end) return (unsigned)end;
-    return c[l] < sv ? (unsigned)(l + 1) : (unsigned)l;
+    return (unsigned)mid;
   }
 
   void build(const float* pos3, int n) {
@@ -258,11 +271,17 @@ struct KdBuild {
       Job j = todo.back();
       todo.pop_back();
       const float big = FLT_MAX / 2;
-      float mn[3] = {big, big, big}, mx[3] = {-big, -big, -big};
-      for (unsigned i = j.start; i < j.end; ++i) {
-        if (x[i] < mn[0]) mn[0] = x[i]; if (x[i] > mx[0]) mx[0] = x[i];
-        if (y[i] < mn[1]) mn[1] = y[i]; if (y[i] > mx[1]) mx[1] = y[i];
-        if (z[i] < mn[2]) mn[2] = z[i]; if (z[i] > mx[2]) mx[2] = z[i];
+      float mn[3], mx[3];
+      {  // bounding box of the node's points (scalars + selects: the compiler vectorises this form)
+        const float* xs = x.data(); const float* ys = y.data(); const float* zs = z.data();
+        float a0 = big, a1 = big, a2 = big, b0 = -big, b1 = -big, b2 = -big;
+        for (unsigned i = j.start; i < j.end; ++i) {
+          const float vx = xs[i], vy = ys[i], vz = zs[i];
+          a0 = vx < a0 ? vx : a0; b0 = vx > b0 ? vx : b0;
+          a1 = vy < a1 ? vy : a1; b1 = vy > b1 ? vy : b1;
+          a2 = vz < a2 ? vz : a2; b2 = vz > b2 ? vz : b2;
+        }
+        mn[0] = a0; mn[1] = a1; mn[2] = a2; mx[0] = b0; mx[1] = b1; mx[2] = b2;
       }
       float hd[3] = {0.5f * (mx[0] - mn[0]), 0.5f * (mx[1] - mn[1]), 0.5f * (mx[2] - mn[2])};
       unsigned dim = 0;
@@ -300,6 +319,85 @@ struct KdBuild {
 // sum (src/stocs.cpp:945-956), i.e. three dependent add chains of length n: one SM needs 5.5 ms for
 // 2^20 points, a host core ~1.3 ms, and the host runs it while the H2D copy of the points is still in
 // flight.  Without host data the single-CTA kernel does the same sum on the device.
+// The reference kd-tree serves one purpose on the device: resolving EXACT distance ties in the scoring
+// kernel.  Nothing before the first scoring launch needs it, so upload_scene starts its build (host
+// work on the centred points, ~0.3 ms for a 13 000-point frame) on a host thread and returns once the
+// grid index is complete; the first scoring launch -- in the online pipeline that is after base
+// sampling, congruent sets and fits have been enqueued -- joins the thread and queues the upload in
+// front of its kernel (stocs_kd_finish).  A new scene or the context's destruction joins it too.
+struct KdPending {
+  std::thread th;
+  KdBuild kb;
+  int S = 0;
+  float4* pts = nullptr;                 // leaf-ordered points {x, y, z, bits(index)}: page-locked staging or `pageable`
+  std::vector<float4> pageable;
+  bool failed = false;
+};
+
+int stocs_kd_finish(stocs_b200_ctx* ctx, cudaStream_t st, bool upload) {
+  KdPending* kp = ctx->kd_pending;
+  if (!kp) return STOCS_OK;
+  if (kp->th.joinable()) kp->th.join();
+  ctx->kd_pending = nullptr;
+  struct Deleter { KdPending* p; ~Deleter() { delete p; } } del{kp};
+  if (!upload) return STOCS_OK;
+  if (kp->failed) STOCS_FAIL(ctx, STOCS_E_CUDA, "upload_scene: kd-tree construction failed (out of host memory)");
+  const size_t node_bytes = kp->kb.nodes.size() * sizeof(KdNodeDev), pts_bytes = (size_t)kp->S * 16;
+  ctx->kd_nodes = (int)kp->kb.nodes.size();
+  STOCS_CUDA(ctx, ctx->d_kd_nodes.ensure(node_bytes));
+  STOCS_CUDA(ctx, ctx->d_kd_pts.ensure(pts_bytes));
+  // (pageable sources -- the node array always, the points of very large scenes -- have been consumed
+  // when cudaMemcpyAsync returns; the page-locked staging buffer is guarded by kd_copy_done)
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_nodes.p, kp->kb.nodes.data(), node_bytes, cudaMemcpyHostToDevice, st));
+  STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_pts.p, kp->pts, pts_bytes, cudaMemcpyHostToDevice, st));
+  if (!ctx->kd_copy_done) STOCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->kd_copy_done, cudaEventDisableTiming));
+  STOCS_CUDA(ctx, cudaEventRecord(ctx->kd_copy_done, st));
+  // scoring launches on the context's other streams (chunked host-buffer calls alternate between two) wait for it too
+  for (cudaStream_t other : {ctx->stream, ctx->aux_stream})
+    if (other && other != st) STOCS_CUDA(ctx, cudaStreamWaitEvent(other, ctx->kd_copy_done, 0));
+  if (!kp->pageable.empty()) STOCS_CUDA(ctx, cudaStreamSynchronize(st));   // the pageable copy dies with kp
+  return STOCS_OK;
+}
+
+// starts the build of the kd-tree over ctx->h_spos (S centred points) on a host thread
+static int kd_start(stocs_b200_ctx* ctx, int S) {
+  stocs_kd_finish(ctx, ctx->stream, false);
+  const size_t pts_bytes = (size_t)S * 16;
+  KdPending* kp = new (std::nothrow) KdPending();
+  if (!kp) STOCS_FAIL(ctx, STOCS_E_CUDA, "upload_scene: out of host memory");
+  kp->S = S;
+  if (pts_bytes <= (size_t)(64u << 20)) {
+    if (ctx->kd_copy_done) cudaEventSynchronize(ctx->kd_copy_done);   // the previous scene's upload has left the staging buffer
+    if (ctx->h_kd_stage_bytes < pts_bytes) {
+      if (ctx->h_kd_stage) cudaFreeHost(ctx->h_kd_stage);
+      ctx->h_kd_stage = nullptr; ctx->h_kd_stage_bytes = 0;
+      if (cudaHostAlloc(&ctx->h_kd_stage, pts_bytes * 2, cudaHostAllocDefault) != cudaSuccess) {
+        delete kp;
+        STOCS_FAIL(ctx, STOCS_E_CUDA, "upload_scene: page-locked allocation failed");
+      }
+      ctx->h_kd_stage_bytes = pts_bytes * 2;
+    }
+    kp->pts = (float4*)ctx->h_kd_stage;
+  }
+  const float* pos = ctx->h_spos.data();
+  ctx->kd_pending = kp;
+  kp->th = std::thread([kp, pos, S] {
+    try {
+      if (!kp->pts) { kp->pageable.resize((size_t)S); kp->pts = kp->pageable.data(); }
+      kp->kb.build(pos, S);
+      for (int i = 0; i < S; ++i) {
+        float w;
+        const int id = kp->kb.idx[i];
+        memcpy(&w, &id, 4);
+        kp->pts[i] = make_float4(kp->kb.x[i], kp->kb.y[i], kp->kb.z[i], w);
+      }
+    } catch (...) {
+      kp->failed = true;
+    }
+  });
+  return STOCS_OK;
+}
+
 int stocs_centre_points(stocs_b200_ctx* ctx, const float* d_pos3, int n, float4* d_out4,
                         float* d_out3, float* h_centroid3, float* h_aabb6, const float* h_pos3, float* h_centred3) {
   cudaStream_t st = ctx->stream;
@@ -374,10 +472,10 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
     if (!(mn[k] <= mx[k]) || !std::isfinite(mn[k]) || !std::isfinite(mx[k]))
       STOCS_FAIL(ctx, STOCS_E_ARG, "upload_scene: scene contains non-finite coordinates");
 
-  // the reference kd-tree is host work on the centred points: it is built on THIS thread further
-  // down, after the grid kernels have been enqueued, so that the device works meanwhile (a second
-  // host thread cost more to start and join than the 90 us build it hid)
-  KdBuild kb;
+  // the reference kd-tree (exact-tie resolution in the scoring kernel): host work on the centred
+  // points, started here on a host thread and collected by the first scoring launch
+  rc = kd_start(ctx, S);
+  if (rc) return rc;
 
   // grid geometry.  Cell edge in units of eps, measured on B200 with the S1 workload (10^6
   // hypotheses, all bit-identical): 2.0 -> 4.3 ms, 1.0 -> 2.93 ms, 0.6 -> 2.73 ms, 0.5 -> 2.64 ms,
@@ -481,7 +579,6 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   const unsigned bb = (g.nbricks + 127) / 128;
   uint32_t* h_counts = ctx->h_index_counts;   // page-locked: {candidate records, occupied cells}
   uint32_t total = 0, n_occ = 0;
-  bool kd_uploaded = false;
   for (int attempt = 0;; ++attempt) {
     const size_t starts_cap = (cap < (size_t)g.ncells ? cap : (size_t)g.ncells) + 1;
     STOCS_CUDA(ctx, ctx->d_cand.ensure(cap * 16));
@@ -505,44 +602,6 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
                                            dense_start + g.ncells, (uint32_t)starts_cap, ctx->d_bricks.as<uint4>(),
                                            ctx->d_cell_start.as<uint32_t>(), ctx->d_coarse.as<uint32_t>(), g, cshift, cnx + 1, cny + 1);
     STOCS_CUDA(ctx, cudaGetLastError());
-    if (!kd_uploaded) {
-      // reference kd-tree (tie resolution only), built here while the device runs the kernels above;
-      // leaf points and nodes go through a page-locked staging buffer (frame-sized scenes) so that the
-      // upload does not block this thread either
-      kb.build(ctx->h_spos.data(), S);
-      ctx->kd_nodes = (int)kb.nodes.size();
-      const size_t node_bytes = kb.nodes.size() * sizeof(KdNodeDev), pts_bytes = (size_t)S * 16;
-      STOCS_CUDA(ctx, ctx->d_kd_nodes.ensure(node_bytes));
-      STOCS_CUDA(ctx, ctx->d_kd_pts.ensure(pts_bytes));
-      float4* kp = nullptr;
-      std::vector<float4> kp_pageable;
-      if (pts_bytes + node_bytes <= (size_t)(64u << 20)) {
-        if (ctx->h_kd_stage_bytes < pts_bytes + node_bytes) {
-          STOCS_CUDA(ctx, cudaStreamSynchronize(st));   // (an earlier upload may still read the old buffer)
-          if (ctx->h_kd_stage) cudaFreeHost(ctx->h_kd_stage);
-          ctx->h_kd_stage = nullptr; ctx->h_kd_stage_bytes = 0;
-          const size_t want = (pts_bytes + node_bytes) * 2;
-          STOCS_CUDA(ctx, cudaHostAlloc(&ctx->h_kd_stage, want, cudaHostAllocDefault));
-          ctx->h_kd_stage_bytes = want;
-        }
-        kp = (float4*)ctx->h_kd_stage;
-      } else {
-        kp_pageable.resize((size_t)S);
-        kp = kp_pageable.data();
-      }
-      for (int i = 0; i < S; ++i) {
-        float w;
-        const int id = kb.idx[i];
-        memcpy(&w, &id, 4);
-        kp[i] = make_float4(kb.x[i], kb.y[i], kb.z[i], w);
-      }
-      const void* nodes_src = kb.nodes.data();
-      if (kp_pageable.empty()) { memcpy((char*)ctx->h_kd_stage + pts_bytes, kb.nodes.data(), node_bytes); nodes_src = (char*)ctx->h_kd_stage + pts_bytes; }
-      STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_nodes.p, nodes_src, node_bytes, cudaMemcpyHostToDevice, st));
-      STOCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_kd_pts.p, kp, pts_bytes, cudaMemcpyHostToDevice, st));
-      kd_uploaded = true;
-      // (pageable sources have been consumed when cudaMemcpyAsync returns; the staging buffer lives in the context)
-    }
     STOCS_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->index_counts_clean = nc1;
     total = h_counts[0]; n_occ = h_counts[1];
@@ -552,7 +611,7 @@ int stocs_build_scene_index(stocs_b200_ctx* ctx) {
   }
   ctx->ncand = total;
   ctx->counters[4] = n_occ;
-  tr.mark("index build + kd-tree");
+  tr.mark("index build");
   ctx->counters[2] = g.ncells;
   ctx->counters[3] = total;
   return STOCS_OK;

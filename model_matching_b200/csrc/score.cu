@@ -647,6 +647,9 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
                        const long long* d_H, long long grid_hint) {
   if (H <= 0) return STOCS_OK;
   if (H >= (1ll << 31)) STOCS_FAIL(ctx, STOCS_E_ARG, "score: at most 2^31-1 hypotheses per call");
+  // the kd-tree of a freshly uploaded scene may still be under construction on a host thread: collect
+  // it and queue its upload in front of this launch (no-op on every later launch)
+  if (ctx->kd_pending) { const int rc = stocs_kd_finish(ctx, st); if (rc) return rc; }
   ScoreArgs a;
   a.bricks = ctx->d_bricks.as<uint4>();
   a.coarse = ctx->d_coarse.as<uint32_t>();

@@ -89,6 +89,10 @@ enum PoolSlot : int {
   POOL_CONG_BLOOM = 48,
   // scene_index.cu: per-cell counters of the index build, zero between builds (state across calls by design)
   POOL_INDEX_COUNTS = 49,
+  // congruent.cu: per-base table of cone directions
+  POOL_CONG_CONE = 50,
+  // congruent.cu: first two congruent partners of every P entry (counting pass -> write pass)
+  POOL_CONG_FIRST2 = 51,
   POOL_COUNT = 56
 };
 
@@ -190,6 +194,8 @@ struct stocs_b200_ctx {
   size_t index_counts_clean = 0;            // leading words of pool[POOL_INDEX_COUNTS] known to be zero
   void* h_kd_stage = nullptr;               // page-locked staging of the kd-tree upload (frame-sized scenes)
   size_t h_kd_stage_bytes = 0;
+  struct KdPending* kd_pending = nullptr;   // kd-tree of the current scene, still being built on a host thread
+  cudaEvent_t kd_copy_done = nullptr;       // the staging buffer may be overwritten once this has completed
 
   // last score call
   int64_t last_H = 0;
@@ -232,6 +238,8 @@ int stocs_launch_score(stocs_b200_ctx* ctx, const float* d_T, int64_t H, float* 
 int stocs_launch_backproject(stocs_b200_ctx* ctx, const uint16_t* d_depth, const uint8_t* d_bgr,
                              int W, int H, float fx, float cx, float fy, float cy, float scale,
                              float* d_xyz, uint32_t* d_rgb, cudaStream_t st);  // backproject.cu
+// joins the kd-tree build started by upload_scene (if any) and, with upload = true, queues its upload on st
+int stocs_kd_finish(stocs_b200_ctx* ctx, cudaStream_t st, bool upload = true);  // scene_index.cu
 bool stocs_fmad_selftest(stocs_b200_ctx* ctx);                             // score.cu
 bool stocs_is_host_memory(const void* p);                                  // capi.cu
 // top-K of a device lcp array (reduce.cu); d_idx/d_val may be NULL when only records are wanted
