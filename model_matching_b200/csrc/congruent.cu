@@ -10,10 +10,12 @@
 // cell.  A (P,Q) combination is emitted iff
 //     cell(P) == cell(Q)  and  normal_bin(P) in cone_bins(Q)  and  |queryQ - invPoint|^2 <= thr
 // and the result is ordered by (rank of P in its list, rank of Q in its list).  That predicate
-// needs no grid at all: one thread computes (cell, normal bin, invPoint) per P entry, one thread
-// computes (cell, 343-bit cone mask, queryQ) per Q entry, and one warp per P entry sweeps its
-// base's Q list (cheap 4-byte cell compare first), counting, then writing in ballot order, which
-// is exactly the std::set order of the reference.
+// needs no 6-D grid: one thread computes (cell, normal bin, invPoint) per P entry, a few lanes
+// compute (cell, 343-bit cone mask, queryQ) per Q entry and chain it into a hash table keyed by
+// (base, cell), and one thread per P entry walks the chain of its own (base, cell) -- a handful of
+// entries -- counting, then writing its partners in ascending Q rank, which is exactly the std::set
+// order of the reference.  (Round 1 swept the base's whole Q list per P entry: 10^4 x 10^4 on the
+// largest base of the YCB frame, 0.12 ms of latency-bound rounds per pose.)
 //
 // The whole search is ENQUEUED without a host round trip (stocs_congruent_enqueue): list lengths,
 // segment offsets and quad counts stay on the device in a StocsPipeState record, the buffers are
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(256) cong_seg_kernel(const BaseInfo* __restric
   unsigned long long offP = block_excl_scan_256(locP, s_buf, &totalP);
   unsigned long long offQ = block_excl_scan_256(locQ, s_buf, &totalQ);
   const unsigned long long total = totalP + totalQ;
-  const uint32_t ovf = (total >= (1ull << 31)) ? 4u : (total > cap_codes ? 1u : 0u);
+  // (2^28 entries: the prepare kernel numbers 8 work items per Q entry in 32 bits)
+  const uint32_t ovf = (total >= (1ull << 28)) ? 4u : (total > cap_codes ? 1u : 0u);
   if (ovf) {
     for (int b = b0; b < b1; ++b) { seg[b] = 0u; seg[n_bases + b] = 0u; }
   } else {
@@ -209,29 +212,47 @@ __device__ __forceinline__ V3 to_unit(const ModelNorm& mn, V3 p) {
   return v3(d.x + 0.5f, d.y + 0.5f, d.z + 0.5f);
 }
 
-struct PEntry { float ix, iy, iz; int cell; int nbin; };          // invPoint (model frame)
-// 4096-bit occupancy filter per base over the position cells of its Q entries: a P entry whose cell's
-// bit is clear has no congruent partner and skips the sweep of the Q list (more than 9 in 10 do)
-constexpr int kBloomWords = 128;
-__device__ __forceinline__ uint32_t bloom_slot(int cell) { return ((uint32_t)cell * 2654435761u) >> 20; }
+struct PEntry { float ix, iy, iz; int cell; int nbin; int base; };   // invPoint (model frame)
+// Q entries are chained by (base, position cell) in one table of `table_size` (a power of two, at least
+// twice the code capacity) heads; chains mix entries of different bases and cells, told apart on the walk
+constexpr uint32_t kNoEntry = 0xffffffffu;
+__device__ __forceinline__ uint32_t chain_slot(int b, int cell, int table_bits) {
+  return (((uint32_t)cell * 2654435761u) ^ ((uint32_t)b * 0x9E3779B1u + 0x7F4A7C15u)) >> (32 - table_bits);
+}
 struct QEntry { float qx, qy, qz; uint32_t mask[11]; };          // queryQ (model frame), cone bins
 
 // entry e of the flat (sorted) code buffer: P entries first, then Q entries
 __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
                                     const BaseInfo* __restrict__ info, int n_bases, const StocsPipeState* __restrict__ stt,
                                     const float4* __restrict__ mpos4, ModelNorm mn, PEntry* __restrict__ pe,
-                                    QEntry* __restrict__ qe, int* __restrict__ qcell, uint32_t* __restrict__ bloom,
-                                    const float4* __restrict__ cone) {
+                                    QEntry* __restrict__ qe, int* __restrict__ qcell, uint32_t* __restrict__ head,
+                                    uint32_t* __restrict__ next, int table_bits, const float4* __restrict__ cone) {
+  // Work items: one thread per P entry, then -- from the next multiple of 32, so that a warp never mixes
+  // the two kinds -- kQLanes consecutive lanes per Q entry, which share the entry's cone of up to 56
+  // directions (the serial loop over the cone was the stage's critical path) and OR their bin masks.
+  constexpr uint32_t kQLanes = 8;
   const uint32_t totalP = stt->totalP, total = stt->total;
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-  const bool isP = e < totalP;
+  const uint32_t P32 = (totalP + 31u) & ~31u;
+  const uint32_t items = P32 + (total - totalP) * kQLanes;
+  const uint32_t items32 = (items + 31u) & ~31u;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < items32; v += gridDim.x * blockDim.x) {
+  const bool isP = v < totalP;
+  const bool inQ = v >= P32;                       // warp-uniform
+  const uint32_t ql = inQ ? ((v - P32) % kQLanes) : 0u;   // lane of the Q entry's group
+  const uint32_t e = isP ? v : (inQ ? totalP + (v - P32) / kQLanes : total);
+  const bool live = e < total;
+  QEntry o;
+  for (int k = 0; k < 11; ++k) o.mask[k] = 0u;
+  o.qx = o.qy = o.qz = 0.f;
+  int b = 0, qc = 0;
+  if (live) {
   // find the base (segment) by binary search in seg_off (2*n_bases+1 entries)
   int lo = isP ? 0 : n_bases, hi = isP ? n_bases : 2 * n_bases;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (seg_off[mid] <= e) lo = mid; else hi = mid;
   }
-  const int b = isP ? lo : lo - n_bases;
+  b = isP ? lo : lo - n_bases;
   const BaseInfo bi = info[b];
   const uint32_t code = codes[e];
   const int i1 = (int)(code >> 16), i2 = (int)(code & 0xffffu);
@@ -240,19 +261,19 @@ __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const ui
   const V3 du = sub(u2, u1);
   const V3 dirn = normalized(du);
   if (isP) {
-    PEntry o;
+    PEntry po;
     const V3 pos = add(u1, scale(du, bi.inv1));
-    o.cell = index_pos(mn, pos);
-    o.nbin = index_normal(mn, dirn);
+    po.cell = index_pos(mn, pos);
+    po.nbin = index_normal(mn, dirn);
     const V3 ip = add(w1, scale(sub(w2, w1), bi.inv1));
-    o.ix = ip.x; o.iy = ip.y; o.iz = ip.z;
-    pe[e] = o;
+    po.ix = ip.x; po.iy = ip.y; po.iz = ip.z;
+    po.base = b;
+    pe[e] = po;
   } else {
-    QEntry o;
     const V3 query = add(u1, scale(du, bi.inv2));
     const V3 qq = add(w1, scale(sub(w2, w1), bi.inv2));
     o.qx = qq.x; o.qy = qq.y; o.qz = qq.z;
-    for (int k = 0; k < 11; ++k) o.mask[k] = 0u;
+    qc = index_pos(mn, query);
     // normalset.hpp:178-195 (cosAlpha clamped: deviation D2); the unrotated cone comes from the base's table
     const unsigned nbSample = bi.nb_sample;
     const bool tabled = nbSample <= (unsigned)kConeMax;
@@ -284,7 +305,7 @@ __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const ui
       qv = scale(axis, invs);
       qw = s * 0.5f;
     }
-    for (unsigned a = 0; a != nbSample; a++) {
+    for (unsigned a = ql; a < nbSample; a += kQLanes) {
       V3 d0;
       if (tabled) {
         const float4 t = cone[(size_t)b * kConeMax + a];
@@ -299,100 +320,90 @@ __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const ui
       const int id = index_normal(mn, normalized(rot));
       if (id >= 0 && id < 343) o.mask[id >> 5] |= 1u << (id & 31);
     }
-    qe[e - totalP] = o;
-    const int qc = index_pos(mn, query);
-    qcell[e - totalP] = qc;
-    const uint32_t h = bloom_slot(qc);
-    atomicOr(&bloom[(size_t)b * kBloomWords + (h >> 5)], 1u << (h & 31));
+  }
+  }
+  if (inQ) {   // whole warp: OR the bin masks of the kQLanes lanes of each entry
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      uint32_t m = o.mask[k];
+      m |= __shfl_xor_sync(0xffffffffu, m, 1);
+      m |= __shfl_xor_sync(0xffffffffu, m, 2);
+      m |= __shfl_xor_sync(0xffffffffu, m, 4);
+      o.mask[k] = m;
+    }
+    if (live && ql == 0) {
+      qe[e - totalP] = o;
+      qcell[e - totalP] = qc;
+      next[e - totalP] = atomicExch(&head[chain_slot(b, qc, table_bits)], e - totalP);
+    }
   }
   }
 }
 
-// one warp per P entry; WRITE=false counts, WRITE=true emits quads
+// does Q entry q (index into the Q block) form a congruent set with P entry p?
+__device__ __forceinline__ bool congruent_pair(const PEntry& p, const QEntry* __restrict__ qe, const int* __restrict__ qcell,
+                                               uint32_t q, float thr) {
+  if (qcell[q] != p.cell) return false;
+  const QEntry& e = qe[q];
+  if (!((e.mask[p.nbin >> 5] >> (p.nbin & 31)) & 1u)) return false;
+  const float dx = e.qx - p.ix, dy = e.qy - p.iy, dz = e.qz - p.iz;
+  return (dx * dx + (dy * dy + dz * dz)) <= thr;  // squared distance vs UNSQUARED threshold (quirk 1)
+}
+
+// one thread per P entry; WRITE=false counts its partners, WRITE=true emits the quads in ascending Q rank
 template <bool WRITE>
 __global__ void cong_match_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
                                   int n_bases, const StocsPipeState* __restrict__ stt, const PEntry* __restrict__ pe,
                                   const QEntry* __restrict__ qe, const int* __restrict__ qcell, float thr,
                                   uint32_t* __restrict__ counts, const uint32_t* __restrict__ out_off,
-                                  int* __restrict__ quads, const uint32_t* __restrict__ bloom, uint32_t* __restrict__ first2) {
-  const int lane = threadIdx.x & 31;
+                                  int* __restrict__ quads, const uint32_t* __restrict__ head,
+                                  const uint32_t* __restrict__ next, int table_bits) {
   const uint32_t totalP = stt->totalP;
   if (WRITE && stt->overflow) return;   // the quads would not fit: the caller grows the buffer and searches again
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < totalP; wid += nwarps) {
-  // the write pass only visits P entries that counted at least one set (counts were zeroed: skipped entries hold 0)
-  if (WRITE) {
-    const uint32_t o0 = out_off[wid], c = out_off[wid + 1] - o0;
-    if (c == 0) continue;
-    if (c <= 2) {   // the counting pass left the entry's first two partners in first2: no second sweep
-      if (lane < (int)c) {
-        const uint32_t pc = codes[wid], qc = codes[totalP + first2[2 * (size_t)wid + lane]];
-        int4 q4 = make_int4((int)(pc >> 16), (int)(pc & 0xffffu), (int)(qc >> 16), (int)(qc & 0xffffu));
-        reinterpret_cast<int4*>(quads)[o0 + lane] = q4;
-      }
-      continue;
+  for (uint32_t wid = blockIdx.x * blockDim.x + threadIdx.x; wid < totalP; wid += gridDim.x * blockDim.x) {
+    uint32_t o0 = 0, want = 0;
+    if (WRITE) {
+      o0 = out_off[wid]; want = out_off[wid + 1] - o0;
+      if (want == 0) continue;
     }
-  }
-  int lo = 0, hi = n_bases;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (seg_off[mid] <= wid) lo = mid; else hi = mid;
-  }
-  const int b = lo;
-  const uint32_t q0 = seg_off[n_bases + b] - totalP, q1 = seg_off[n_bases + b + 1] - totalP;
-  const PEntry p = pe[wid];
-  const bool pvalid = p.nbin >= 0 && p.nbin < 343;  // std::array::at would throw otherwise
-  if (!pvalid) continue;   // no congruent set (counts[wid] stays 0; the write pass never gets here: its count is 0)
-  if (!WRITE) {
-    const uint32_t h = bloom_slot(p.cell);
-    if (!((bloom[(size_t)b * kBloomWords + (h >> 5)] >> (h & 31)) & 1u)) continue;   // counts[wid] stays 0
-  }
-  const uint32_t pcode = codes[wid];
-  uint32_t cnt = 0;
-  uint32_t wpos = WRITE ? out_off[wid] : 0;
-  // 8 tiles of 32 Q entries per round, their cell loads issued together: one round trip to L2 per
-  // 256 entries (one per 32 left a warp waiting ~0.3 us per tile: 130 us for the 10 540-entry list of
-  // one YCB base, whatever the other 9 000 warps did)
-  constexpr int kTiles = 8;
-  for (uint32_t base = q0; base < q1; base += 32 * kTiles) {
-    int qc[kTiles];
-#pragma unroll
-    for (int k = 0; k < kTiles; ++k) {
-      const uint32_t i = base + 32 * k + lane;
-      qc[k] = (i < q1) ? qcell[i] : -1;
-    }
-#pragma unroll
-    for (int k = 0; k < kTiles; ++k) {
-      const uint32_t i = base + 32 * k + lane;
-      bool m = false;
-      if (i < q1 && qc[k] == p.cell) {
-        const QEntry& q = qe[i];
-        if ((q.mask[p.nbin >> 5] >> (p.nbin & 31)) & 1u) {
-          const float dx = q.qx - p.ix, dy = q.qy - p.iy, dz = q.qz - p.iz;
-          m = (dx * dx + (dy * dy + dz * dz)) <= thr;  // squared distance vs UNSQUARED threshold (quirk 1)
+    const PEntry p = pe[wid];
+    if (p.nbin < 0 || p.nbin >= 343) { if (!WRITE) counts[wid] = 0u; continue; }  // std::array::at would throw
+    const uint32_t q0 = seg_off[n_bases + p.base] - totalP, q1 = seg_off[n_bases + p.base + 1] - totalP;
+    const uint32_t first = head[chain_slot(p.base, p.cell, table_bits)];
+    if (!WRITE) {
+      uint32_t cnt = 0;
+      for (uint32_t q = first; q != kNoEntry; q = next[q])
+        if (q >= q0 && q < q1 && congruent_pair(p, qe, qcell, q, thr)) ++cnt;
+      counts[wid] = cnt;
+    } else {
+      // partners in ascending Q rank; the chain is in insertion (arbitrary) order
+      const uint32_t pcode = codes[wid];
+      constexpr uint32_t kLocal = 24;
+      if (want <= kLocal) {   // one walk, then an insertion sort of the few partners
+        uint32_t found[kLocal];
+        uint32_t n = 0;
+        for (uint32_t q = first; q != kNoEntry; q = next[q])
+          if (q >= q0 && q < q1 && congruent_pair(p, qe, qcell, q, thr)) {
+            uint32_t k = n++;
+            while (k > 0 && found[k - 1] > q) { found[k] = found[k - 1]; --k; }
+            found[k] = q;
+          }
+        for (uint32_t k = 0; k < n; ++k) {
+          const uint32_t qcode = codes[totalP + found[k]];
+          reinterpret_cast<int4*>(quads)[o0 + k] = make_int4((int)(pcode >> 16), (int)(pcode & 0xffffu), (int)(qcode >> 16), (int)(qcode & 0xffffu));
+        }
+      } else {                // many partners: the smallest rank above the previous one, `want` times
+        uint32_t last = 0; bool have_last = false;
+        for (uint32_t k = 0; k < want; ++k) {
+          uint32_t best = kNoEntry;
+          for (uint32_t q = first; q != kNoEntry; q = next[q])
+            if (q >= q0 && q < q1 && q < best && (!have_last || q > last) && congruent_pair(p, qe, qcell, q, thr)) best = q;
+          last = best; have_last = true;
+          const uint32_t qcode = codes[totalP + best];
+          reinterpret_cast<int4*>(quads)[o0 + k] = make_int4((int)(pcode >> 16), (int)(pcode & 0xffffu), (int)(qcode >> 16), (int)(qcode & 0xffffu));
         }
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, m);
-      if (WRITE) {
-        if (m) {
-          const uint32_t o = wpos + __popc(bal & ((1u << lane) - 1u));
-          const uint32_t qcode = codes[totalP + i];
-          quads[4 * (size_t)o + 0] = (int)(pcode >> 16);
-          quads[4 * (size_t)o + 1] = (int)(pcode & 0xffffu);
-          quads[4 * (size_t)o + 2] = (int)(qcode >> 16);
-          quads[4 * (size_t)o + 3] = (int)(qcode & 0xffffu);
-        }
-        wpos += __popc(bal);
-      } else {
-        if (m) {   // remember the first two partners (Q index relative to the Q block) for the write pass
-          const uint32_t rank = cnt + __popc(bal & ((1u << lane) - 1u));
-          if (rank < 2) first2[2 * (size_t)wid + rank] = i;
-        }
-        cnt += __popc(bal);
-      }
     }
-  }
-  if (!WRITE && lane == 0) counts[wid] = cnt;
   }
 }
 
@@ -453,8 +464,8 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   const PpfView v = stocs_ppf_view(ctx);
   DevBuf &d_info = ctx->pool[POOL_CONG_INFO], &d_seg = ctx->pool[POOL_CONG_SEG], &d_codes_a = ctx->pool[POOL_CONG_CODES_A], &d_codes_b = ctx->pool[POOL_CONG_CODES_B], &d_tmp = ctx->pool[POOL_CONG_TMP],
          &d_pe = ctx->pool[POOL_CONG_PE], &d_qe = ctx->pool[POOL_CONG_QE], &d_qcell = ctx->pool[POOL_CONG_QCELL], &d_cnt = ctx->pool[POOL_CONG_CNT], &d_scan = ctx->pool[POOL_CONG_SCAN],
-         &quads_buf = ctx->pool[POOL_CONG_QUADS], &d_bloom = ctx->pool[POOL_CONG_BLOOM], &d_cone = ctx->pool[POOL_CONG_CONE],
-         &d_first2 = ctx->pool[POOL_CONG_FIRST2];
+         &quads_buf = ctx->pool[POOL_CONG_QUADS], &d_head = ctx->pool[POOL_CONG_HEAD], &d_cone = ctx->pool[POOL_CONG_CONE],
+         &d_next = ctx->pool[POOL_CONG_NEXT];
 #define CG(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return STOCS_E_CUDA; } } while (0)
   const size_t cap = (size_t)ctx->cong_cap_codes, capq = (size_t)ctx->cong_cap_quads;
   CG(d_info.ensure((size_t)n_bases * sizeof(BaseInfo)));
@@ -467,9 +478,12 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   CG(d_cnt.ensure((cap + 1) * 4));
   CG(d_scan.ensure((cap + 1) * 4));
   CG(quads_buf.ensure(capq * 16));
-  CG(d_bloom.ensure((size_t)n_bases * kBloomWords * 4));
+  int table_bits = 10;
+  while (table_bits < 31 && ((size_t)1 << table_bits) < 2 * cap) ++table_bits;
+  const size_t table_size = (size_t)1 << table_bits;
+  CG(d_head.ensure(table_size * 4));
   CG(d_cone.ensure((size_t)n_bases * kConeMax * 16));
-  CG(d_first2.ensure(cap * 8));
+  CG(d_next.ensure(cap * 4));
   // (id1 << 16) | id2 with ids < M: the bits above 16 + ceil(log2 M) are zero
   int end_bit = 17;
   while (end_bit < 32 && (1 << (end_bit - 16)) < ctx->M) ++end_bit;
@@ -490,32 +504,33 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   const uint32_t* codes = d_codes_b.as<uint32_t>();
   const ModelNorm mn = model_norm(ctx);
   const unsigned wide = (unsigned)ctx->num_sms * 8;
-  CG(cudaMemsetAsync(d_bloom.p, 0, (size_t)n_bases * kBloomWords * 4, st));
+  CG(cudaMemsetAsync(d_head.p, 0xff, table_size * 4, st));   // kNoEntry
   cong_prepare_kernel<<<wide, 128, 0, st>>>(codes, d_seg.as<uint32_t>(), d_info.as<BaseInfo>(), n_bases, d_state,
                                             ctx->d_mpos4.as<float4>(), mn, d_pe.as<PEntry>(), d_qe.as<QEntry>(), d_qcell.as<int>(),
-                                            d_bloom.as<uint32_t>(), d_cone.as<float4>());
+                                            d_head.as<uint32_t>(), d_next.as<uint32_t>(), table_bits, d_cone.as<float4>());
   CG(cudaMemsetAsync(d_cnt.p, 0, (cap + 1) * 4, st));
-  cong_match_kernel<false><<<wide, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
-                                                 d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, d_cnt.as<uint32_t>(), nullptr, nullptr,
-                                                 d_bloom.as<uint32_t>(), d_first2.as<uint32_t>());
+  const unsigned mgrid = (unsigned)ctx->num_sms * 4;
+  cong_match_kernel<false><<<mgrid, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
+                                                  d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, d_cnt.as<uint32_t>(), nullptr, nullptr,
+                                                  d_head.as<uint32_t>(), d_next.as<uint32_t>(), table_bits);
   cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(cap + 1), st);
   cong_base_offsets_kernel<<<1, 256, 0, st>>>(d_seg.as<uint32_t>(), d_scan.as<uint32_t>(), n_bases, (unsigned long long)capq,
                                               d_state, d_quad_off);
-  cong_match_kernel<true><<<wide, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
-                                                d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, nullptr, d_scan.as<uint32_t>(),
-                                                quads_buf.as<int>(), nullptr, d_first2.as<uint32_t>());
+  cong_match_kernel<true><<<mgrid, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
+                                                 d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, nullptr, d_scan.as<uint32_t>(),
+                                                 quads_buf.as<int>(), d_head.as<uint32_t>(), d_next.as<uint32_t>(), table_bits);
   CG(cudaGetLastError());
 #undef CG
   return STOCS_OK;
 }
 
 // After a state record came back with overflow bits 1 or 2: raise the capacities to what the search
-// needs (+25 %).  Returns false when the search can never fit (bit 4: pair lists of 2^31 entries or more).
+// needs (+25 %).  Returns false when the search can never fit (bit 4: pair lists of 2^28 entries or more).
 bool stocs_congruent_grow(stocs_b200_ctx* ctx, const StocsPipeState& s) {
   if (s.overflow & 4u) return false;
   if ((s.overflow & 1u) && (long long)s.need_codes > ctx->cong_cap_codes) {
     long long want = (long long)(s.need_codes + s.need_codes / 4 + 1024);
-    if (want >= (1ll << 31)) want = (1ll << 31) - 1;
+    if (want >= (1ll << 28)) want = (1ll << 28) - 1;
     ctx->cong_cap_codes = want;
   }
   if ((s.overflow & 2u) && (long long)s.need_quads > ctx->cong_cap_quads)

@@ -85,14 +85,14 @@ enum PoolSlot : int {
   POOL_TOPK_LISTS_AUX = 46,
   // congruent.cu / fit.cu: device scalars of one congruent-set search or pipeline run (StocsPipeState)
   POOL_PIPE_STATE = 47,
-  // congruent.cu: per-base occupancy filter over the Q entries' position cells (128 words per base)
-  POOL_CONG_BLOOM = 48,
+  // congruent.cu: chain heads of the (base, cell) hash of the Q entries
+  POOL_CONG_HEAD = 48,
   // scene_index.cu: per-cell counters of the index build, zero between builds (state across calls by design)
   POOL_INDEX_COUNTS = 49,
   // congruent.cu: per-base table of cone directions
   POOL_CONG_CONE = 50,
-  // congruent.cu: first two congruent partners of every P entry (counting pass -> write pass)
-  POOL_CONG_FIRST2 = 51,
+  // congruent.cu: chain links of the Q entries
+  POOL_CONG_NEXT = 51,
   POOL_COUNT = 56
 };
 
@@ -105,7 +105,7 @@ struct StocsPipeState {
   unsigned long long need_quads;   // congruent sets of all bases
   uint32_t totalP, total;          // entries of the flat code buffer in use: P lists first, then Q lists
   uint32_t total_quads;
-  uint32_t overflow;               // 1: code buffers too small, 2: quad buffer too small, 4: pair lists >= 2^31 entries
+  uint32_t overflow;               // 1: code buffers too small, 2: quad buffer too small, 4: pair lists >= 2^28 entries
   long long n_items;               // transforms to fit (at most max_sets per base)
   long long n_ok;                  // of which pass the fit's orthogonality test
   long long best_item, rank_of_best;
