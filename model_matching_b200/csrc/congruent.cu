@@ -11,10 +11,10 @@
 //     cell(P) == cell(Q)  and  normal_bin(P) in cone_bins(Q)  and  |queryQ - invPoint|^2 <= thr
 // and the result is ordered by (rank of P in its list, rank of Q in its list).  That predicate
 // needs no 6-D grid: one thread computes (cell, normal bin, invPoint) per P entry, a few lanes
-// compute (cell, 343-bit cone mask, queryQ) per Q entry and chain it into a hash table keyed by
-// (base, cell), and one thread per P entry walks the chain of its own (base, cell) -- a handful of
-// entries -- counting, then writing its partners in ascending Q rank, which is exactly the std::set
-// order of the reference.  (Round 1 swept the base's whole Q list per P entry: 10^4 x 10^4 on the
+// compute (cell, 343-bit cone mask, queryQ) per Q entry, the Q entries are bucketed by a hash of
+// (base, cell) -- count, scan, scatter: every bucket a contiguous run of {Q index, cell} records -- and
+// one thread per P entry reads the bucket of its own (base, cell), counting, then writing its partners
+// in ascending Q rank, which is exactly the std::set order of the reference.  (Round 1 swept the base's whole Q list per P entry: 10^4 x 10^4 on the
 // largest base of the YCB frame, 0.12 ms of latency-bound rounds per pose.)
 //
 // The whole search is ENQUEUED without a host round trip (stocs_congruent_enqueue): list lengths,
@@ -213,8 +213,8 @@ __device__ __forceinline__ V3 to_unit(const ModelNorm& mn, V3 p) {
 }
 
 struct PEntry { float ix, iy, iz; int cell; int nbin; int base; };   // invPoint (model frame)
-// Q entries are chained by (base, position cell) in one table of `table_size` (a power of two, at least
-// twice the code capacity) heads; chains mix entries of different bases and cells, told apart on the walk
+// Q entries are bucketed by (base, position cell) in one table of `table_size` (a power of two, at least
+// twice the code capacity) buckets; a bucket may mix entries of different bases and cells, told apart on the read
 constexpr uint32_t kNoEntry = 0xffffffffu;
 __device__ __forceinline__ uint32_t chain_slot(int b, int cell, int table_bits) {
   return (((uint32_t)cell * 2654435761u) ^ ((uint32_t)b * 0x9E3779B1u + 0x7F4A7C15u)) >> (32 - table_bits);
@@ -225,8 +225,8 @@ struct QEntry { float qx, qy, qz; uint32_t mask[11]; };          // queryQ (mode
 __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
                                     const BaseInfo* __restrict__ info, int n_bases, const StocsPipeState* __restrict__ stt,
                                     const float4* __restrict__ mpos4, ModelNorm mn, PEntry* __restrict__ pe,
-                                    QEntry* __restrict__ qe, int* __restrict__ qcell, uint32_t* __restrict__ head,
-                                    uint32_t* __restrict__ next, int table_bits, const float4* __restrict__ cone) {
+                                    QEntry* __restrict__ qe, int* __restrict__ qcell, uint32_t* __restrict__ bcount,
+                                    uint32_t* __restrict__ qslot, int table_bits, const float4* __restrict__ cone) {
   // Work items: one thread per P entry, then -- from the next multiple of 32, so that a warp never mixes
   // the two kinds -- kQLanes consecutive lanes per Q entry, which share the entry's cone of up to 56
   // directions (the serial loop over the cone was the stage's critical path) and OR their bin masks.
@@ -334,73 +334,114 @@ __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const ui
     if (live && ql == 0) {
       qe[e - totalP] = o;
       qcell[e - totalP] = qc;
-      next[e - totalP] = atomicExch(&head[chain_slot(b, qc, table_bits)], e - totalP);
+      const uint32_t h = chain_slot(b, qc, table_bits);
+      qslot[e - totalP] = h;
+      atomicAdd(&bcount[h], 1u);
     }
   }
   }
 }
 
-// does Q entry q (index into the Q block) form a congruent set with P entry p?
-__device__ __forceinline__ bool congruent_pair(const PEntry& p, const QEntry* __restrict__ qe, const int* __restrict__ qcell,
-                                               uint32_t q, float thr) {
-  if (qcell[q] != p.cell) return false;
+// second half of the bucketing: every Q entry takes a slot of its bucket, from the back (the counts go
+// back to zero, so the table needs no clearing between searches)
+__global__ void cong_scatter_kernel(const StocsPipeState* __restrict__ stt, const uint32_t* __restrict__ qslot,
+                                    const int* __restrict__ qcell, const uint32_t* __restrict__ bstart,
+                                    uint32_t* __restrict__ bcount, uint2* __restrict__ bucket) {
+  const uint32_t totalQ = stt->total - stt->totalP;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < totalQ; q += gridDim.x * blockDim.x) {
+    const uint32_t h = qslot[q];
+    const uint32_t pos = bstart[h] + atomicSub(&bcount[h], 1u) - 1u;
+    bucket[pos] = make_uint2(q, (uint32_t)qcell[q]);
+  }
+}
+
+// does Q entry q (index into the Q block, same base and cell as p) form a congruent set with P entry p?
+__device__ __forceinline__ bool congruent_pair(const PEntry& p, const QEntry* __restrict__ qe, uint32_t q, float thr) {
   const QEntry& e = qe[q];
   if (!((e.mask[p.nbin >> 5] >> (p.nbin & 31)) & 1u)) return false;
   const float dx = e.qx - p.ix, dy = e.qy - p.iy, dz = e.qz - p.iz;
   return (dx * dx + (dy * dy + dz * dz)) <= thr;  // squared distance vs UNSQUARED threshold (quirk 1)
 }
 
-// one thread per P entry; WRITE=false counts its partners, WRITE=true emits the quads in ascending Q rank
+// one warp per P entry, 32 records of its bucket per step; WRITE=false counts its partners, WRITE=true
+// emits the quads in ascending Q rank.  (One THREAD per P entry left the stage waiting on the few hundred
+// entries whose cell holds a thousand Q entries: 64 + 93 us on a YCB frame with one 10^4-entry base.)
 template <bool WRITE>
-__global__ void cong_match_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
+__global__ void __launch_bounds__(256) cong_match_kernel(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ seg_off,
                                   int n_bases, const StocsPipeState* __restrict__ stt, const PEntry* __restrict__ pe,
-                                  const QEntry* __restrict__ qe, const int* __restrict__ qcell, float thr,
+                                  const QEntry* __restrict__ qe, float thr,
                                   uint32_t* __restrict__ counts, const uint32_t* __restrict__ out_off,
-                                  int* __restrict__ quads, const uint32_t* __restrict__ head,
-                                  const uint32_t* __restrict__ next, int table_bits) {
+                                  int* __restrict__ quads, const uint32_t* __restrict__ bstart,
+                                  const uint2* __restrict__ bucket, int table_bits) {
+  constexpr uint32_t kLocal = 64;
+  __shared__ uint32_t s_found[8][kLocal];
   const uint32_t totalP = stt->totalP;
   if (WRITE && stt->overflow) return;   // the quads would not fit: the caller grows the buffer and searches again
-  for (uint32_t wid = blockIdx.x * blockDim.x + threadIdx.x; wid < totalP; wid += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < totalP; wid += nwarps) {
     uint32_t o0 = 0, want = 0;
     if (WRITE) {
       o0 = out_off[wid]; want = out_off[wid + 1] - o0;
       if (want == 0) continue;
     }
     const PEntry p = pe[wid];
-    if (p.nbin < 0 || p.nbin >= 343) { if (!WRITE) counts[wid] = 0u; continue; }  // std::array::at would throw
+    if (p.nbin < 0 || p.nbin >= 343) { if (!WRITE && lane == 0) counts[wid] = 0u; continue; }  // std::array::at would throw
     const uint32_t q0 = seg_off[n_bases + p.base] - totalP, q1 = seg_off[n_bases + p.base + 1] - totalP;
-    const uint32_t first = head[chain_slot(p.base, p.cell, table_bits)];
+    const uint32_t h = chain_slot(p.base, p.cell, table_bits);
+    const uint32_t r0 = bstart[h], r1 = bstart[h + 1];
+    const uint32_t pcell = (uint32_t)p.cell;
+    // a record of the bucket is a partner when it is a Q entry of this base in this cell (the bucket may
+    // hold others) and passes the normal-bin and distance tests (the 56-byte Q entry is read only then)
+    auto partner = [&](uint32_t r, uint32_t& q) -> bool {
+      if (r >= r1) return false;
+      const uint2 rec = bucket[r];
+      q = rec.x;
+      return q >= q0 && q < q1 && rec.y == pcell && congruent_pair(p, qe, q, thr);
+    };
     if (!WRITE) {
       uint32_t cnt = 0;
-      for (uint32_t q = first; q != kNoEntry; q = next[q])
-        if (q >= q0 && q < q1 && congruent_pair(p, qe, qcell, q, thr)) ++cnt;
-      counts[wid] = cnt;
+      for (uint32_t r = r0; r < r1; r += 32) {
+        uint32_t q;
+        cnt += __popc(__ballot_sync(0xffffffffu, partner(r + lane, q)));
+      }
+      if (lane == 0) counts[wid] = cnt;
     } else {
-      // partners in ascending Q rank; the chain is in insertion (arbitrary) order
+      // partners in ascending Q rank; a bucket holds its records in arrival (arbitrary) order
       const uint32_t pcode = codes[wid];
-      constexpr uint32_t kLocal = 24;
-      if (want <= kLocal) {   // one walk, then an insertion sort of the few partners
-        uint32_t found[kLocal];
+      if (want <= kLocal) {   // collect, then every partner counts the smaller ones: that is its place
         uint32_t n = 0;
-        for (uint32_t q = first; q != kNoEntry; q = next[q])
-          if (q >= q0 && q < q1 && congruent_pair(p, qe, qcell, q, thr)) {
-            uint32_t k = n++;
-            while (k > 0 && found[k - 1] > q) { found[k] = found[k - 1]; --k; }
-            found[k] = q;
-          }
-        for (uint32_t k = 0; k < n; ++k) {
-          const uint32_t qcode = codes[totalP + found[k]];
-          reinterpret_cast<int4*>(quads)[o0 + k] = make_int4((int)(pcode >> 16), (int)(pcode & 0xffffu), (int)(qcode >> 16), (int)(qcode & 0xffffu));
+        for (uint32_t r = r0; r < r1; r += 32) {
+          uint32_t q = 0;
+          const bool m = partner(r + lane, q);
+          const unsigned bal = __ballot_sync(0xffffffffu, m);
+          if (m) s_found[w][n + __popc(bal & lt)] = q;
+          n += __popc(bal);
         }
+        __syncwarp();
+        for (uint32_t k = lane; k < n; k += 32) {
+          const uint32_t q = s_found[w][k];
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < n; ++j) rank += (s_found[w][j] < q) ? 1u : 0u;
+          const uint32_t qcode = codes[totalP + q];
+          reinterpret_cast<int4*>(quads)[o0 + rank] = make_int4((int)(pcode >> 16), (int)(pcode & 0xffffu), (int)(qcode >> 16), (int)(qcode & 0xffffu));
+        }
+        __syncwarp();
       } else {                // many partners: the smallest rank above the previous one, `want` times
         uint32_t last = 0; bool have_last = false;
         for (uint32_t k = 0; k < want; ++k) {
           uint32_t best = kNoEntry;
-          for (uint32_t q = first; q != kNoEntry; q = next[q])
-            if (q >= q0 && q < q1 && q < best && (!have_last || q > last) && congruent_pair(p, qe, qcell, q, thr)) best = q;
+          for (uint32_t r = r0; r < r1; r += 32) {
+            uint32_t q = 0;
+            if (partner(r + lane, q) && q < best && (!have_last || q > last)) best = q;
+          }
+          best = __reduce_min_sync(0xffffffffu, best);
           last = best; have_last = true;
-          const uint32_t qcode = codes[totalP + best];
-          reinterpret_cast<int4*>(quads)[o0 + k] = make_int4((int)(pcode >> 16), (int)(pcode & 0xffffu), (int)(qcode >> 16), (int)(qcode & 0xffffu));
+          if (lane == 0) {
+            const uint32_t qcode = codes[totalP + best];
+            reinterpret_cast<int4*>(quads)[o0 + k] = make_int4((int)(pcode >> 16), (int)(pcode & 0xffffu), (int)(qcode >> 16), (int)(qcode & 0xffffu));
+          }
         }
       }
     }
@@ -464,8 +505,8 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   const PpfView v = stocs_ppf_view(ctx);
   DevBuf &d_info = ctx->pool[POOL_CONG_INFO], &d_seg = ctx->pool[POOL_CONG_SEG], &d_codes_a = ctx->pool[POOL_CONG_CODES_A], &d_codes_b = ctx->pool[POOL_CONG_CODES_B], &d_tmp = ctx->pool[POOL_CONG_TMP],
          &d_pe = ctx->pool[POOL_CONG_PE], &d_qe = ctx->pool[POOL_CONG_QE], &d_qcell = ctx->pool[POOL_CONG_QCELL], &d_cnt = ctx->pool[POOL_CONG_CNT], &d_scan = ctx->pool[POOL_CONG_SCAN],
-         &quads_buf = ctx->pool[POOL_CONG_QUADS], &d_head = ctx->pool[POOL_CONG_HEAD], &d_cone = ctx->pool[POOL_CONG_CONE],
-         &d_next = ctx->pool[POOL_CONG_NEXT];
+         &quads_buf = ctx->pool[POOL_CONG_QUADS], &d_bcount = ctx->pool[POOL_CONG_HEAD], &d_cone = ctx->pool[POOL_CONG_CONE],
+         &d_qslot = ctx->pool[POOL_CONG_NEXT], &d_bstart = ctx->pool[POOL_CONG_BSTART], &d_bucket = ctx->pool[POOL_CONG_BUCKET];
 #define CG(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return STOCS_E_CUDA; } } while (0)
   const size_t cap = (size_t)ctx->cong_cap_codes, capq = (size_t)ctx->cong_cap_quads;
   CG(d_info.ensure((size_t)n_bases * sizeof(BaseInfo)));
@@ -481,17 +522,26 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   int table_bits = 10;
   while (table_bits < 31 && ((size_t)1 << table_bits) < 2 * cap) ++table_bits;
   const size_t table_size = (size_t)1 << table_bits;
-  CG(d_head.ensure(table_size * 4));
+  // bucket counters: every search leaves them zero (cong_scatter_kernel), so they are cleared only when
+  // the buffer is new -- or after a search that did not run to its end
+  const bool fresh = d_bcount.bytes < (table_size + 1) * 4 || ctx->cong_table_size != (long long)table_size || !ctx->cong_bcount_clean;
+  CG(d_bcount.ensure((table_size + 1) * 4));
+  CG(d_bstart.ensure((table_size + 1) * 4));
+  CG(d_bucket.ensure(cap * 8));
   CG(d_cone.ensure((size_t)n_bases * kConeMax * 16));
-  CG(d_next.ensure(cap * 4));
+  CG(d_qslot.ensure(cap * 4));
   // (id1 << 16) | id2 with ids < M: the bits above 16 + ceil(log2 M) are zero
   int end_bit = 17;
   while (end_bit < 32 && (1 << (end_bit - 16)) < ctx->M) ++end_bit;
-  size_t tb = 0, tb2 = 0;
+  size_t tb = 0, tb2 = 0, tb3 = 0;
   cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, d_codes_a.as<uint32_t>(), d_codes_b.as<uint32_t>(), (int)cap,
                                           2 * n_bases, d_seg.as<uint32_t>(), d_seg.as<uint32_t>() + 1, 0, end_bit, st);
   cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(cap + 1), st);
-  CG(d_tmp.ensure(tb > tb2 ? tb : tb2));
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_bcount.as<uint32_t>(), d_bstart.as<uint32_t>(), (int)(table_size + 1), st);
+  CG(d_tmp.ensure(std::max(tb, std::max(tb2, tb3))));
+  if (fresh) CG(cudaMemsetAsync(d_bcount.p, 0, (table_size + 1) * 4, st));
+  ctx->cong_table_size = (long long)table_size;
+  ctx->cong_bcount_clean = false;   // until the whole search has been enqueued
 
   cong_count_kernel<<<n_bases, 256, 0, st>>>(ctx->d_spos4.as<float4>(), ctx->d_sattr.as<float4>(), v, d_base_idx4, d_inv2,
                                              d_valid, n_bases, d_info.as<BaseInfo>(), d_cone.as<float4>());
@@ -504,22 +554,26 @@ int stocs_congruent_enqueue(stocs_b200_ctx* ctx, int n_bases, const int* d_base_
   const uint32_t* codes = d_codes_b.as<uint32_t>();
   const ModelNorm mn = model_norm(ctx);
   const unsigned wide = (unsigned)ctx->num_sms * 8;
-  CG(cudaMemsetAsync(d_head.p, 0xff, table_size * 4, st));   // kNoEntry
+
   cong_prepare_kernel<<<wide, 128, 0, st>>>(codes, d_seg.as<uint32_t>(), d_info.as<BaseInfo>(), n_bases, d_state,
                                             ctx->d_mpos4.as<float4>(), mn, d_pe.as<PEntry>(), d_qe.as<QEntry>(), d_qcell.as<int>(),
-                                            d_head.as<uint32_t>(), d_next.as<uint32_t>(), table_bits, d_cone.as<float4>());
+                                            d_bcount.as<uint32_t>(), d_qslot.as<uint32_t>(), table_bits, d_cone.as<float4>());
+  cub::DeviceScan::ExclusiveSum(d_tmp.p, tb3, d_bcount.as<uint32_t>(), d_bstart.as<uint32_t>(), (int)(table_size + 1), st);
+  cong_scatter_kernel<<<wide, 256, 0, st>>>(d_state, d_qslot.as<uint32_t>(), d_qcell.as<int>(), d_bstart.as<uint32_t>(),
+                                            d_bcount.as<uint32_t>(), d_bucket.as<uint2>());
   CG(cudaMemsetAsync(d_cnt.p, 0, (cap + 1) * 4, st));
-  const unsigned mgrid = (unsigned)ctx->num_sms * 4;
+  const unsigned mgrid = (unsigned)ctx->num_sms * 4;   // one wave of 256-thread blocks at up to 64 registers; one P entry per warp at a time
   cong_match_kernel<false><<<mgrid, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
-                                                  d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, d_cnt.as<uint32_t>(), nullptr, nullptr,
-                                                  d_head.as<uint32_t>(), d_next.as<uint32_t>(), table_bits);
+                                                  d_qe.as<QEntry>(), ctx->eps, d_cnt.as<uint32_t>(), nullptr, nullptr,
+                                                  d_bstart.as<uint32_t>(), d_bucket.as<uint2>(), table_bits);
   cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_cnt.as<uint32_t>(), d_scan.as<uint32_t>(), (int)(cap + 1), st);
   cong_base_offsets_kernel<<<1, 256, 0, st>>>(d_seg.as<uint32_t>(), d_scan.as<uint32_t>(), n_bases, (unsigned long long)capq,
                                               d_state, d_quad_off);
   cong_match_kernel<true><<<mgrid, 256, 0, st>>>(codes, d_seg.as<uint32_t>(), n_bases, d_state, d_pe.as<PEntry>(),
-                                                 d_qe.as<QEntry>(), d_qcell.as<int>(), ctx->eps, nullptr, d_scan.as<uint32_t>(),
-                                                 quads_buf.as<int>(), d_head.as<uint32_t>(), d_next.as<uint32_t>(), table_bits);
+                                                 d_qe.as<QEntry>(), ctx->eps, nullptr, d_scan.as<uint32_t>(),
+                                                 quads_buf.as<int>(), d_bstart.as<uint32_t>(), d_bucket.as<uint2>(), table_bits);
   CG(cudaGetLastError());
+  ctx->cong_bcount_clean = true;
 #undef CG
   return STOCS_OK;
 }

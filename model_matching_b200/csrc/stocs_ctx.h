@@ -85,14 +85,14 @@ enum PoolSlot : int {
   POOL_TOPK_LISTS_AUX = 46,
   // congruent.cu / fit.cu: device scalars of one congruent-set search or pipeline run (StocsPipeState)
   POOL_PIPE_STATE = 47,
-  // congruent.cu: chain heads of the (base, cell) hash of the Q entries
+  // congruent.cu: bucket counters of the (base, cell) hash of the Q entries (zero between searches)
   POOL_CONG_HEAD = 48,
   // scene_index.cu: per-cell counters of the index build, zero between builds (state across calls by design)
   POOL_INDEX_COUNTS = 49,
   // congruent.cu: per-base table of cone directions
   POOL_CONG_CONE = 50,
-  // congruent.cu: chain links of the Q entries
-  POOL_CONG_NEXT = 51,
+  // congruent.cu: bucket number of every Q entry; bucket starts; {Q index, cell} records in bucket order
+  POOL_CONG_NEXT = 51, POOL_CONG_BSTART = 52, POOL_CONG_BUCKET = 53,
   POOL_COUNT = 56
 };
 
@@ -188,6 +188,8 @@ struct stocs_b200_ctx {
 
   // capacities the online stages are enqueued against (entries; grown when a search reports overflow)
   long long cong_cap_codes = 1 << 18, cong_cap_quads = 1 << 21;
+  long long cong_table_size = 0;       // buckets the counters in pool[POOL_CONG_HEAD] were cleared for
+  bool cong_bcount_clean = false;      // ... and whether the last search left them zero
   long long pipe_last_items = 0;       // transforms of the previous pipeline run (sizes the next run's grids)
   StocsPipeState* h_pipe_state = nullptr;   // page-locked landing zone of the state record
   uint32_t* h_index_counts = nullptr;       // page-locked: list lengths of the scene-index build

@@ -1,7 +1,7 @@
-mkdir -p gpurun_out/r2x
-(timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -30) > gpurun_out/r2x/pytest.log
+mkdir -p gpurun_out/r2z
+(timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -30) > gpurun_out/r2z/pytest.log
 P="python profiles/pose_latency.py --trace-child"
-$P > gpurun_out/r2x/plain_child.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r2x/pose_launches.csv $P > gpurun_out/r2x/ncu_child.log 2>&1
-timeout 300 python profiles/pose_latency.py --trace > gpurun_out/r2x/pose_latency.json 2> gpurun_out/r2x/pose_latency.err
-tail -5 gpurun_out/r2x/pytest.log; tail -3 gpurun_out/r2x/ncu_child.log; head -c 400 gpurun_out/r2x/pose_latency.json
+$P > gpurun_out/r2z/plain_child.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r2z/pose_launches.csv $P > gpurun_out/r2z/ncu_child.log 2>&1
+timeout 300 python profiles/pose_latency.py --trace > gpurun_out/r2z/pose_latency.json 2> gpurun_out/r2z/pose_latency.err
+tail -5 gpurun_out/r2z/pytest.log; tail -3 gpurun_out/r2z/ncu_child.log; head -c 400 gpurun_out/r2z/pose_latency.json
