@@ -74,7 +74,10 @@ int stocs_b200_build_scene_cloud(stocs_b200_ctx* ctx, const uint16_t* depth, con
  * upload_scene replaces the scene half of centroid_shift (src/stocs.cpp:948-960) and
  * kdtree_initialize (src/stocs.cpp:966-980): the scene is centred with the reference's sequential
  * fp32 centroid and indexed by a voxel grid (+ the reference kd-tree, used only to break exact
- * distance ties the way kdtree.h:416-428 does).  pixel_rc may be NULL. */
+ * distance ties the way kdtree.h:416-428 does).  pixel_rc may be NULL.
+ * upload_scene returns when the grid index is complete; the kd-tree (host work) is finished on a
+ * host thread and collected by the first scoring launch that follows, or by the next upload_scene /
+ * destroy.  The input buffers are not referenced after the call returns. */
 int stocs_b200_upload_model(stocs_b200_ctx* ctx, const float* pos3, const float* nrm3, int M);
 int stocs_b200_upload_scene(stocs_b200_ctx* ctx, const float* pos3, const float* nrm3,
                             const float* class_probability, const int32_t* pixel_rc, int S);
@@ -195,7 +198,10 @@ int stocs_b200_icp_point_to_plane(stocs_b200_ctx* ctx, const float* src_pos3, in
  * sample n_bases bases -> congruent sets -> at most max_sets transforms per base (when a base has
  * max_sets quads or more: the even spread floor(k * count / max_sets), k = 0..max_sets-1, over its
  * list in set order; see DESIGN.md on quirk 5) -> score -> best.
- * Everything stays on the device; only the summary comes back.  Outputs may be NULL. */
+ * Everything stays on the device and is enqueued without a host round trip -- list lengths, offsets
+ * and counts live in device memory, buffers are sized by capacities the context remembers -- and the
+ * call synchronises once, on the summary below (a frame whose lists outgrow the capacities is run a
+ * second time after growing them; the result is the same). */
 typedef struct stocs_b200_pipeline_result {
   int32_t n_valid_bases;
   int64_t n_congruent_sets;

@@ -178,8 +178,11 @@ struct stocs_b200_ctx {
   std::vector<uint32_t> h_ppf_bin_start, h_ppf_pairs;
 
   // grow-only scratch slots reused by the multi-kernel stages (no cudaMalloc/cudaFree per call).
-  // Slots are named by PoolSlot below.  Rule: a slot is single-stream scratch -- NO slot may hold
-  // state across ABI calls, so stages that never run inside one another may share a number.
+  // Slots are named by PoolSlot below.  Rule: a slot is single-stream scratch -- no slot may hold
+  // state across ABI calls, so stages that never run inside one another may share a number.  Two
+  // deliberate exceptions, each with a number of its own: POOL_INDEX_COUNTS and POOL_CONG_HEAD are
+  // counter arrays that every run leaves ZEROED (tracked by index_counts_clean / cong_bcount_clean),
+  // so that the next run need not clear tens of megabytes first.
   DevBuf pool[POOL_COUNT];
   // scratch
   DevBuf d_T, d_lcp, d_inl, d_work, d_tmp, d_tmp2, d_small;

@@ -179,6 +179,32 @@ def main():
         out.append(f"#   bench.py (CUDA events): kernel_ms {bj['roofline']['kernel_ms']:.3f} of ms_per_step {bj['ms_per_step']:.3f}"
                    f" -> share {bj['roofline']['kernel_ms'] / bj['ms_per_step']:.3f}")
     open(os.path.join(ROOT, f"profiles/{tag}_launch_shares.txt"), "w").write("\n".join(out) + "\n")
+    # ---- one frame of the online path (profiles/pose_latency.py --trace-child under the same ncu pass)
+    pl = os.path.join(d, "pose_launches.csv")
+    if os.path.exists(pl):
+        rows = list(csv.reader(open(pl)))
+        hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+        h = rows[hi]
+        kn, mv = h.index("Kernel Name"), h.index("Metric Value")
+        data = [(r[kn], num(r[mv])) for r in rows[hi + 1:] if len(r) > mv]
+        # the last upload_scene + run_pipeline: from the last pack_attr_kernel on
+        start = max(i for i, (k, _) in enumerate(data) if "pack_attr_kernel" in k)
+        lines = [f"# kernels of ONE frame on the YCB example (|S| = 13 419, |M| = 472, 100 bases, <= 200 sets per base), steady state:",
+                 "# upload_scene (pack_attr .. brick_table) then run_pipeline (sample_bases .. pipe_finalize);",
+                 "# ncu gpu__time_duration.sum per launch, cold caches, serialised -- read as a breakdown, not as the call's latency",
+                 "# (python profiles/pose_latency.py --trace-child; wall-clock figures: bench.py extra.pose_latency)"]
+        tot_u = tot_p = 0.0
+        seen_sample = False
+        for k, v in data[start:]:
+            name = k.split("(")[0].replace("<unnamed>::", "").replace("void ", "")[-60:]
+            if "cub::" in k:
+                name = "cub::" + k.split("cub::")[1].split("<")[0]
+            seen_sample = seen_sample or "sample_bases_kernel" in k
+            if seen_sample: tot_p += v
+            else: tot_u += v
+            lines.append(f"{name:62s} {v / 1e3:9.2f} us")
+        lines.append(f"# upload_scene kernels {tot_u / 1e3:.1f} us, run_pipeline kernels {tot_p / 1e3:.1f} us")
+        open(os.path.join(ROOT, f"profiles/{tag}_pose_frame_launches.txt"), "w").write("\n".join(lines) + "\n")
     if os.path.abspath(bench) != os.path.abspath(os.path.join(ROOT, f"profiles/{tag}_bench_n1.json")):
         shutil.copy(bench, os.path.join(ROOT, f"profiles/{tag}_bench_n1.json"))
     print("\n".join(out[:14]))
