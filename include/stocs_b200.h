@@ -302,6 +302,12 @@ int stocs_b200_last_kernel_ms(stocs_b200_ctx* ctx, float* ms);
  * ran on.  Synchronises with those launches.  reset != 0 restarts the window. */
 int stocs_b200_kernel_ms_stats(stocs_b200_ctx* ctx, int reset, int32_t* n_launches, float* mean_ms,
                                float* max_ms);
+/* Host-only test hook (no context, no GPU): builds the reference kd-tree (kdtree.h:461-538: split at the
+ * middle of the longest box side, leaves of <= 64 points, depth <= 32) over n points exactly as
+ * upload_scene does for the scoring kernel's tie rule, and returns the original index of every point
+ * in leaf order plus the node count.  The build's partition is a branch-free rewrite of the reference's
+ * loop; the CPU tests compare its output with the oracle's literal restatement. */
+int stocs_b200_host_kdtree_order(const float* pos3, int n, int32_t* leaf_order, int32_t* n_nodes);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ SYMBOLS = [
     "stocs_b200_score_lcp_device", "stocs_b200_reduce_best", "stocs_b200_reduce_best_device", "stocs_b200_select_above",
     "stocs_b200_icp_point_to_plane",
     "stocs_b200_run_pipeline", "stocs_b200_run_pipeline_instance", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
-    "stocs_b200_score_counters", "stocs_b200_kernel_ms_stats",
+    "stocs_b200_score_counters", "stocs_b200_kernel_ms_stats", "stocs_b200_host_kdtree_order",
     "stocs_b200_comm_unique_id", "stocs_b200_comm_init", "stocs_b200_comm_destroy", "stocs_b200_shard_range",
     "stocs_b200_score_sharded_device", "stocs_b200_score_sharded",
     "stocs_b200_group_create", "stocs_b200_group_destroy", "stocs_b200_group_size", "stocs_b200_group_ctx",
@@ -95,6 +95,7 @@ def lib():
     L.stocs_b200_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
     L.stocs_b200_score_counters.argtypes = [vp, vp, i64, vp, i32]
     L.stocs_b200_kernel_ms_stats.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
+    L.stocs_b200_host_kdtree_order.argtypes = [vp, i32, vp, C.POINTER(i32)]
     L.stocs_b200_comm_unique_id.argtypes = [vp]
     L.stocs_b200_comm_init.argtypes = [vp, vp, i32, i32]
     L.stocs_b200_comm_destroy.argtypes = [vp]
@@ -130,6 +131,16 @@ def _f32(a, shape=None):
 # stocs_b200_record (include/stocs_b200.h): the 64-byte unit of the multi-GPU all-gather
 RECORD = np.dtype([("lcp", np.float32), ("inliers", np.int32), ("index", np.int64), ("T", np.float32, (12,))])
 assert RECORD.itemsize == 64
+
+
+def host_kdtree_order(pos):
+    """Host-only (no GPU): leaf order and node count of the reference kd-tree as upload_scene builds it."""
+    pos = _f32(pos, (-1, 3))
+    order, nn = np.empty(pos.shape[0], np.int32), C.c_int32(0)
+    rc = lib().stocs_b200_host_kdtree_order(_ptr(pos), pos.shape[0], _ptr(order), C.byref(nn))
+    if rc:
+        raise StocsError("stocs_b200_host_kdtree_order failed: %d" % rc)
+    return order, nn.value
 
 
 def shard_range(H, rank, nranks):

@@ -334,6 +334,15 @@ struct KdPending {
   bool failed = false;
 };
 
+extern "C" int stocs_b200_host_kdtree_order(const float* pos3, int n, int32_t* leaf_order, int32_t* n_nodes) {
+  if (!pos3 || n <= 0 || !leaf_order) return STOCS_E_ARG;
+  KdBuild kb;
+  kb.build(pos3, n);
+  for (int i = 0; i < n; ++i) leaf_order[i] = kb.idx[i];
+  if (n_nodes) *n_nodes = (int32_t)kb.nodes.size();
+  return STOCS_OK;
+}
+
 int stocs_kd_finish(stocs_b200_ctx* ctx, cudaStream_t st, bool upload) {
   KdPending* kp = ctx->kd_pending;
   if (!kp) return STOCS_OK;

@@ -63,6 +63,7 @@ def lib():
     L.orc_est_centred.argtypes = [C.c_void_p, f32p, f32p]
     L.orc_est_kd_query.argtypes = [C.c_void_p, f32p, C.c_int, C.c_float, i32p]
     L.orc_est_kd_num_nodes.argtypes = [C.c_void_p]
+    L.orc_est_kd_order.argtypes = [C.c_void_p, i32p]
     L.orc_est_score.argtypes = [C.c_void_p, f32p, C.c_longlong, f32p, i32p, C.c_int]
     L.orc_est_score_counters.argtypes = [C.c_void_p, f32p, C.c_longlong, C.c_int, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
     L.orc_icp_point_to_plane.restype = C.c_int
@@ -207,6 +208,12 @@ class Estimator:
         s, m = np.empty((self.S, 3), np.float32), np.empty((self.M, 3), np.float32)
         lib().orc_est_centred(self.h, s, m)
         return s, m
+
+    def kd_order(self):
+        """original index of every scene point in the reference kd-tree's leaf order, and the node count"""
+        out = np.empty(self.S, np.int32)
+        lib().orc_est_kd_order(self.h, out)
+        return out, int(lib().orc_est_kd_num_nodes(self.h))
 
     def kd_query(self, q, sqdist):
         q = _f32(q).reshape(-1, 3)

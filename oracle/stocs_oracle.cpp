@@ -969,6 +969,11 @@ void orc_est_kd_query(void* h, const float* q, int n, float sqdist, int* out) {
   for (int i = 0; i < n; ++i) out[i] = e->kd.query(v3(q[3 * i], q[3 * i + 1], q[3 * i + 2]), sqdist);
 }
 int orc_est_kd_num_nodes(void* h) { return (int)((orc::Estimator*)h)->kd.nodes.size(); }
+// original index of every scene point in the kd-tree's leaf order (kdtree.h:522-538 decides it)
+void orc_est_kd_order(void* h, int* out) {
+  auto* e = (orc::Estimator*)h;
+  for (size_t i = 0; i < e->kd.idx.size(); ++i) out[i] = e->kd.idx[i];
+}
 
 // T: H column-major 4x4 matrices.  threads<=1: the reference's single-threaded loop;
 // threads>1: std::thread pool over hypotheses (the "all host cores" CPU baseline).
