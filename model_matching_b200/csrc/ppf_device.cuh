@@ -37,6 +37,53 @@ __device__ __forceinline__ bool ppf_distance_may_exist(const PpfView& v, stocsm:
   return !(f0 <= 5 || f0 / v.tr > v.n1);
 }
 
+// ---- fast exact evaluation of the PPF angles on the device ------------------------------------------
+// The reference's angle features are int(atan2(y, x) * 180 / M_PI) with y = |n x u| >= 0: only the
+// INTEGER part of the degree value enters the key.  stocs_math.h evaluates it the pinned way (binary64
+// polynomial, correctly rounded to binary32, the reference's float * 180 / M_PI): ~150 binary64
+// operations per angle, three angles per candidate, and the samplers evaluate thousands of candidates
+// per base.  An fp32 estimate (CUDA atan2f, <= 2 ulp) lies within 1e-4 degree of the pinned value
+// (2.2e-5 from the pinned value's own two fp32 roundings, 6.5e-5 from the estimate's), so whenever its
+// fractional part is farther than 1e-3 from 0 and 1 -- 998 cases in 1000 -- its floor IS the pinned
+// integer; the other cases, and anything that is not a finite value in [0, 180], take the pinned path.
+__device__ __forceinline__ int deg_atan2_floor(float y, float x) {
+  const float est = atan2f(y, x) * 57.29577951308232f;
+  const float fl = floorf(est);
+  const float fr = est - fl;
+  if (fr > 1e-3f && fr < 0.999f && est > 0.f && est < 180.f) return (int)fl;   // (false for NaN)
+  return (int)stocsm::deg_atan2_ref(y, x);
+}
+
+// ppf_compute (stocs_math.h, src/rgbd.cpp:85-121) with the three angles through deg_atan2_floor: same key
+__device__ __forceinline__ stocsm::Ppf4 ppf_compute_dev(stocsm::V3 p1, stocsm::V3 n1, stocsm::V3 p2, stocsm::V3 n2,
+                                                        int tr_disc, int rot_disc) {
+  using namespace stocsm;
+  const V3 u = sub(p1, p2);
+  const int a1 = (int)(norm(u) * 1000.0f);
+  const int a2 = deg_atan2_floor(norm(cross(n1, u)), dot(n1, u));
+  const int a3 = deg_atan2_floor(norm(cross(n2, u)), dot(n2, u));
+  const int a4 = deg_atan2_floor(norm(cross(n1, n2)), dot(n1, n2));
+  Ppf4 r;
+  r.f[0] = ppf_closest_bin(a1, tr_disc);
+  r.f[1] = ppf_closest_bin(a2, rot_disc);
+  r.f[2] = ppf_closest_bin(a3, rot_disc);
+  r.f[3] = ppf_closest_bin(a4, rot_disc);
+  return r;
+}
+
+// "internal angle < 30 degrees" (src/stocs.cpp:424-442): min(ang, 180 - ang) < 30 with ang the pinned
+// float acos(d) * 180 / M_PI.  The estimate decides whenever it is more than 0.01 degree away from 30
+// and 150 (its error is below 1e-4); NaN (|d| > 1) and the band around the thresholds take the pinned path.
+__device__ __forceinline__ bool internal_angle_below_30(float d) {
+  const float est = acosf(d) * 57.29577951308232f;
+  if (est > 30.01f && est < 149.99f) return false;
+  if (est < 29.99f || est > 150.01f) return true;
+  float ang = stocsm::deg_acos_unqualified_ref(d);
+  const float other = 180.0f - ang;
+  ang = (other < ang) ? other : ang;
+  return ang < 30.0f;
+}
+
 // Enumerates the own bins whose expansion contains key f; calls fn(bin_index) for each valid one
 // (at most 128).  Returns false when the key cannot exist (p1 <= 5).
 template <class Fn>

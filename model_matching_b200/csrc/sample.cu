@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(1024) sample_bases_kernel(SampleArgs a) {
   V3 pb[3], nb[3];
   V3 v_1 = v3(0, 0, 0);
   float pA = 0, pB = 0, pC = 0, denom = 0;
-  const float plane_threshold = 0.015f, min_distance_base = 0.01f, internal_angle_threshold = 30.0f;
+  const float plane_threshold = 0.015f, min_distance_base = 0.01f;
 
   for (int stage = 0; stage < 4; ++stage) {
     if (stage >= 1) {
@@ -109,14 +109,11 @@ __global__ void __launch_bounds__(1024) sample_bases_kernel(SampleArgs a) {
           const int i = c0 + o;
           const float4 p4 = a.spos4[i], n4 = a.sattr[i];
           const V3 p = v3(p4.x, p4.y, p4.z), n = v3(n4.x, n4.y, n4.z);
-          const Ppf4 f = ppf_compute(pb[stage - 1], nb[stage - 1], p, n, a.ppf.tr, a.ppf.rot);
+          const Ppf4 f = ppf_compute_dev(pb[stage - 1], nb[stage - 1], p, n, a.ppf.tr, a.ppf.rot);
           bool zero = !ppf_key_exists(a.ppf, f);
           if (stage == 2) {
             const V3 v_2 = normalized(sub(p, pb[0]));
-            float ang = deg_acos_unqualified_ref(dot(v_1, v_2));
-            const float other = 180.0f - ang;
-            ang = (other < ang) ? other : ang;
-            zero = zero || (ang < internal_angle_threshold);
+            zero = zero || internal_angle_below_30(dot(v_1, v_2));
           } else if (stage == 3) {
             float planar = 10000.0f;
             if (denom != 0) planar = (float)fabs((double)((pA * p.x + pB * p.y) + pC * p.z) - 1.0);

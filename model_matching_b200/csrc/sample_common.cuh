@@ -83,10 +83,7 @@ __device__ inline Plane fit_plane(V3 p1, V3 p2, V3 p3) {
 // predicates of the update passes (reference src/stocs.cpp:424-442 and :456-497); true = zero it
 __device__ inline bool angle_too_small(V3 v_1, V3 p, V3 pb0) {
   const V3 v_2 = normalized(sub(p, pb0));
-  float ang = deg_acos_unqualified_ref(dot(v_1, v_2));
-  const float other = 180.0f - ang;
-  ang = (other < ang) ? other : ang;
-  return ang < 30.0f;
+  return internal_angle_below_30(dot(v_1, v_2));   // ppf_device.cuh: the pinned predicate, decided by an fp32 estimate when safe
 }
 __device__ inline bool off_plane_or_too_close(const Plane& pl, V3 p, V3 pb0, V3 pb1, V3 pb2) {
   float planar = 10000.0f;

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(1024) sample_instance_kernel(InstArgs a) {
     bool al = false;
     if (i < a.S && ((a.alive[t] >> lane) & 1u)) {
       const float4 p4 = a.spos4[i], n4 = a.sattr[i];
-      const Ppf4 f = ppf_compute(pb0, nb0, v3(p4.x, p4.y, p4.z), v3(n4.x, n4.y, n4.z), a.ppf.tr, a.ppf.rot);
+      const Ppf4 f = ppf_compute_dev(pb0, nb0, v3(p4.x, p4.y, p4.z), v3(n4.x, n4.y, n4.z), a.ppf.tr, a.ppf.rot);
       al = ppf_key_exists(a.ppf, f) && i != b1;
       if (al) {
         const int2 px = a.spix[i];
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(1024) sample_instance_kernel(InstArgs a) {
       const float4 p4 = a.spos4[i], n4 = a.sattr[i];
       const V3 p = v3(p4.x, p4.y, p4.z);
       cls = n4.w;
-      const Ppf4 f = ppf_compute(pb1, nb1, p, v3(n4.x, n4.y, n4.z), a.ppf.tr, a.ppf.rot);
+      const Ppf4 f = ppf_compute_dev(pb1, nb1, p, v3(n4.x, n4.y, n4.z), a.ppf.tr, a.ppf.rot);
       al = ppf_key_exists(a.ppf, f) && i != b2 && !angle_too_small(v_1, p, pb0);
     }
     const unsigned word = __ballot_sync(0xffffffffu, al);
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(1024) sample_instance_kernel(InstArgs a) {
       const float4 p4 = a.spos4[i], n4 = a.sattr[i];
       const V3 p = v3(p4.x, p4.y, p4.z);
       cls = n4.w;
-      const Ppf4 f = ppf_compute(pb2, nb2, p, v3(n4.x, n4.y, n4.z), a.ppf.tr, a.ppf.rot);
+      const Ppf4 f = ppf_compute_dev(pb2, nb2, p, v3(n4.x, n4.y, n4.z), a.ppf.tr, a.ppf.rot);
       al = ppf_key_exists(a.ppf, f) && i != b3 && !off_plane_or_too_close(pl, p, pb0, pb1, pb2);
     }
     const unsigned word = __ballot_sync(0xffffffffu, al);
