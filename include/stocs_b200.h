@@ -308,6 +308,14 @@ int stocs_b200_kernel_ms_stats(stocs_b200_ctx* ctx, int reset, int32_t* n_launch
  * in leaf order plus the node count.  The build's partition is a branch-free rewrite of the reference's
  * loop; the CPU tests compare its output with the oracle's literal restatement. */
 int stocs_b200_host_kdtree_order(const float* pos3, int n, int32_t* leaf_order, int32_t* n_nodes);
+/* Test hook: the samplers decide the integer part of a PPF angle (int(atan2(y, x) * 180 / M_PI)) and the
+ * side of 30 degrees an internal angle lies on from fp32 estimates whenever those are safely away from
+ * the deciding thresholds, and by the pinned binary64 evaluation otherwise.  For n pairs (y, x) this
+ * returns the estimate, the pinned value, both integer parts, and -- with d = x -- both forms of the
+ * 30-degree predicate, so that a test can bound the estimate's error and compare the decisions. */
+int stocs_b200_debug_angle_estimates(stocs_b200_ctx* ctx, const float* y, const float* x, int64_t n, float* est_deg,
+                                     double* pinned_deg, int32_t* fast_floor, int32_t* pinned_floor,
+                                     uint8_t* below30_fast, uint8_t* below30_pinned);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ SYMBOLS = [
     "stocs_b200_icp_point_to_plane",
     "stocs_b200_run_pipeline", "stocs_b200_run_pipeline_instance", "stocs_b200_get_counters", "stocs_b200_last_kernel_ms",
     "stocs_b200_score_counters", "stocs_b200_kernel_ms_stats", "stocs_b200_host_kdtree_order",
+    "stocs_b200_debug_angle_estimates",
     "stocs_b200_comm_unique_id", "stocs_b200_comm_init", "stocs_b200_comm_destroy", "stocs_b200_shard_range",
     "stocs_b200_score_sharded_device", "stocs_b200_score_sharded",
     "stocs_b200_group_create", "stocs_b200_group_destroy", "stocs_b200_group_size", "stocs_b200_group_ctx",
@@ -96,6 +97,7 @@ def lib():
     L.stocs_b200_score_counters.argtypes = [vp, vp, i64, vp, i32]
     L.stocs_b200_kernel_ms_stats.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32)]
     L.stocs_b200_host_kdtree_order.argtypes = [vp, i32, vp, C.POINTER(i32)]
+    L.stocs_b200_debug_angle_estimates.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.stocs_b200_comm_unique_id.argtypes = [vp]
     L.stocs_b200_comm_init.argtypes = [vp, vp, i32, i32]
     L.stocs_b200_comm_destroy.argtypes = [vp]
@@ -457,6 +459,19 @@ class Context:
         n, mean, mx = C.c_int32(0), C.c_float(0), C.c_float(0)
         self._check(self._L.stocs_b200_kernel_ms_stats(self.h, int(reset), C.byref(n), C.byref(mean), C.byref(mx)))
         return n.value, mean.value, mx.value
+
+    def debug_angle_estimates(self, y, x):
+        """-> dict: fp32 estimate / pinned value of atan2(y, x) in degrees, both integer parts, and both forms
+        of the 30-degree predicate on d = x (test hook, see include/stocs_b200.h)"""
+        y, x = _f32(y, (-1,)), _f32(x, (-1,))
+        n = y.shape[0]
+        assert x.shape[0] == n
+        est, pin = np.empty(n, np.float32), np.empty(n, np.float64)
+        ff, pf = np.empty(n, np.int32), np.empty(n, np.int32)
+        bf, bp = np.empty(n, np.uint8), np.empty(n, np.uint8)
+        self._check(self._L.stocs_b200_debug_angle_estimates(self.h, _ptr(y), _ptr(x), n, _ptr(est), _ptr(pin), _ptr(ff),
+                                                             _ptr(pf), _ptr(bf), _ptr(bp)))
+        return {"est": est, "pinned": pin, "fast_floor": ff, "pinned_floor": pf, "below30_fast": bf, "below30_pinned": bp}
 
     def last_kernel_ms(self):
         ms = C.c_float(0)

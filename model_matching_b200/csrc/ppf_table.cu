@@ -341,3 +341,55 @@ int stocs_b200_ppf_lookup(stocs_b200_ctx* ctx, const int32_t* key4, int32_t* pai
 }
 
 }  // extern "C"
+
+// ---- test hook: the fp32 angle estimates of ppf_device.cuh beside the pinned evaluation -------------
+namespace {
+__global__ void angle_estimates_kernel(const float* __restrict__ y, const float* __restrict__ x, long long n,
+                                       float* __restrict__ est, double* __restrict__ pinned, int* __restrict__ fast_floor,
+                                       int* __restrict__ pinned_floor, unsigned char* __restrict__ below30_fast,
+                                       unsigned char* __restrict__ below30_pinned) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float yy = y[i], xx = x[i];
+  est[i] = atan2f(yy, xx) * 57.29577951308232f;
+  const double p = stocsm::deg_atan2_ref(yy, xx);
+  pinned[i] = p;
+  fast_floor[i] = deg_atan2_floor(yy, xx);
+  pinned_floor[i] = (int)p;
+  // the 30-degree predicate on d = x (y unused): fast form and the pinned statement of src/stocs.cpp:428-436
+  below30_fast[i] = internal_angle_below_30(xx) ? 1 : 0;
+  float ang = stocsm::deg_acos_unqualified_ref(xx);
+  const float other = 180.0f - ang;
+  ang = (other < ang) ? other : ang;
+  below30_pinned[i] = (ang < 30.0f) ? 1 : 0;
+}
+}  // namespace
+
+extern "C" int stocs_b200_debug_angle_estimates(stocs_b200_ctx* ctx, const float* y, const float* x, int64_t n, float* est_deg,
+                                                double* pinned_deg, int32_t* fast_floor, int32_t* pinned_floor,
+                                                uint8_t* below30_fast, uint8_t* below30_pinned) {
+  if (!ctx) return STOCS_E_ARG;
+  if (n <= 0 || !y || !x || !est_deg || !pinned_deg || !fast_floor || !pinned_floor || !below30_fast || !below30_pinned)
+    STOCS_FAIL(ctx, STOCS_E_ARG, "debug_angle_estimates: bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  DevBuf in, out;
+  auto fail = [&](const char* what) { in.release(); out.release(); ctx->err = what; return STOCS_E_CUDA; };
+  if (in.ensure((size_t)n * 8) != cudaSuccess || out.ensure((size_t)n * (4 + 8 + 4 + 4 + 1 + 1) + 64) != cudaSuccess) return fail("debug_angle_estimates: allocation failed");
+  float* d_y = in.as<float>(); float* d_x = d_y + n;
+  double* d_p = out.as<double>(); float* d_e = (float*)(d_p + n); int* d_ff = (int*)(d_e + n); int* d_pf = d_ff + n;
+  unsigned char* d_bf = (unsigned char*)(d_pf + n); unsigned char* d_bp = d_bf + n;
+  bool ok = cudaMemcpyAsync(d_y, y, (size_t)n * 4, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+            cudaMemcpyAsync(d_x, x, (size_t)n * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+  if (ok) angle_estimates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_y, d_x, n, d_e, d_p, d_ff, d_pf, d_bf, d_bp);
+  ok = ok && cudaMemcpyAsync(est_deg, d_e, (size_t)n * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+       cudaMemcpyAsync(pinned_deg, d_p, (size_t)n * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+       cudaMemcpyAsync(fast_floor, d_ff, (size_t)n * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+       cudaMemcpyAsync(pinned_floor, d_pf, (size_t)n * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+       cudaMemcpyAsync(below30_fast, d_bf, (size_t)n, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+       cudaMemcpyAsync(below30_pinned, d_bp, (size_t)n, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+       cudaStreamSynchronize(st) == cudaSuccess;
+  if (!ok) return fail("debug_angle_estimates: CUDA call failed");
+  in.release(); out.release();
+  return STOCS_OK;
+}

@@ -1,3 +1,3 @@
-mkdir -p gpurun_out/r2fb3
-timeout 900 python bench.py --steps 200 --warmup 3 > gpurun_out/r2fb3/bench_n1.json 2> gpurun_out/r2fb3/bench_n1.err
-tail -2 gpurun_out/r2fb3/bench_n1.err; head -c 300 gpurun_out/r2fb3/bench_n1.json; echo
+mkdir -p gpurun_out/r2ang
+(timeout 600 python -m pytest tests/test_angle_estimates_gpu.py tests/test_pipeline_gpu.py -m gpu -x -q 2>&1 | tail -15) > gpurun_out/r2ang/pytest.log
+tail -6 gpurun_out/r2ang/pytest.log
