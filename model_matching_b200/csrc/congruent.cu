@@ -216,7 +216,7 @@ struct PEntry { float ix, iy, iz; int cell; int nbin; int base; };   // invPoint
 // Q entries are bucketed by (base, position cell) in one table of `table_size` (a power of two, at least
 // twice the code capacity) buckets; a bucket may mix entries of different bases and cells, told apart on the read
 constexpr uint32_t kNoEntry = 0xffffffffu;
-__device__ __forceinline__ uint32_t chain_slot(int b, int cell, int table_bits) {
+__device__ __forceinline__ uint32_t bucket_of(int b, int cell, int table_bits) {
   return (((uint32_t)cell * 2654435761u) ^ ((uint32_t)b * 0x9E3779B1u + 0x7F4A7C15u)) >> (32 - table_bits);
 }
 struct QEntry { float qx, qy, qz; uint32_t mask[11]; };          // queryQ (model frame), cone bins
@@ -334,7 +334,7 @@ __global__ void cong_prepare_kernel(const uint32_t* __restrict__ codes, const ui
     if (live && ql == 0) {
       qe[e - totalP] = o;
       qcell[e - totalP] = qc;
-      const uint32_t h = chain_slot(b, qc, table_bits);
+      const uint32_t h = bucket_of(b, qc, table_bits);
       qslot[e - totalP] = h;
       atomicAdd(&bcount[h], 1u);
     }
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256) cong_match_kernel(const uint32_t* __restr
     const PEntry p = pe[wid];
     if (p.nbin < 0 || p.nbin >= 343) { if (!WRITE && lane == 0) counts[wid] = 0u; continue; }  // std::array::at would throw
     const uint32_t q0 = seg_off[n_bases + p.base] - totalP, q1 = seg_off[n_bases + p.base + 1] - totalP;
-    const uint32_t h = chain_slot(p.base, p.cell, table_bits);
+    const uint32_t h = bucket_of(p.base, p.cell, table_bits);
     const uint32_t r0 = bstart[h], r1 = bstart[h + 1];
     const uint32_t pcell = (uint32_t)p.cell;
     // a record of the bucket is a partner when it is a Q entry of this base in this cell (the bucket may
