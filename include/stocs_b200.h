@@ -60,7 +60,9 @@ int stocs_b200_backproject(stocs_b200_ctx* ctx, const uint16_t* depth, const uin
  * (r = 2*voxel_size + 0.005, more than 10 neighbours) -> per centroid: 0 < z <= 2, re-projection to
  * (row, col), class probability (uint16 / 10000) >= class_threshold, valid depth normal.
  * class_prob: H*W uint16; edge: H*W uint8 or NULL (treated as 0).  Outputs hold up to cap points
- * (rgb3, edge_p may be NULL); *n_out = number of points (STOCS_E_CAPACITY if > cap). */
+ * (rgb3, edge_p may be NULL); *n_out = number of points (STOCS_E_CAPACITY if > cap).  Entries of
+ * the output arrays beyond *n_out (up to cap) may be overwritten: the call fetches its results before
+ * it knows their count, with the previous frame's as the estimate. */
 int stocs_b200_build_scene_cloud(stocs_b200_ctx* ctx, const uint16_t* depth, const uint8_t* bgr,
                                  const uint16_t* class_prob, const uint8_t* edge, int W, int H, float fx,
                                  float cx, float fy, float cy, float depth_scale, float voxel_size,

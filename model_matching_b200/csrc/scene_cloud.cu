@@ -59,24 +59,29 @@ __global__ void voxel_keys_kernel(const float* __restrict__ xyz, const uint16_t*
   if (valid) atomicAdd(n_valid, 1);
 }
 
-__global__ void head_flags_kernel(const unsigned long long* __restrict__ keys, int n_valid, int* __restrict__ flags) {
+// (list lengths -- valid pixels, voxels -- live in device memory: the host enqueues every stage with
+// grids sized by the pixel count and reads the lengths back once, with the result)
+__global__ void head_flags_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ n_valid_p, int* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_valid) return;
+  if (i >= *n_valid_p) return;
   flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
 __global__ void voxel_starts_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ flags,
-                                    const int* __restrict__ scan, int n_valid, int* __restrict__ starts,
-                                    unsigned long long* __restrict__ ukeys) {
+                                    const int* __restrict__ scan, const int* __restrict__ n_valid_p, int* __restrict__ starts,
+                                    unsigned long long* __restrict__ ukeys, int* __restrict__ nvox_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_valid = *n_valid_p;
+  if (i == 0) *nvox_out = scan[n_valid];   // flags are zero from n_valid on: the exclusive sum there is the voxel count
   if (i >= n_valid) return;
   if (flags[i]) { starts[scan[i]] = i; ukeys[scan[i]] = keys[i]; }
 }
 
 __global__ void centroid_kernel(const float* __restrict__ xyz, const uint16_t* __restrict__ depth, const int* __restrict__ idx,
-                                const int* __restrict__ starts, int nvox, int n_valid, const int* __restrict__ first_zero,
-                                const int* __restrict__ n_zero, float4* __restrict__ cent) {
+                                const int* __restrict__ starts, const int* __restrict__ nvox_p, const int* __restrict__ n_valid_p,
+                                const int* __restrict__ first_zero, const int* __restrict__ n_zero, float4* __restrict__ cent) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nvox = *nvox_p, n_valid = *n_valid_p;
   if (v >= nvox) return;
   const int s = starts[v], e = (v + 1 < nvox) ? starts[v + 1] : n_valid;
   float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -91,9 +96,10 @@ __global__ void centroid_kernel(const float* __restrict__ xyz, const uint16_t* _
   cent[v] = make_float4(sx / c, sy / c, sz / c, 0.f);
 }
 
-__global__ void outlier_kernel(const float4* __restrict__ cent, const unsigned long long* __restrict__ ukeys, int nvox,
-                               float r2, int reach, int min_neighbors, int* __restrict__ keep) {
+__global__ void outlier_kernel(const float4* __restrict__ cent, const unsigned long long* __restrict__ ukeys,
+                               const int* __restrict__ nvox_p, float r2, int reach, int min_neighbors, int* __restrict__ keep) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nvox = *nvox_p;
   if (v >= nvox) return;
   const float4 p = cent[v];
   const unsigned long long key = ukeys[v];
@@ -123,7 +129,7 @@ __global__ void outlier_kernel(const float4* __restrict__ cent, const unsigned l
 }
 
 struct FilterArgs {
-  const float4* cent; const int* keep; int nvox;
+  const float4* cent; const int* keep; const int* nvox_p; int out_cap;
   const float* xyz; const uint16_t* depth; const uint8_t* bgr; const uint16_t* prob; const uint8_t* edge;
   int W, H; float fx, cx, fy, cy; float class_threshold;
   int* flags;      // out: 1 = emitted
@@ -134,7 +140,7 @@ struct FilterArgs {
 // src/rgbd.cpp:238-279 per centroid
 __global__ void final_filter_kernel(FilterArgs a) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= a.nvox) return;
+  if (v >= *a.nvox_p) return;
   int ok = 0;
   if (a.keep[v]) {
     const float4 p = a.cent[v];
@@ -162,8 +168,9 @@ __global__ void final_filter_kernel(FilterArgs a) {
 __global__ void emit_kernel(FilterArgs a, const int* __restrict__ scan, float* __restrict__ pos3, float* __restrict__ nrm3,
                             float* __restrict__ rgb3, int* __restrict__ pix2, float* __restrict__ cls, float* __restrict__ edgep) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= a.nvox || !a.flags[v]) return;
+  if (v >= *a.nvox_p || !a.flags[v]) return;
   const int o = scan[v];
+  if (o >= a.out_cap) return;   // more points than the caller's buffers hold: reported after the read-back
   const float4 p = a.cent[v];
   const int row = a.rc[2 * (size_t)v], col = a.rc[2 * (size_t)v + 1];
   pos3[3 * (size_t)o] = p.x; pos3[3 * (size_t)o + 1] = p.y; pos3[3 * (size_t)o + 2] = p.z;
@@ -237,71 +244,82 @@ extern "C" int stocs_b200_build_scene_cloud(stocs_b200_ctx* ctx, const uint16_t*
   SC(d_tmp.ensure(tb));
   cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_keys_a.as<unsigned long long>(), d_keys_b.as<unsigned long long>(), d_idx_a.as<int>(),
                                   d_idx_b.as<int>(), n, 0, 64, st);
-  int hcnt[3];
-  SC(cudaMemcpyAsync(hcnt, d_cnt, 12, cudaMemcpyDeviceToHost, st));
-  SC(cudaStreamSynchronize(st));
-  const int n_valid = hcnt[2];
+  // ---- every later stage is enqueued against the pixel count n; the list lengths stay on the device
+  int* d_nvalid = d_cnt + 2;
+  int* d_nvox = d_cnt + 3;
   *n_out = 0;
-  if (n_valid == 0) { cleanup(); return STOCS_OK; }
   const unsigned long long* keys = d_keys_b.as<unsigned long long>();
   const int* idx = d_idx_b.as<int>();
-  const int nvb = (n_valid + 255) / 256;
-  SC(d_flags.ensure((size_t)(n_valid + 1) * 4)); SC(d_scan.ensure((size_t)(n_valid + 1) * 4));
-  SC(cudaMemsetAsync(d_flags.p, 0, (size_t)(n_valid + 1) * 4, st));
-  head_flags_kernel<<<nvb, 256, 0, st>>>(keys, n_valid, d_flags.as<int>());
+  SC(d_flags.ensure((size_t)(n + 1) * 4)); SC(d_scan.ensure((size_t)(n + 1) * 4));
+  SC(d_starts.ensure((size_t)n * 4)); SC(d_ukeys.ensure((size_t)n * 8)); SC(d_cent.ensure((size_t)n * 16));
+  SC(d_keep.ensure((size_t)(n + 1) * 4)); SC(d_nrm.ensure((size_t)n * 12)); SC(d_rc.ensure((size_t)n * 8));
+  SC(cudaMemsetAsync(d_flags.p, 0, (size_t)(n + 1) * 4, st));
+  head_flags_kernel<<<nb, 256, 0, st>>>(keys, d_nvalid, d_flags.as<int>());
   size_t tb2 = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_flags.as<int>(), d_scan.as<int>(), n_valid + 1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_flags.as<int>(), d_scan.as<int>(), n + 1, st);
   SC(d_tmp.ensure(tb2));
-  cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_flags.as<int>(), d_scan.as<int>(), n_valid + 1, st);
-  int nvox = 0;
-  SC(cudaMemcpyAsync(&nvox, d_scan.as<int>() + n_valid, 4, cudaMemcpyDeviceToHost, st));
-  SC(cudaStreamSynchronize(st));
-  SC(d_starts.ensure((size_t)nvox * 4)); SC(d_ukeys.ensure((size_t)nvox * 8)); SC(d_cent.ensure((size_t)nvox * 16));
-  SC(d_keep.ensure((size_t)(nvox + 1) * 4)); SC(d_nrm.ensure((size_t)nvox * 12)); SC(d_rc.ensure((size_t)nvox * 8));
-  voxel_starts_kernel<<<nvb, 256, 0, st>>>(keys, d_flags.as<int>(), d_scan.as<int>(), n_valid, d_starts.as<int>(),
-                                           d_ukeys.as<unsigned long long>());
-  const int nxb = (nvox + 127) / 128;
-  centroid_kernel<<<nxb, 128, 0, st>>>(d_xyz.as<float>(), d_depth.as<uint16_t>(), idx, d_starts.as<int>(), nvox, n_valid, d_cnt,
+  cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_flags.as<int>(), d_scan.as<int>(), n + 1, st);
+  voxel_starts_kernel<<<nb, 256, 0, st>>>(keys, d_flags.as<int>(), d_scan.as<int>(), d_nvalid, d_starts.as<int>(),
+                                          d_ukeys.as<unsigned long long>(), d_nvox);
+  const int nxb = (n + 127) / 128;
+  centroid_kernel<<<nxb, 128, 0, st>>>(d_xyz.as<float>(), d_depth.as<uint16_t>(), idx, d_starts.as<int>(), d_nvox, d_nvalid, d_cnt,
                                        d_cnt + 1, d_cent.as<float4>());
   // src/rgbd.cpp:234: setRadiusSearch(double(2*voxel_size) + 0.005); the search compares squared
   // distances with float(radius * radius) (pcl::KdTreeFLANN::radiusSearch)
   const double radius = (double)(2 * voxel_size) + 0.005;
   const float r2 = (float)(radius * radius);
   const int reach = (int)std::ceil(radius / (double)voxel_size) + 1;
-  outlier_kernel<<<nxb, 128, 0, st>>>(d_cent.as<float4>(), d_ukeys.as<unsigned long long>(), nvox, r2, reach, 10, d_keep.as<int>());
-  // flags / scan buffers are reused for the emit compaction (nvox <= n_valid)
+  outlier_kernel<<<nxb, 128, 0, st>>>(d_cent.as<float4>(), d_ukeys.as<unsigned long long>(), d_nvox, r2, reach, 10, d_keep.as<int>());
+  // flags / scan buffers are reused for the emit compaction (voxels <= valid pixels <= n)
+  const long long out_cap = cap < (long long)n ? cap : (long long)n;
   FilterArgs fa;
-  fa.cent = d_cent.as<float4>(); fa.keep = d_keep.as<int>(); fa.nvox = nvox; fa.xyz = d_xyz.as<float>(); fa.depth = d_depth.as<uint16_t>();
+  fa.cent = d_cent.as<float4>(); fa.keep = d_keep.as<int>(); fa.nvox_p = d_nvox; fa.out_cap = (int)out_cap;
+  fa.xyz = d_xyz.as<float>(); fa.depth = d_depth.as<uint16_t>();
   fa.bgr = bgr ? d_bgr.as<uint8_t>() : nullptr; fa.prob = d_prob.as<uint16_t>(); fa.edge = edge ? d_edge.as<uint8_t>() : nullptr;
   fa.W = W; fa.H = H; fa.fx = fx; fa.cx = cx; fa.fy = fy; fa.cy = cy; fa.class_threshold = class_threshold;
   fa.flags = d_flags.as<int>(); fa.nrm = d_nrm.as<float>(); fa.rc = d_rc.as<int>();
-  SC(cudaMemsetAsync(d_flags.p, 0, (size_t)(nvox + 1) * 4, st));
+  SC(cudaMemsetAsync(d_flags.p, 0, (size_t)(n + 1) * 4, st));
   final_filter_kernel<<<nxb, 128, 0, st>>>(fa);
-  cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_flags.as<int>(), d_scan.as<int>(), nvox + 1, st);
-  int n_emit = 0;
-  SC(cudaMemcpyAsync(&n_emit, d_scan.as<int>() + nvox, 4, cudaMemcpyDeviceToHost, st));
+  cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_flags.as<int>(), d_scan.as<int>(), n + 1, st);   // scan[n] = emitted points
+  // out: pos3 | nrm3 | rgb3 | pix2 | cls | edge, each with room for out_cap points
+  const size_t oc = (size_t)(out_cap > 0 ? out_cap : 1);
+  SC(d_out.ensure(oc * (12 + 12 + 12 + 8 + 4 + 4)));
+  float* o_pos = d_out.as<float>();
+  float* o_nrm = o_pos + 3 * oc;
+  float* o_rgb = o_nrm + 3 * oc;
+  int* o_pix = (int*)(o_rgb + 3 * oc);
+  float* o_cls = (float*)(o_pix + 2 * oc);
+  float* o_edge = o_cls + oc;
+  emit_kernel<<<nxb, 128, 0, st>>>(fa, d_scan.as<int>(), o_pos, o_nrm, o_rgb, o_pix, o_cls, o_edge);
+  SC(cudaGetLastError());
+  // read-back: the two lengths, and -- in the same queue, before anything is known -- as many points as
+  // the previous frame's voxel count (an upper bound of what it emitted); a frame that emits more
+  // fetches the rest afterwards
+  uint32_t* h_len = ctx->h_index_counts + 8;   // page-locked: {voxels, emitted}
+  SC(cudaMemcpyAsync(&h_len[0], d_nvox, 4, cudaMemcpyDeviceToHost, st));
+  SC(cudaMemcpyAsync(&h_len[1], d_scan.as<int>() + n, 4, cudaMemcpyDeviceToHost, st));
+  const bool have_out = pos3 && nrm3 && pixel_rc && class_p;
+  long long guess = have_out ? ctx->counters[5] : 0;
+  if (guess > out_cap) guess = out_cap;
+  auto fetch = [&](long long from, long long to) -> cudaError_t {
+    const size_t c = (size_t)(to - from);
+    cudaError_t e = cudaMemcpyAsync(pos3 + 3 * from, o_pos + 3 * from, c * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nrm3 + 3 * from, o_nrm + 3 * from, c * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rgb3) e = cudaMemcpyAsync(rgb3 + 3 * from, o_rgb + 3 * from, c * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pixel_rc + 2 * from, o_pix + 2 * from, c * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(class_p + from, o_cls + from, c * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && edge_p) e = cudaMemcpyAsync(edge_p + from, o_edge + from, c * 4, cudaMemcpyDeviceToHost, st);
+    return e;
+  };
+  if (guess > 0) SC(fetch(0, guess));
   SC(cudaStreamSynchronize(st));
+  const long long nvox = (long long)h_len[0], n_emit = (long long)h_len[1];
   *n_out = n_emit;
   ctx->counters[5] = nvox;
   if (n_emit > cap) { cleanup(); STOCS_FAIL(ctx, STOCS_E_CAPACITY, "build_scene_cloud: output capacity too small"); }
-  if (n_emit > 0) {
-    if (!pos3 || !nrm3 || !pixel_rc || !class_p) { cleanup(); STOCS_FAIL(ctx, STOCS_E_ARG, "build_scene_cloud: output pointer is NULL"); }
-    // out: pos3 | nrm3 | rgb3 | pix2 | cls | edge
-    SC(d_out.ensure((size_t)n_emit * (12 + 12 + 12 + 8 + 4 + 4)));
-    float* o_pos = d_out.as<float>();
-    float* o_nrm = o_pos + 3 * (size_t)n_emit;
-    float* o_rgb = o_nrm + 3 * (size_t)n_emit;
-    int* o_pix = (int*)(o_rgb + 3 * (size_t)n_emit);
-    float* o_cls = (float*)(o_pix + 2 * (size_t)n_emit);
-    float* o_edge = o_cls + n_emit;
-    emit_kernel<<<nxb, 128, 0, st>>>(fa, d_scan.as<int>(), o_pos, o_nrm, o_rgb, o_pix, o_cls, o_edge);
-    SC(cudaGetLastError());
-    SC(cudaMemcpyAsync(pos3, o_pos, (size_t)n_emit * 12, cudaMemcpyDeviceToHost, st));
-    SC(cudaMemcpyAsync(nrm3, o_nrm, (size_t)n_emit * 12, cudaMemcpyDeviceToHost, st));
-    if (rgb3) SC(cudaMemcpyAsync(rgb3, o_rgb, (size_t)n_emit * 12, cudaMemcpyDeviceToHost, st));
-    SC(cudaMemcpyAsync(pixel_rc, o_pix, (size_t)n_emit * 8, cudaMemcpyDeviceToHost, st));
-    SC(cudaMemcpyAsync(class_p, o_cls, (size_t)n_emit * 4, cudaMemcpyDeviceToHost, st));
-    if (edge_p) SC(cudaMemcpyAsync(edge_p, o_edge, (size_t)n_emit * 4, cudaMemcpyDeviceToHost, st));
+  if (n_emit > 0 && !have_out) { cleanup(); STOCS_FAIL(ctx, STOCS_E_ARG, "build_scene_cloud: output pointer is NULL"); }
+  if (n_emit > guess) {
+    SC(fetch(guess, n_emit));
     SC(cudaStreamSynchronize(st));
   }
 #undef SC
